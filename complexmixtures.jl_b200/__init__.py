@@ -1,0 +1,34 @@
+"""complexmixtures.jl_b200 -- B200-native minimum-distance engine behind ComplexMixtures.jl's API.
+
+The directory name carries a dot (it is the name the build contract fixes), so it cannot be
+imported with a plain ``import``; ``cmx_b200.py`` at the repository root loads it under the
+module name ``cmx_b200``.  Layout:
+
+  csrc/            CUDA kernels (sm_100a) + the C-ABI (include/cmx_b200.h) -> libcmx_b200.so
+  engine.py        ctypes binding of the C-ABI (what the Julia shim does with ccall)
+  mddf.py          mddf() / coordination_number() drivers (mirror of src/mddf.jl)
+  options.py, selection.py, trajectory.py, results.py, contributions.py   host-side mirrors
+  synthetic.py     generators of the synthetic benchmark systems named in BASELINE.json
+"""
+from .options import Options
+from .selection import AtomSelection, SoluteGroup, SolventGroup
+from .trajectory import (ArrayTrajectory, NamdDCD, PDBTraj, Trajectory, make_trajectory,
+                         trajectory_metadata, cell_from_lengths_angles)
+from .results import (Result, finalresults, load, save, setbin, shellradius, sphericalshellvolume)
+from .contributions import contributions, coordination_number_of
+
+__all__ = ["Options", "AtomSelection", "SoluteGroup", "SolventGroup", "Trajectory", "NamdDCD", "PDBTraj",
+           "ArrayTrajectory", "make_trajectory", "trajectory_metadata", "Result", "finalresults", "load", "save",
+           "setbin", "shellradius", "sphericalshellvolume", "contributions", "coordination_number_of",
+           "cell_from_lengths_angles"]
+
+
+def __getattr__(name):
+    # engine-backed entry points are imported lazily so that the pure-host modules (and the
+    # CPU test-suite) work on machines where the CUDA library has not been built
+    if name in ("mddf", "coordination_number", "Engine", "engine", "synthetic"):
+        import importlib
+        mod = importlib.import_module(f"{__name__}.mddf" if name in ("mddf", "coordination_number") else
+                                      f"{__name__}.engine" if name in ("Engine", "engine") else f"{__name__}.synthetic")
+        return mod if name in ("engine", "synthetic") else getattr(mod, name)
+    raise AttributeError(name)
