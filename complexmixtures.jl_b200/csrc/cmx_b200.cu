@@ -1,0 +1,711 @@
+// cmx_b200.cu -- C-ABI (include/cmx_b200.h) and host-side frame pipeline of libcmx_b200.so.
+//
+// Host responsibilities restated from the reference's chunk task (src/mddf.jl:288-337):
+// per-handle state (build_particle_system / Buffer / Result -> cmx_create), frame staging
+// (pinned ring, async H2D), per-frame kernel sequence (mddf_frame!, src/mddf.jl:361-429),
+// frame-weight handling and the final counters (sum!, src/results.jl:629-649).
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cmx_b200.h"
+#include "cmx_kernels.cuh"
+#include "cmx_pairs.cuh"
+
+using namespace cmx;
+
+namespace {
+
+std::string g_create_error;
+
+struct Slot {
+    float *h_in = nullptr;   // pinned: solute xyz then solvent xyz (autocorrelation: solvent only)
+    float *d_in = nullptr;
+    cudaEvent_t h2d_done = nullptr, consumed = nullptr;
+    bool in_flight = false;
+};
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t want, bool zero = false) {
+        if (want <= n && p) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; n = 0; }
+        size_t cap = want + want / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        n = cap;
+        if (zero) return cudaMemset(p, 0, cap * sizeof(T));
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct cmx_handle {
+    cmx_config cfg{};
+    std::string err;
+    int device = 0;
+    int path = 1;            // 1 grid path, 2 molecule-pair path
+    int G = 8;               // lanes per solvent molecule in the search kernel
+    int nbins = 0;
+    size_t ns_atoms = 0, nv_atoms = 0, in_floats = 0;
+    double cut_eff = 0;
+    int Kdiv = 4;
+    double side = 0, cside = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    std::vector<Slot> ring;
+    int next_slot = 0, acquired = -1;
+    // static device data
+    Prob P{};
+    DevBuf<int> d_sol_off, d_sol_ids, d_solv_off, d_solv_ids;
+    DevBuf<u64> d_cnt;              // integer run accumulators (contiguous block)
+    DevBuf<double> d_acc;           // fp64 accumulators, only once the frame weight changes
+    size_t cnt_len = 0;
+    bool acc_used = false;
+    // per-frame scratch (grid path)
+    DevBuf<int> d_cell_count, d_cell_start;
+    DevBuf<float4> d_sorted;
+    DevBuf<u64> d_occ;
+    DevBuf<unsigned char> d_cdist, d_bulk_flags;
+    DevBuf<MdRec> d_list, d_rand_list, d_list_all;
+    DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
+    DevBuf<u64> d_def_real, d_def_rand;
+    DevBuf<int> d_scalars;          // [0] work_count, [1] rand_work_count, [2] def_real, [3] def_rand, [4] n_bulk, [5] rmax bits, [6..7] spare
+    DevBuf<u64> d_stats;            // [0] pair_evals, [1] deferred total
+    DevBuf<unsigned char> d_cub_tmp;
+    // pair path scratch
+    PairScratch pairs;
+    int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
+    float rmax_bound = 0.f;
+    // bookkeeping
+    double cur_weight = 1.0; bool have_weight = false;
+    double volume_total = 0, sum_weights = 0;
+    cmx_stats stats{};
+    bool count_pairs = false, profile = false;
+    cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool ev_first_set = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    int64_t last_frame = -1;
+    Geom last_g{};
+    const float *last_dsol = nullptr, *last_dsolv = nullptr;
+    int num_sms = 148;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return CMX_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+int fail(cmx_handle *h, int code, const std::string &msg) { h->err = msg; return code; }
+
+// molecule-pair path (cmx_pairs_host.inl)
+int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent, uint32_t frame, const Geom &g);
+int pairs_create(cmx_handle *h);
+void pairs_release(cmx_handle *h);
+PairGeom make_pair_geom(cmx_handle *h, const Geom &g);
+
+// ---- host Philox (same counter convention as the device) for ref_solutes -------------------
+void philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+int ref_solute_host(const cmx_handle *h, uint32_t frame, uint32_t s) {
+    uint32_t o[4];
+    philox_host(0xffffffffu, s, frame, 2u, h->P.seed_lo, h->P.seed_hi, o);
+    return (int)(((uint64_t)o[0] * (uint64_t)h->cfg.solute_nmols) >> 32);
+}
+
+// ---- geometry ---------------------------------------------------------------------------------
+int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
+    std::memset(&g, 0, sizeof g);
+    std::memcpy(g.m, cell, sizeof(double) * 9);
+    const double *a = cell, *b = cell + 3, *c = cell + 6;
+    double mind = std::min(std::fabs(a[0]), std::min(std::fabs(b[1]), std::fabs(c[2])));
+    double tol = 1e-10 * mind;   // convert_unitcell, src/Trajectory.jl:72-77
+    g.ortho = std::fabs(a[1]) < tol && std::fabs(a[2]) < tol && std::fabs(b[0]) < tol && std::fabs(b[2]) < tol &&
+              std::fabs(c[0]) < tol && std::fabs(c[1]) < tol;
+    double bxc[3] = {b[1] * c[2] - b[2] * c[1], b[2] * c[0] - b[0] * c[2], b[0] * c[1] - b[1] * c[0]};
+    double cxa[3] = {c[1] * a[2] - c[2] * a[1], c[2] * a[0] - c[0] * a[2], c[0] * a[1] - c[1] * a[0]};
+    double axb[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    double det = axb[0] * c[0] + axb[1] * c[1] + axb[2] * c[2];
+    if (!(std::fabs(det) > 0)) return fail(h, CMX_ERR_CELL, "singular unit cell");
+    for (int k = 0; k < 3; ++k) {
+        g.inv[0 + 3 * k] = bxc[k] / det; g.inv[1 + 3 * k] = cxa[k] / det; g.inv[2 + 3 * k] = axb[k] / det;
+    }
+    double w[3] = {std::fabs(det) / std::sqrt(bxc[0] * bxc[0] + bxc[1] * bxc[1] + bxc[2] * bxc[2]),
+                   std::fabs(det) / std::sqrt(cxa[0] * cxa[0] + cxa[1] * cxa[1] + cxa[2] * cxa[2]),
+                   std::fabs(det) / std::sqrt(axb[0] * axb[0] + axb[1] * axb[1] + axb[2] * axb[2])};
+    for (int k = 0; k < 3; ++k)
+        if (w[k] < 2.0 * h->cut_eff) {
+            char buf[200];
+            std::snprintf(buf, sizeof buf, "unit cell too small for the cutoff: perpendicular width %.4f < 2*%.4f "
+                          "(CellListMap requires sides > 2*cutoff)", w[k], h->cut_eff);
+            return fail(h, CMX_ERR_CELL, buf);
+        }
+    // AABB of the primary cell
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int n = 0; n < 8; ++n)
+        for (int k = 0; k < 3; ++k) {
+            double v = ((n & 1) ? a[k] : 0) + ((n & 2) ? b[k] : 0) + ((n & 4) ? c[k] : 0);
+            lo[k] = std::min(lo[k], v); hi[k] = std::max(hi[k], v);
+        }
+    double maxabs = 0;
+    double margin0 = h->cut_eff + 0.1;
+    for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, 0.5 * (hi[k] - lo[k]) + margin0);
+    int ex; std::frexp(maxabs, &ex);                 // maxabs = f * 2^ex, f in [0.5,1)
+    double ulp = std::ldexp(1.0, ex - 24);
+    double tau = std::max(16.0 * ulp, 2e-5);
+    g.tau = (float)tau; g.cut = (float)h->cut_eff;
+    g.cut_lo = (float)(h->cut_eff - tau); g.cut_hi = (float)(h->cut_eff + tau);
+    g.search2 = (float)((h->cut_eff + tau) * (h->cut_eff + tau) * (1.0 + 1e-6));
+    g.tol_d2 = (float)(2.0 * h->cut_eff * tau + tau * tau);
+    g.cutd = h->cut_eff;
+    double margin = h->cut_eff + tau + 0.05;
+    for (int k = 0; k < 3; ++k) {
+        g.elo[k] = lo[k] - margin; g.ehi[k] = hi[k] + margin; g.ctr[k] = 0.5 * (lo[k] + hi[k]);
+        g.gmin[k] = (float)(g.elo[k] - g.ctr[k]);
+    }
+    g.side = (float)h->side; g.inv_side = (float)(1.0 / h->side);
+    g.K = h->Kdiv; g.nrows_tab = (2 * g.K + 1) * (2 * g.K + 1);
+    g.nx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->side) + 1;
+    g.ny = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->side) + 1;
+    g.nz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->side) + 1;
+    g.cside = (float)h->cside; g.inv_cside = (float)(1.0 / h->cside);
+    g.ncx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->cside) + 1;
+    g.ncy = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->cside) + 1;
+    g.ncz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->cside) + 1;
+    g.cw = (g.ncx + 63) / 64;
+    g.d_real = 2;
+    g.rmax_bound = h->rmax_bound;
+    g.d_rand_cap = std::min(15, std::max(2, (int)std::ceil((h->cut_eff + tau + h->rmax_bound + 1e-3) / h->cside)));
+    if ((double)g.nx * g.ny * g.nz > 2.0e8) return fail(h, CMX_ERR_CELL, "search grid too large for this cell/cutoff");
+    return CMX_OK;
+}
+
+template <class K, class... Args>
+void launch(cmx_handle *h, K kernel, dim3 grid, dim3 block, Args... args) {
+    kernel<<<grid, block, 0, h->s_comp>>>(args...);
+    h->stats.kernel_launches++;
+}
+
+cudaEvent_t prof_begin(cmx_handle *h) {
+    if (!h->profile) return nullptr;
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        h->prof_events.push_back({a, b});
+    }
+    cudaEventRecord(h->prof_events[h->prof_used].first, h->s_comp);
+    return h->prof_events[h->prof_used].second;
+}
+void prof_end(cmx_handle *h, cudaEvent_t e) {
+    if (!e) return;
+    cudaEventRecord(e, h->s_comp);
+    h->prof_used++;
+}
+void prof_collect(cmx_handle *h) {
+    for (size_t k = 0; k < h->prof_used; ++k) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->prof_events[k].first, h->prof_events[k].second) == cudaSuccess) h->stats.gpu_ms_main += ms;
+    }
+    h->prof_used = 0;
+}
+
+template <bool RANDOM>
+void launch_search(cmx_handle *h, const Geom &g, uint32_t frame, const float *xs, const float *xv, int isolute,
+                   const int *worklist, const int *work_count, MdRec *list, u64 *deferred, int *def_count, int nblocks) {
+    u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
+    dim3 grid(nblocks), block(256);
+#define CMX_LAUNCH_G(GG)                                                                                             \
+    launch(h, k_search<GG, RANDOM>, grid, block, g, h->P, frame, xs, xv, isolute, h->d_cell_start.p, h->d_sorted.p,  \
+           h->d_cdist.p, worklist, work_count, h->d_bulk_idx.p, h->d_scalars.p + 4, list, deferred, def_count, pe)
+    switch (h->G) {
+        case 1: CMX_LAUNCH_G(1); break;
+        case 2: CMX_LAUNCH_G(2); break;
+        case 4: CMX_LAUNCH_G(4); break;
+        case 16: CMX_LAUNCH_G(16); break;
+        case 32: CMX_LAUNCH_G(32); break;
+        default: CMX_LAUNCH_G(8); break;
+    }
+#undef CMX_LAUNCH_G
+}
+
+// ---- one frame on the grid path (mddf_frame!, src/mddf.jl:361-429) --------------------------------
+int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent, uint32_t frame, const Geom &g) {
+    const cmx_config &c = h->cfg;
+    const int ns_apm = c.solute_natomspermol, nv_mols = c.solvent_nmols;
+    size_t ncells = (size_t)g.nx * g.ny * g.nz, ncc = (size_t)g.ncx * g.ncy * g.ncz;
+    size_t occ_words = (size_t)g.ncy * g.ncz * g.cw;
+    CK(h->d_cell_count.ensure(ncells + 1, true));
+    CK(h->d_cell_start.ensure(ncells + 1));
+    CK(h->d_occ.ensure(occ_words));
+    CK(h->d_cdist.ensure(ncc));
+    const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
+    int *sc = h->d_scalars.p;
+    for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
+        const float *xs = d_solute + (size_t)3 * ns_apm * isolute;
+        const int skip = c.autocorrelation ? isolute : -1;
+        int nrand_k = 0;
+        if (c.solute_nmols == 1) nrand_k = nrand;
+        else for (int s = 0; s < nrand; ++s) nrand_k += (ref_solute_host(h, frame, (uint32_t)s) == isolute);
+        CK(cudaMemsetAsync(sc, 0, 8 * sizeof(int), h->s_comp));
+        CK(cudaMemsetAsync(h->d_occ.p, 0, occ_words * sizeof(u64), h->s_comp));
+        int tb = 128;
+        launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->d_cell_count.p,
+               (const int *)nullptr, h->d_occ.p, (float4 *)nullptr);
+        size_t tmp_bytes = h->d_cub_tmp.n;
+        CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp_bytes, h->d_cell_count.p, h->d_cell_start.p, (int)(ncells + 1), h->s_comp));
+        h->stats.kernel_launches += 2;
+        launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->d_cell_count.p,
+               (const int *)h->d_cell_start.p, h->d_occ.p, h->d_sorted.p);
+        launch(h, k_coarse_dist, dim3((unsigned)((ncc + 127) / 128)), dim3(128), g, (const u64 *)h->d_occ.p, h->d_cdist.p);
+        launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
+               (const unsigned char *)h->d_cdist.p, h->d_list.p, h->d_worklist.p, sc + 0, sc + 5);
+        CK(cudaMemcpyAsync(h->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
+        cudaEvent_t pe = prof_begin(h);
+        int nblk = h->num_sms * 8;
+        launch_search<false>(h, g, frame, xs, d_solvent, isolute, h->d_worklist.p, sc + 0, h->d_list.p, h->d_def_real.p, sc + 2, nblk);
+        prof_end(h, pe);
+        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const int *)h->d_bulk_idx.p,
+               (const int *)(sc + 4), (const u64 *)h->d_def_real.p, (const int *)(sc + 2), h->d_list.p, (MdRec *)nullptr);
+        if (c.keep_lists)
+            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
+                               cudaMemcpyDeviceToDevice, h->s_comp));
+        if (nrand_k == 0) {
+            launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)nullptr, h->d_stats.p);
+            continue;
+        }
+        // bulk list of this solute molecule, ascending molecule index (src/mddf.jl:406-415)
+        launch(h, k_bulk_flags, dim3((nv_mols + 255) / 256), dim3(256), h->P, (const MdRec *)h->d_list.p, skip, h->d_bulk_flags.p);
+        tmp_bytes = h->d_cub_tmp.n;
+        CK(cub::DeviceSelect::Flagged(h->d_cub_tmp.p, tmp_bytes, cub::CountingInputIterator<int>(0), h->d_bulk_flags.p,
+                                      h->d_bulk_idx.p, sc + 4, nv_mols, h->s_comp));
+        h->stats.kernel_launches += 2;
+        long long total = (long long)nrand * nv_mols;
+        launch(h, k_filter_rand, dim3((unsigned)((total + 255) / 256)), dim3(256), g, h->P, frame, isolute, skip,
+               (const unsigned char *)h->d_cdist.p, (const int *)(sc + 5), h->d_rand_worklist.p, sc + 1);
+        pe = prof_begin(h);
+        launch_search<true>(h, g, frame, xs, d_solvent, isolute, h->d_rand_worklist.p, sc + 1,
+                            c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_def_rand.p, sc + 3, nblk);
+        prof_end(h, pe);
+        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const int *)h->d_bulk_idx.p,
+               (const int *)(sc + 4), (const u64 *)h->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
+               c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
+        launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)(sc + 3), h->d_stats.p);
+    }
+    return CMX_OK;
+}
+
+__global__ void k_check_overflow(const int *flag, int *sticky) {
+    if (threadIdx.x == 0 && *flag) *sticky = 1;
+}
+
+__global__ void k_fold(const u64 *cnt, double *acc, size_t n, size_t half_lo, size_t half_hi, double w) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = (k >= half_lo && k < half_hi) ? w / 2 : w;
+    acc[k] += s * (double)cnt[k];
+}
+
+int fold_weight(cmx_handle *h) {
+    // acc += w * cnt ; cnt = 0  (the counters are sums of frame weights, src/update_counters.jl:47,60)
+    if (!h->acc_used) { CK(h->d_acc.ensure(h->cnt_len, true)); CK(cudaMemsetAsync(h->d_acc.p, 0, sizeof(double) * h->cnt_len, h->s_comp)); h->acc_used = true; }
+    size_t nb = h->nbins, lo = 4 * nb, hi = 4 * nb + 2 * nb * h->cfg.n_groups_solute;
+    if (!h->cfg.autocorrelation) lo = hi = 0;
+    launch(h, k_fold, dim3((unsigned)((h->cnt_len + 255) / 256)), dim3(256), (const u64 *)h->d_cnt.p, h->d_acc.p, h->cnt_len, lo, hi, h->cur_weight);
+    CK(cudaMemsetAsync(h->d_cnt.p, 0, sizeof(u64) * h->cnt_len, h->s_comp));
+    return CMX_OK;
+}
+
+int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, int64_t frame_index, double weight,
+                  const double cell[9]) {
+    if (!(weight > 0) && weight != 0) return fail(h, CMX_ERR_ARG, "frame weight must be finite and non-negative");
+    if (weight == 0) return fail(h, CMX_ERR_ARG, "zero-weight frames must be skipped by the caller (src/mddf.jl:102)");
+    Geom g;
+    int rc = build_geom(h, cell, g);
+    if (rc) return rc;
+    if (h->have_weight && weight != h->cur_weight) { rc = fold_weight(h); if (rc) return rc; }
+    h->cur_weight = weight; h->have_weight = true;
+    // rmax feedback from earlier frames (pinned mirror, may lag)
+    float seen = 0.f; std::memcpy(&seen, h->h_scalars + 5, sizeof(float));
+    if (seen > 0.f && seen * 1.25f + 0.1f > h->rmax_bound && seen > h->rmax_bound * 0.999f)
+        h->rmax_bound = std::max(h->rmax_bound, seen * 1.25f + 0.1f);
+    g.rmax_bound = h->rmax_bound;
+    g.d_rand_cap = std::min(15, std::max(2, (int)std::ceil((h->cut_eff + g.tau + h->rmax_bound + 1e-3) / h->cside)));
+    if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, h->s_comp)); h->ev_first_set = true; }
+    uint32_t frame = (uint32_t)(frame_index & 0xffffffffll);
+    if (h->cfg.keep_lists && h->d_rand_list.p) CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, h->s_comp));
+    h->last_g = g; h->last_dsol = d_solute; h->last_dsolv = d_solvent;
+    rc = h->path == 1 ? frame_grid_path(h, d_solute, d_solvent, frame, g)
+                      : frame_pair_path(h, d_solute, d_solvent, frame, g);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    // update_volume!, src/mddf.jl:350-352
+    const double *a = cell, *b = cell + 3, *c = cell + 6;
+    double axb[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    h->volume_total += weight * (axb[0] * c[0] + axb[1] * c[1] + axb[2] * c[2]);
+    h->sum_weights += weight;
+    h->stats.frames++;
+    h->last_frame = frame_index;
+    return CMX_OK;
+}
+
+}  // namespace
+
+#include "cmx_pairs_host.inl"
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" {
+
+const char *cmx_version(void) { return "cmx_b200 0.1.0 (sm_100a)"; }
+
+const char *cmx_last_error(cmx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t cmx_destroy(cmx_handle *h) {
+    if (!h) return CMX_OK;
+    cudaSetDevice(h->device);
+    if (h->s_comp) cudaStreamSynchronize(h->s_comp);
+    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    for (auto &s : h->ring) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    h->d_sol_off.release(); h->d_sol_ids.release(); h->d_solv_off.release(); h->d_solv_ids.release();
+    h->d_cnt.release(); h->d_acc.release(); h->d_cell_count.release(); h->d_cell_start.release(); h->d_sorted.release();
+    h->d_occ.release(); h->d_cdist.release(); h->d_bulk_flags.release(); h->d_list.release(); h->d_rand_list.release();
+    h->d_list_all.release(); h->d_worklist.release(); h->d_rand_worklist.release(); h->d_bulk_idx.release();
+    h->d_def_real.release(); h->d_def_rand.release(); h->d_scalars.release(); h->d_stats.release(); h->d_cub_tmp.release();
+    pairs_release(h);
+    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    for (auto &p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    if (h->ev_first) cudaEventDestroy(h->ev_first);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    delete h;
+    return CMX_OK;
+}
+
+static int create_impl(cmx_handle *h, const cmx_config *cfg) {
+    const cmx_config &c = *cfg;
+    if (c.struct_size != (int32_t)sizeof(cmx_config)) return fail(h, CMX_ERR_ARG, "cmx_config.struct_size mismatch (ABI)");
+    if (c.solute_nmols < 1 || c.solute_natomspermol < 1 || c.solvent_nmols < 1 || c.solvent_natomspermol < 1)
+        return fail(h, CMX_ERR_ARG, "selections must have at least one molecule and one atom per molecule");
+    if (c.irefatom < 1 || c.irefatom > c.solvent_natomspermol)
+        return fail(h, CMX_ERR_ARG, "in MDDF options: Reference atom index is greater than number of atoms of the solvent molecule.");
+    if (!(c.binstep > 0) || !(c.cutoff > 0) || !(c.dbulk > 0)) return fail(h, CMX_ERR_ARG, "binstep, cutoff and dbulk must be positive");
+    if (c.usecutoff && c.dbulk >= c.cutoff) return fail(h, CMX_ERR_ARG, "in MDDF options: The bulk volume is zero (dbulk must be smaller than cutoff).");
+    if (c.n_random_samples < 1 && !c.coordination_number_only) return fail(h, CMX_ERR_ARG, "in MDDF options: n_random_samples must be greater than 0.");
+    if (c.autocorrelation && (c.solute_nmols != c.solvent_nmols || c.solute_natomspermol != c.solvent_natomspermol))
+        return fail(h, CMX_ERR_ARG, "autocorrelation requires identical solute and solvent selections");
+    if (c.n_groups_solute < 1 || c.n_groups_solvent < 1) return fail(h, CMX_ERR_ARG, "n_groups_* must be positive");
+    if (!c.solute_group_offsets && c.n_groups_solute != c.solute_natomspermol) return fail(h, CMX_ERR_ARG, "n_groups_solute must equal solute_natomspermol without custom groups");
+    if (!c.solvent_group_offsets && c.n_groups_solvent != c.solvent_natomspermol) return fail(h, CMX_ERR_ARG, "n_groups_solvent must equal solvent_natomspermol without custom groups");
+    if ((double)c.n_random_samples * c.solvent_nmols > 2.0e9) return fail(h, CMX_ERR_ARG, "n_random_samples * solvent_nmols exceeds 2^31");
+    h->cfg = c;
+    h->device = c.device;
+    CK(cudaSetDevice(c.device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, c.device));
+    h->num_sms = prop.multiProcessorCount;
+    h->nbins = std::max(1, (int)std::ceil(c.cutoff / c.binstep));   // setbin(cutoff, binstep), src/results.jl:131
+    h->cut_eff = c.usecutoff ? c.cutoff : c.dbulk;                   // src/minimum_distances.jl:168
+    h->ns_atoms = (size_t)c.solute_nmols * c.solute_natomspermol;
+    h->nv_atoms = (size_t)c.solvent_nmols * c.solvent_natomspermol;
+    h->in_floats = 3 * (c.autocorrelation ? h->nv_atoms : h->ns_atoms + h->nv_atoms);
+    h->path = c.path ? c.path : ((c.solute_nmols == 1 || c.solute_natomspermol > 64) ? 1 : 2);
+    if (h->path != 1 && h->path != 2) return fail(h, CMX_ERR_ARG, "path must be 0 (auto), 1 (grid) or 2 (molecule pairs)");
+    int G = c.group_lanes ? c.group_lanes : 8;
+    if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");
+    h->G = G;
+    // fine grid: side ~ 3.5 A, K = reach in cells
+    h->Kdiv = std::min(8, std::max(2, (int)std::lround(h->cut_eff / 3.5)));
+    h->side = (h->cut_eff + 0.02) / h->Kdiv;
+    h->cside = (h->cut_eff + 0.02) / 2.0;
+    CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_last));
+    int slots = c.ring_slots > 0 ? c.ring_slots : 3;
+    h->ring.resize(slots);
+    for (auto &s : h->ring) {
+        CK(cudaHostAlloc(&s.h_in, sizeof(float) * h->in_floats, cudaHostAllocDefault));
+        CK(cudaMalloc(&s.d_in, sizeof(float) * h->in_floats));
+        CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
+    CK(cudaHostAlloc(&h->h_scalars, sizeof(int) * 8, cudaHostAllocDefault));
+    std::memset(h->h_scalars, 0, sizeof(int) * 8);
+    // problem description
+    Prob &P = h->P;
+    P.ns_mols = c.solute_nmols; P.ns_apm = c.solute_natomspermol; P.nv_mols = c.solvent_nmols; P.nv_apm = c.solvent_natomspermol;
+    P.autocorr = c.autocorrelation; P.iref = c.irefatom - 1; P.usecutoff = c.usecutoff; P.nbins = h->nbins;
+    P.nrand = c.coordination_number_only ? 0 : c.n_random_samples; P.cn_only = c.coordination_number_only;
+    P.ng_sol = c.n_groups_solute; P.ng_solv = c.n_groups_solvent;
+    P.custom_sol = c.solute_group_offsets != nullptr; P.custom_solv = c.solvent_group_offsets != nullptr;
+    P.cutoff = c.cutoff; P.dbulk = c.dbulk; P.binstep = c.binstep;
+    P.seed_lo = (uint32_t)(c.seed & 0xffffffffull); P.seed_hi = (uint32_t)(c.seed >> 32);
+    auto upload_csr = [&](const int32_t *off, const int32_t *ids, size_t npos, DevBuf<int> &doff, DevBuf<int> &dids) -> cudaError_t {
+        if (!off) return cudaSuccess;
+        size_t nids = (size_t)off[npos];
+        cudaError_t e = doff.ensure(npos + 1); if (e != cudaSuccess) return e;
+        e = dids.ensure(std::max<size_t>(nids, 1)); if (e != cudaSuccess) return e;
+        e = cudaMemcpy(doff.p, off, sizeof(int) * (npos + 1), cudaMemcpyHostToDevice); if (e != cudaSuccess) return e;
+        if (nids) e = cudaMemcpy(dids.p, ids, sizeof(int) * nids, cudaMemcpyHostToDevice);
+        return e;
+    };
+    if (P.custom_sol) {
+        for (size_t k = 0; k < (size_t)c.solute_group_offsets[h->ns_atoms]; ++k)
+            if (c.solute_group_ids[k] < 0 || c.solute_group_ids[k] >= c.n_groups_solute) return fail(h, CMX_ERR_ARG, "solute group id out of range");
+        CK(upload_csr(c.solute_group_offsets, c.solute_group_ids, h->ns_atoms, h->d_sol_off, h->d_sol_ids));
+    }
+    if (P.custom_solv) {
+        for (size_t k = 0; k < (size_t)c.solvent_group_offsets[h->nv_atoms]; ++k)
+            if (c.solvent_group_ids[k] < 0 || c.solvent_group_ids[k] >= c.n_groups_solvent) return fail(h, CMX_ERR_ARG, "solvent group id out of range");
+        CK(upload_csr(c.solvent_group_offsets, c.solvent_group_ids, h->nv_atoms, h->d_solv_off, h->d_solv_ids));
+    }
+    P.sol_off = h->d_sol_off.p; P.sol_ids = h->d_sol_ids.p; P.solv_off = h->d_solv_off.p; P.solv_ids = h->d_solv_ids.p;
+    size_t nb = h->nbins;
+    h->cnt_len = nb * (4 + 2 * (size_t)c.n_groups_solute + 2 * (size_t)c.n_groups_solvent);
+    CK(h->d_cnt.ensure(h->cnt_len)); CK(cudaMemset(h->d_cnt.p, 0, sizeof(u64) * h->d_cnt.n));
+    u64 *q = h->d_cnt.p;
+    P.md = q; q += nb; P.md_r = q; q += nb; P.rdf = q; q += nb; P.rdf_r = q; q += nb;
+    P.gsol = q; q += nb * c.n_groups_solute; P.gsol_r = q; q += nb * c.n_groups_solute;
+    P.gsolv = q; q += nb * c.n_groups_solvent; P.gsolv_r = q;
+    // scratch common to both paths
+    size_t nvm = c.solvent_nmols, nrand = (size_t)P.nrand;
+    CK(h->d_scalars.ensure(16, true)); CK(h->d_stats.ensure(8, true));
+    CK(h->d_list.ensure(nvm));
+    CK(h->d_bulk_flags.ensure(nvm)); CK(h->d_bulk_idx.ensure(nvm));
+    CK(h->d_worklist.ensure(nvm)); CK(h->d_rand_worklist.ensure(std::max<size_t>(nrand * nvm, 1)));
+    CK(h->d_def_real.ensure(nvm)); CK(h->d_def_rand.ensure(std::max<size_t>(nrand * nvm, 1)));
+    if (c.keep_lists) {
+        if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
+        CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));
+    }
+    if (h->path == 1) {
+        CK(h->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
+        // row traversal table: (dy,dz) offsets ordered by a lower bound of the row distance
+        int K = h->Kdiv, n = 0;
+        struct Row { short dy, dz; float lb; };
+        std::vector<Row> rows;
+        for (int dz = -K; dz <= K; ++dz)
+            for (int dy = -K; dy <= K; ++dy) {
+                int ay = std::max(std::abs(dy) - 1, 0), az = std::max(std::abs(dz) - 1, 0);
+                rows.push_back({(short)dy, (short)dz, (float)(ay * ay + az * az)});
+            }
+        std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+            if (a.lb != b.lb) return a.lb < b.lb;
+            return (a.dy * a.dy + a.dz * a.dz) < (b.dy * b.dy + b.dz * b.dz); });
+        n = (int)rows.size();
+        std::vector<short> dy(n), dz(n); std::vector<float> lb(n);
+        // keep a tiny safety factor on the lower bound (the search compares it with slack-free bounds)
+        for (int k = 0; k < n; ++k) { dy[k] = rows[k].dy; dz[k] = rows[k].dz; lb[k] = rows[k].lb * 0.998f; }
+        CK(cudaMemcpyToSymbol(c_row_dy, dy.data(), sizeof(short) * n));
+        CK(cudaMemcpyToSymbol(c_row_dz, dz.data(), sizeof(short) * n));
+        CK(cudaMemcpyToSymbol(c_row_lb, lb.data(), sizeof(float) * n));
+    } else {
+        int rc = pairs_create(h); if (rc) return rc;
+    }
+    // cub temp storage sized for the largest call we make
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, t1, (int *)nullptr, (int *)nullptr, 1 << 28);
+    cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, (int)std::max<size_t>(nvm, 1));
+    CK(h->d_cub_tmp.ensure(std::max(t1, t2) + 1024));
+    CK(cudaDeviceSynchronize());
+    return CMX_OK;
+}
+
+int32_t cmx_create(const cmx_config *cfg, cmx_handle **out) {
+    if (!cfg || !out) { g_create_error = "cmx_create: null argument"; return CMX_ERR_ARG; }
+    cmx_handle *h = new cmx_handle();
+    int rc = create_impl(h, cfg);
+    if (rc) { g_create_error = h->err; cmx_destroy(h); *out = nullptr; return rc; }
+    *out = h;
+    return CMX_OK;
+}
+
+int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solvent_xyz) {
+    if (!h) return CMX_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->acquired >= 0) return fail(h, CMX_ERR_STATE, "cmx_acquire_frame_buffer: previous slot not submitted");
+    Slot &s = h->ring[h->next_slot];
+    if (s.in_flight) { CK(cudaEventSynchronize(s.consumed)); s.in_flight = false; }
+    h->acquired = h->next_slot;
+    h->next_slot = (h->next_slot + 1) % (int)h->ring.size();
+    if (h->cfg.autocorrelation) { if (solute_xyz) *solute_xyz = s.h_in; if (solvent_xyz) *solvent_xyz = s.h_in; }
+    else { if (solute_xyz) *solute_xyz = s.h_in; if (solvent_xyz) *solvent_xyz = s.h_in + 3 * h->ns_atoms; }
+    return CMX_OK;
+}
+
+int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, const double cell[9]) {
+    if (!h || !cell) return CMX_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->acquired < 0) return fail(h, CMX_ERR_STATE, "cmx_submit_frame: no frame buffer acquired");
+    Slot &s = h->ring[h->acquired];
+    h->acquired = -1;
+    CK(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * h->in_floats, cudaMemcpyHostToDevice, h->s_copy));
+    CK(cudaEventRecord(s.h2d_done, h->s_copy));
+    CK(cudaStreamWaitEvent(h->s_comp, s.h2d_done, 0));
+    h->stats.h2d_bytes += (int64_t)(sizeof(float) * h->in_floats);
+    const float *dsol = s.d_in, *dsolv = h->cfg.autocorrelation ? s.d_in : s.d_in + 3 * h->ns_atoms;
+    int rc = submit_common(h, dsol, dsolv, frame_index, weight, cell);
+    // the slot is reusable once the frame's kernels are done (even on error, to keep the ring consistent)
+    cudaEventRecord(s.consumed, h->s_comp);
+    s.in_flight = true;
+    return rc;
+}
+
+int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const float *d_solvent_xyz, int64_t frame_index,
+                                double weight, const double cell[9]) {
+    if (!h || !cell || !d_solvent_xyz) return CMX_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    const float *dsol = h->cfg.autocorrelation ? d_solvent_xyz : d_solute_xyz;
+    if (!dsol) return fail(h, CMX_ERR_ARG, "cmx_submit_frame_device: null solute pointer");
+    return submit_common(h, dsol, d_solvent_xyz, frame_index, weight, cell);
+}
+
+int32_t cmx_sync(cmx_handle *h) {
+    if (!h) return CMX_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->ev_first_set) CK(cudaEventRecord(h->ev_last, h->s_comp));
+    CK(cudaStreamSynchronize(h->s_copy));
+    CK(cudaStreamSynchronize(h->s_comp));
+    if (h->ev_first_set) {
+        float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev_first, h->ev_last));
+        h->stats.gpu_ms_total += ms; h->ev_first_set = false;
+    }
+    prof_collect(h);
+    for (auto &s : h->ring) s.in_flight = false;
+    int sticky = 0;
+    CK(cudaMemcpy(&sticky, h->d_scalars.p + 8, sizeof(int), cudaMemcpyDeviceToHost));
+    if (sticky) return fail(h, CMX_ERR_STATE, "deferred-pair buffer overflow: too many exactly tied / cutoff-edge pairs in one frame");
+    return CMX_OK;
+}
+
+int32_t cmx_counters_device(cmx_handle *h, void **device_ptr, int64_t *n_uint64) {
+    if (!h || !device_ptr || !n_uint64) return CMX_ERR_ARG;
+    if (h->acc_used) return fail(h, CMX_ERR_STATE, "cmx_counters_device: frame weights varied; integer counters were folded to fp64 (use cmx_finish per GPU and sum)");
+    *device_ptr = h->d_cnt.p; *n_uint64 = (int64_t)h->cnt_len;
+    return CMX_OK;
+}
+
+int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
+    if (!h || !out) return CMX_ERR_ARG;
+    int rc = cmx_sync(h); if (rc) return rc;
+    size_t n = h->cnt_len, nb = h->nbins;
+    std::vector<u64> cnt(n);
+    CK(cudaMemcpy(cnt.data(), h->d_cnt.p, sizeof(u64) * n, cudaMemcpyDeviceToHost));
+    std::vector<double> acc;
+    if (h->acc_used) { acc.resize(n); CK(cudaMemcpy(acc.data(), h->d_acc.p, sizeof(double) * n, cudaMemcpyDeviceToHost)); }
+    const double w = h->have_weight ? h->cur_weight : 1.0;
+    const size_t gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
+    auto emit = [&](double *dst, size_t off, size_t len, double scale) {
+        if (!dst) return;
+        for (size_t k = 0; k < len; ++k) dst[k] = (h->acc_used ? acc[off + k] : 0.0) + scale * (double)cnt[off + k];
+    };
+    const double wg = h->cfg.autocorrelation ? w / 2 : w;   // src/update_counters.jl:52-53
+    emit(out->md_count, 0, nb, w); emit(out->md_count_random, nb, nb, w);
+    emit(out->rdf_count, 2 * nb, nb, w); emit(out->rdf_count_random, 3 * nb, nb, w);
+    emit(out->solute_group_count, 4 * nb, gs, wg); emit(out->solute_group_count_random, 4 * nb + gs, gs, wg);
+    emit(out->solvent_group_count, 4 * nb + 2 * gs, gv, w); emit(out->solvent_group_count_random, 4 * nb + 2 * gs + gv, gv, w);
+    out->nbins = h->nbins; out->n_groups_solute = h->cfg.n_groups_solute; out->n_groups_solvent = h->cfg.n_groups_solvent;
+    out->volume_total = h->volume_total; out->sum_weights = h->sum_weights;
+    return CMX_OK;
+}
+
+static void md_to_abi(const MdRec &e, cmx_md &o) {
+    o.within_cutoff = e.flags & 1; o.ref_atom_within_cutoff = (e.flags >> 1) & 1;
+    o.i = (e.flags & 1) ? e.i + 1 : 0; o.j = (e.flags & 1) ? e.j + 1 : 0;
+    o.d = (e.flags & 1) ? e.d : INFINITY; o.d_ref_atom = (e.flags & 2) ? e.dref : INFINITY;
+}
+
+int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out) {
+    if (!h || !out) return CMX_ERR_ARG;
+    if (!h->cfg.keep_lists) return fail(h, CMX_ERR_STATE, "cmx_read_minimum_distances needs cmx_config.keep_lists = 1");
+    if (isolute < 0 || isolute >= h->cfg.solute_nmols) return fail(h, CMX_ERR_ARG, "isolute out of range");
+    int rc = cmx_sync(h); if (rc) return rc;
+    size_t nvm = h->cfg.solvent_nmols;
+    std::vector<MdRec> tmp(nvm);
+    if (h->path == 2) {
+        // molecule-pair path keeps no per-solute lists: recompute the exact list of this solute
+        // molecule from the last frame (still resident in its staging slot)
+        if (!h->last_dsolv) return fail(h, CMX_ERR_STATE, "no frame submitted yet");
+        PairGeom pg = make_pair_geom(h, h->last_g);
+        launch(h, k_ref_lists, dim3((unsigned)((nvm + 127) / 128), 1), dim3(128), h->last_g, pg, h->P, (uint32_t)h->last_frame, (int)isolute,
+               h->last_dsol, h->last_dsolv, h->pairs.sol, h->pairs.solv, h->d_list.p);
+        CK(cudaStreamSynchronize(h->s_comp));
+        CK(cudaMemcpy(tmp.data(), h->d_list.p, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
+    } else
+    CK(cudaMemcpy(tmp.data(), h->d_list_all.p + (size_t)isolute * nvm, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
+    for (size_t m = 0; m < nvm; ++m) md_to_abi(tmp[m], out[m]);
+    return CMX_OK;
+}
+
+int32_t cmx_read_random_minimum_distances(cmx_handle *h, int32_t sample, cmx_md *out) {
+    if (!h || !out) return CMX_ERR_ARG;
+    if (!h->cfg.keep_lists) return fail(h, CMX_ERR_STATE, "cmx_read_random_minimum_distances needs cmx_config.keep_lists = 1");
+    if (sample < 0 || sample >= h->P.nrand) return fail(h, CMX_ERR_ARG, "sample out of range");
+    int rc = cmx_sync(h); if (rc) return rc;
+    size_t nvm = h->cfg.solvent_nmols;
+    std::vector<MdRec> tmp(nvm);
+    CK(cudaMemcpy(tmp.data(), h->d_rand_list.p + (size_t)sample * nvm, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
+    for (size_t m = 0; m < nvm; ++m) md_to_abi(tmp[m], out[m]);
+    return CMX_OK;
+}
+
+int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out) {
+    if (!h || !out) return CMX_ERR_ARG;
+    int rc = cmx_sync(h); if (rc) return rc;
+    u64 st[8];
+    CK(cudaMemcpy(st, h->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
+    h->stats.pair_evals = (int64_t)st[0]; h->stats.deferred = (int64_t)st[1];
+    *out = h->stats;
+    return CMX_OK;
+}
+
+int32_t cmx_reset(cmx_handle *h) {
+    if (!h) return CMX_ERR_ARG;
+    int rc = cmx_sync(h); if (rc) return rc;
+    CK(cudaMemset(h->d_cnt.p, 0, sizeof(u64) * h->d_cnt.n));
+    if (h->acc_used) CK(cudaMemset(h->d_acc.p, 0, sizeof(double) * h->d_acc.n));
+    CK(cudaMemset(h->d_stats.p, 0, sizeof(u64) * 8));
+    h->acc_used = false; h->have_weight = false; h->cur_weight = 1.0;
+    h->volume_total = 0; h->sum_weights = 0;
+    h->stats = cmx_stats{};
+    return CMX_OK;
+}
+
+int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
+    if (!h || !name) return CMX_ERR_ARG;
+    std::string n(name);
+    if (n == "count_pairs") h->count_pairs = value != 0;
+    else if (n == "profile") h->profile = value != 0;
+    else if (n == "group_lanes") {
+        int G = (int)value;
+        if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");
+        h->G = G;
+    } else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
+    return CMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+"""ctypes binding of the C ABI (include/cmx_b200.h) -- the Python twin of the Julia ``ccall`` shim.
+
+There is no CPU fallback: if libcmx_b200.so is missing or no CUDA device is present the
+constructor raises.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmx_b200.so")
+_SRC = [os.path.join(_HERE, "csrc", f) for f in
+        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl")]
+_HDR = os.path.join(os.path.dirname(_HERE), "include", "cmx_b200.h")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "63"]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libcmx_b200.so (in-tree)."""
+    newest = max(os.path.getmtime(p) for p in _SRC + [_HDR])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, _SRC[0]]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+class CmxConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("solute_nmols", C.c_int32),
+                ("solute_natomspermol", C.c_int32), ("solvent_nmols", C.c_int32), ("solvent_natomspermol", C.c_int32),
+                ("autocorrelation", C.c_int32), ("irefatom", C.c_int32), ("usecutoff", C.c_int32),
+                ("n_random_samples", C.c_int32), ("coordination_number_only", C.c_int32), ("lcell", C.c_int32),
+                ("n_groups_solute", C.c_int32), ("n_groups_solvent", C.c_int32), ("path", C.c_int32),
+                ("ring_slots", C.c_int32), ("keep_lists", C.c_int32), ("group_lanes", C.c_int32),
+                ("cutoff", C.c_double), ("dbulk", C.c_double), ("binstep", C.c_double), ("seed", C.c_uint64),
+                ("solute_group_offsets", C.c_void_p), ("solute_group_ids", C.c_void_p),
+                ("solvent_group_offsets", C.c_void_p), ("solvent_group_ids", C.c_void_p)]
+
+
+class CmxCounters(C.Structure):
+    _fields_ = [("nbins", C.c_int32), ("n_groups_solute", C.c_int32), ("n_groups_solvent", C.c_int32), ("reserved", C.c_int32),
+                ("md_count", C.c_void_p), ("md_count_random", C.c_void_p), ("rdf_count", C.c_void_p),
+                ("rdf_count_random", C.c_void_p), ("solute_group_count", C.c_void_p), ("solute_group_count_random", C.c_void_p),
+                ("solvent_group_count", C.c_void_p), ("solvent_group_count_random", C.c_void_p),
+                ("volume_total", C.c_double), ("sum_weights", C.c_double)]
+
+
+class CmxStats(C.Structure):
+    _fields_ = [("frames", C.c_int64), ("kernel_launches", C.c_int64), ("deferred", C.c_int64), ("pair_evals", C.c_int64),
+                ("hits_real", C.c_int64), ("hits_random", C.c_int64), ("h2d_bytes", C.c_int64),
+                ("gpu_ms_total", C.c_double), ("gpu_ms_main", C.c_double)]
+
+
+MD_DTYPE = np.dtype([("within_cutoff", np.int32), ("i", np.int32), ("j", np.int32),
+                     ("ref_atom_within_cutoff", np.int32), ("d", np.float64), ("d_ref_atom", np.float64)])
+
+EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_acquire_frame_buffer", "cmx_submit_frame",
+           "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_finish", "cmx_read_minimum_distances",
+           "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option"]
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library and declare the signatures (no compute call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build it with cmx_b200.engine.build() (nvcc, sm_100a). "
+                           "There is no CPU fallback for the minimum-distance path.")
+    lib = C.CDLL(path)
+    vp = C.c_void_p
+    lib.cmx_version.restype = C.c_char_p
+    lib.cmx_last_error.restype = C.c_char_p; lib.cmx_last_error.argtypes = [vp]
+    lib.cmx_create.argtypes = [C.POINTER(CmxConfig), C.POINTER(vp)]
+    lib.cmx_destroy.argtypes = [vp]
+    lib.cmx_acquire_frame_buffer.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float))]
+    lib.cmx_submit_frame.argtypes = [vp, C.c_int64, C.c_double, C.POINTER(C.c_double)]
+    lib.cmx_submit_frame_device.argtypes = [vp, vp, vp, C.c_int64, C.c_double, C.POINTER(C.c_double)]
+    lib.cmx_sync.argtypes = [vp]
+    lib.cmx_counters_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.cmx_finish.argtypes = [vp, C.POINTER(CmxCounters)]
+    lib.cmx_read_minimum_distances.argtypes = [vp, C.c_int32, vp]
+    lib.cmx_read_random_minimum_distances.argtypes = [vp, C.c_int32, vp]
+    lib.cmx_get_stats.argtypes = [vp, C.POINTER(CmxStats)]
+    lib.cmx_reset.argtypes = [vp]
+    lib.cmx_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    for name in EXPORTS:
+        if name not in ("cmx_version", "cmx_last_error"):
+            getattr(lib, name).restype = C.c_int32
+    _lib = lib
+    return lib
+
+
+class CmxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libcmx_b200 error {code}: {msg}")
+        self.code = code
+
+
+def cell_to_c(cell) -> np.ndarray:
+    """3x3 matrix, lattice vectors as COLUMNS (convert_unitcell) -> column-major double[9]."""
+    cell = np.asarray(cell, dtype=np.float64)
+    if cell.shape == (3,):
+        cell = np.diag(cell)
+    return np.ascontiguousarray(cell.T).reshape(9).copy()
+
+
+class Engine:
+    """One ``mddf`` problem on one GPU (= one chunk task of the reference, src/mddf.jl:288-337)."""
+
+    def __init__(self, *, solute, solvent, options, irefatom: int, autocorrelation: bool,
+                 coordination_number_only: bool = False, device: int = 0, path: int = 0, keep_lists: bool = False,
+                 ring_slots: int = 3, group_lanes: int = 0):
+        self.lib = load_library()
+        cfg = CmxConfig()
+        cfg.struct_size = C.sizeof(CmxConfig)
+        cfg.device = device
+        cfg.solute_nmols, cfg.solute_natomspermol = solute.nmols, solute.natomspermol
+        cfg.solvent_nmols, cfg.solvent_natomspermol = solvent.nmols, solvent.natomspermol
+        cfg.autocorrelation = int(autocorrelation)
+        cfg.irefatom = irefatom
+        cfg.usecutoff = int(options.usecutoff)
+        cfg.n_random_samples = options.n_random_samples
+        cfg.coordination_number_only = int(coordination_number_only)
+        cfg.lcell = options.lcell
+        cfg.n_groups_solute, cfg.n_groups_solvent = solute.n_groups, solvent.n_groups
+        cfg.path, cfg.ring_slots, cfg.keep_lists, cfg.group_lanes = path, ring_slots, int(keep_lists), group_lanes
+        cfg.cutoff, cfg.dbulk, cfg.binstep = options.cutoff, options.dbulk, options.binstep
+        cfg.seed = options.seed if options.seed > 0 else 0
+        self._keep = []
+        for side, sel in (("solute", solute), ("solvent", solvent)):
+            off, ids = sel.group_csr()
+            if off is not None:
+                off = np.ascontiguousarray(off, dtype=np.int32); ids = np.ascontiguousarray(ids, dtype=np.int32)
+                self._keep += [off, ids]
+                setattr(cfg, f"{side}_group_offsets", off.ctypes.data); setattr(cfg, f"{side}_group_ids", ids.ctypes.data)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.cmx_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            raise CmxError(rc, self.lib.cmx_last_error(None).decode())
+        self.nbins = max(1, int(np.ceil(options.cutoff / options.binstep)))
+        self.n_solute_atoms = solute.nmols * solute.natomspermol
+        self.n_solvent_atoms = solvent.nmols * solvent.natomspermol
+        self.autocorrelation = bool(autocorrelation)
+        self.nmols_solvent = solvent.nmols
+
+    def _ck(self, rc):
+        if rc:
+            raise CmxError(rc, self.lib.cmx_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.cmx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- frame feed ---------------------------------------------------------------------------
+    def acquire(self):
+        """numpy views (fp32 [n,3]) over the next pinned staging slot."""
+        ps, pv = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        self._ck(self.lib.cmx_acquire_frame_buffer(self.h, C.byref(ps), C.byref(pv)))
+        xv = np.ctypeslib.as_array(pv, shape=(self.n_solvent_atoms, 3))
+        xs = xv if self.autocorrelation else np.ctypeslib.as_array(ps, shape=(self.n_solute_atoms, 3))
+        return xs, xv
+
+    def submit(self, frame_index: int, weight: float, cell):
+        c = cell_to_c(cell)
+        self._ck(self.lib.cmx_submit_frame(self.h, int(frame_index), float(weight), c.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def submit_arrays(self, xsolute, xsolvent, cell, frame_index: int = 0, weight: float = 1.0):
+        xs, xv = self.acquire()
+        xv[...] = xsolvent
+        if not self.autocorrelation:
+            xs[...] = xsolute
+        self.submit(frame_index, weight, cell)
+
+    def submit_device(self, d_solute_ptr: int, d_solvent_ptr: int, cell, frame_index: int = 0, weight: float = 1.0):
+        c = cell_to_c(cell)
+        self._ck(self.lib.cmx_submit_frame_device(self.h, C.c_void_p(d_solute_ptr or 0), C.c_void_p(d_solvent_ptr), int(frame_index),
+                                                  float(weight), c.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def sync(self):
+        self._ck(self.lib.cmx_sync(self.h))
+
+    def reset(self):
+        self._ck(self.lib.cmx_reset(self.h))
+
+    def set_option(self, name: str, value: float):
+        self._ck(self.lib.cmx_set_option(self.h, name.encode(), float(value)))
+
+    # ---- results --------------------------------------------------------------------------------
+    def counters_device(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.cmx_counters_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def finish(self) -> dict:
+        nb, gs, gv = self.nbins, self.cfg.n_groups_solute, self.cfg.n_groups_solvent
+        out = dict(md_count=np.zeros(nb), md_count_random=np.zeros(nb), rdf_count=np.zeros(nb), rdf_count_random=np.zeros(nb),
+                   solute_group_count=np.zeros((gs, nb)), solute_group_count_random=np.zeros((gs, nb)),
+                   solvent_group_count=np.zeros((gv, nb)), solvent_group_count_random=np.zeros((gv, nb)))
+        c = CmxCounters()
+        for k, v in out.items():
+            setattr(c, k, v.ctypes.data)
+        self._ck(self.lib.cmx_finish(self.h, C.byref(c)))
+        out["volume_total"] = c.volume_total
+        out["sum_weights"] = c.sum_weights
+        return out
+
+    def minimum_distances(self, isolute: int = 0) -> np.ndarray:
+        out = np.zeros(self.nmols_solvent, dtype=MD_DTYPE)
+        self._ck(self.lib.cmx_read_minimum_distances(self.h, isolute, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def random_minimum_distances(self, sample: int) -> np.ndarray:
+        out = np.zeros(self.nmols_solvent, dtype=MD_DTYPE)
+        self._ck(self.lib.cmx_read_random_minimum_distances(self.h, sample, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def stats(self) -> dict:
+        s = CmxStats()
+        self._ck(self.lib.cmx_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in CmxStats._fields_}

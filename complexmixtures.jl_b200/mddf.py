@@ -1,0 +1,136 @@
+"""mddf() / coordination_number() -- the drivers of the reference (src/mddf.jl:186-347, 539-574)
+with the chunk loop (src/mddf.jl:263-339) replaced by calls into libcmx_b200.so.
+
+What is kept from the reference: argument validation, TrajectoryMetaData, Result construction,
+frame selection (firstframe/lastframe/stride, zero-weight frames skipped: goto_nextframe!,
+src/mddf.jl:95-111), the cooperative stop file (src/mddf.jl:301-304) and finalresults!.
+What changes (src/parallel_setup.jl): instead of nthreads chunk tasks with private Result copies,
+computed frames are dealt round-robin to the ranks of a torch.distributed job (one process per
+GPU); every rank runs its own engine and the integer counters are summed with ONE all-reduce.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+
+from .engine import Engine
+from .options import Options
+from .results import Result, finalresults, new_result
+from .selection import AtomSelection
+from .trajectory import Trajectory, make_trajectory, trajectory_metadata
+
+
+def frames_to_compute(options: Options, lastframe_read: int, frame_weights) -> list:
+    """1-based frame numbers that are computed (to_compute_frames minus zero-weight frames)."""
+    fw = np.asarray(frame_weights, dtype=np.float64).reshape(-1)
+    out = []
+    for iframe in range(options.firstframe, lastframe_read + 1, options.stride):
+        w = 1.0 if fw.size == 0 else float(fw[iframe - 1])
+        if w != 0.0:
+            out.append((iframe, w))
+    return out
+
+
+def shard(frames: list, rank: int, world: int) -> list:
+    """Frame f -> rank (position in the computed-frame list) mod world."""
+    return [fw for k, fw in enumerate(frames) if k % world == rank]
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def allreduce_counters(eng: Engine, volume_total: float, sum_weights: float):
+    """The single exchange step: sum the integer accumulators over the GPUs (sum!, results.jl:629-649)."""
+    import torch
+    import torch.distributed as dist
+    ptr, n = eng.counters_device()
+
+    class _Wrap:
+        pass
+    w = _Wrap()
+    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+    t = torch.as_tensor(w, device=f"cuda:{eng.cfg.device}")
+    eng.sync()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    s = torch.tensor([volume_total, sum_weights], dtype=torch.float64, device=t.device)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize(t.device)
+    return float(s[0]), float(s[1])
+
+
+def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[AtomSelection] = None,
+         options: Optional[Options] = None, *, trajectory_format: str = "", frame_weights=(),
+         coordination_number_only: bool = False, low_memory: bool = False, device: Optional[int] = None,
+         path: int = 0, _engine_kw: Optional[dict] = None) -> Result:
+    """mddf(trajectory_file, solute, solvent, options; ...) or mddf(trajectory, options; ...).
+
+    ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
+    counters per GPU regardless of the thread count (src/parallel_setup.jl:21-54 does not apply).
+    """
+    if isinstance(trajectory, str):
+        if isinstance(solvent, Options) and options is None:      # mddf(file, solute_and_solvent, options)
+            options, solvent = solvent, None
+        options = options or Options()
+        trajectory = make_trajectory(trajectory, solute, solvent, format=trajectory_format, lastframe=options.lastframe)
+    else:
+        if isinstance(solute, Options) and options is None:       # mddf(trajectory, options)
+            options = solute
+        options = options or Options()
+    assert isinstance(trajectory, Trajectory)
+    tmeta = trajectory_metadata(trajectory, options)
+    R = new_result(trajectory, options, tmeta, frame_weights)
+    rank, world = _dist_info()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
+    eng = Engine(solute=trajectory.solute, solvent=trajectory.solvent, options=options, irefatom=tmeta.irefatom,
+                 autocorrelation=R.autocorrelation, coordination_number_only=coordination_number_only, device=device,
+                 path=path, **(_engine_kw or {}))
+    todo = frames_to_compute(options, tmeta.lastframe_read, R.files[0].frame_weights)
+    mine = set(f for f, _ in shard(todo, rank, world))
+    weights = dict(todo)
+    trajectory.open()
+    trajectory.firstframe()
+    iframe = 0
+    try:
+        for iframe in range(1, tmeta.lastframe_read + 1):
+            if os.path.isfile("stop_complexmixtures"):   # src/mddf.jl:301-304
+                break
+            if iframe in mine:
+                xs, xv = eng.acquire()
+                trajectory.nextframe(xs, xv)             # reader writes fp32 straight into the pinned slot
+                eng.submit(iframe, weights[iframe], trajectory.getunitcell())
+            else:
+                trajectory.nextframe()
+    finally:
+        trajectory.close()
+    if world > 1:
+        c0 = eng.finish()
+        vol, sw = allreduce_counters(eng, c0["volume_total"], c0["sum_weights"])
+        c = eng.finish()
+        c["volume_total"], c["sum_weights"] = vol, sw
+    else:
+        c = eng.finish()
+    R.engine_stats = eng.stats()
+    eng.close()
+    for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count",
+              "solute_group_count_random", "solvent_group_count", "solvent_group_count_random"):
+        setattr(R, k, c[k])
+    R.volume.total = c["volume_total"]
+    return finalresults(R, options, coordination_number_only=coordination_number_only)
+
+
+def coordination_number(trajectory, solute=None, solvent=None, options=None, **kw) -> Result:
+    """coordination_number(...) == mddf(...; coordination_number_only=true), src/mddf.jl:539-574."""
+    if "coordination_number_only" in kw:
+        raise ValueError("The keyword argument `coordination_number_only` is not valid for this function. "
+                         "It is, by definition, set to `true` in this function.")
+    return mddf(trajectory, solute, solvent, options, coordination_number_only=True, **kw)

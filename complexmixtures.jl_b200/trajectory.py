@@ -153,7 +153,7 @@ class PDBTraj(Trajectory):
         with open(filename) as f:
             for line in f:
                 if line.startswith("CRYST1"):
-                    v = [float(t) for t in line[6:54].split()]
+                    v = [float(t) for t in line[6:].split()[:6]]
                     cell = cell_from_lengths_angles(*v[:6])
                 elif line.startswith(("ATOM", "HETATM")):
                     cur.append((float(line[30:38]), float(line[38:46]), float(line[46:54])))

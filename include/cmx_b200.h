@@ -1,0 +1,145 @@
+/*
+ * cmx_b200.h -- C ABI of libcmx_b200.so, the B200 (sm_100a) replacement of the per-frame
+ * minimum-distance hot path of ComplexMixtures.jl.
+ *
+ * The reference has no FFI/plugin interface: the path is reached by ordinary Julia calls.
+ * The seam this ABI replaces is the body of the chunk task of mddf(), reference
+ * src/mddf.jl:288-337:
+ *
+ *     build_particle_system(...)            src/minimum_distances.jl:157-176   -> cmx_create
+ *     Buffer(...), Result(...)              src/mddf.jl:18-26, results.jl:124  -> cmx_create
+ *     @. buff.solute_read = trajectory.x_solute ; unitcell      mddf.jl:307-321 -> cmx_acquire_frame_buffer
+ *     update!(system; unitcell)             src/mddf.jl:326                    -> cmx_submit_frame
+ *     mddf_frame!(r_chunk, system, buff, options, w, RNG)       mddf.jl:329,361-429 -> cmx_submit_frame
+ *     coordination_number_frame!(...)       src/mddf.jl:331,438-471            -> cmx_submit_frame (coordination_number_only)
+ *     sum!(R, r_chunk)                      src/mddf.jl:336, results.jl:629-649 -> cmx_finish (+ cmx_counters_device for the NCCL all-reduce)
+ *
+ * Conventions: every function returns int32 status (0 = CMX_OK); cmx_last_error() gives the
+ * message; no exception crosses the boundary; all pointers are caller-owned unless stated.
+ * Plain C types only -- no torch / CUDA types in any signature.
+ */
+#ifndef CMX_B200_H
+#define CMX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMX_OK 0
+#define CMX_ERR_ARG 1      /* invalid argument / configuration                         */
+#define CMX_ERR_CUDA 2     /* CUDA runtime error (message has the CUDA error string)   */
+#define CMX_ERR_CELL 3     /* unit cell narrower than 2*cutoff in some direction       */
+#define CMX_ERR_STATE 4    /* call sequence error (e.g. submit without acquire)        */
+
+typedef struct cmx_handle cmx_handle;
+
+/* Flattened Options (src/Options.jl:6-42) + AtomSelection (src/AtomSelection.jl:48-59) +
+ * TrajectoryMetaData (src/Trajectory.jl:180-187). */
+typedef struct cmx_config {
+    int32_t struct_size;              /* = sizeof(cmx_config), ABI check                        */
+    int32_t device;                   /* CUDA device ordinal                                     */
+    int32_t solute_nmols;             /* AtomSelection.nmols                                     */
+    int32_t solute_natomspermol;      /* AtomSelection.natomspermol                              */
+    int32_t solvent_nmols;
+    int32_t solvent_natomspermol;
+    int32_t autocorrelation;          /* solute and solvent are the same selection               */
+    int32_t irefatom;                 /* 1-based, resolved (TrajectoryMetaData.irefatom)          */
+    int32_t usecutoff;                /* Options.usecutoff                                       */
+    int32_t n_random_samples;         /* Options.n_random_samples                                */
+    int32_t coordination_number_only; /* mddf(...; coordination_number_only)                     */
+    int32_t lcell;                    /* Options.lcell: accepted, a hint only                    */
+    int32_t n_groups_solute;          /* rows of solute_group_count (natomspermol or #groups)     */
+    int32_t n_groups_solvent;
+    int32_t path;                     /* 0 auto, 1 grid path (large solute molecule), 2 molecule-pair path */
+    int32_t ring_slots;               /* pinned staging slots (0 -> 3)                           */
+    int32_t keep_lists;               /* keep per-frame minimum-distance lists for cmx_read_*    */
+    int32_t group_lanes;              /* lanes cooperating on one solvent molecule (0 -> auto)   */
+    double cutoff;                    /* Options.cutoff                                          */
+    double dbulk;                     /* Options.dbulk                                           */
+    double binstep;                   /* Options.binstep                                         */
+    uint64_t seed;                    /* Options.seed (Philox key)                               */
+    /* custom groups: CSR "position in the selection -> group ids" (NULL = per atom type,
+     * src/update_counters.jl:22-36) */
+    const int32_t *solute_group_offsets, *solute_group_ids;
+    const int32_t *solvent_group_offsets, *solvent_group_ids;
+} cmx_config;
+
+/* Output of cmx_finish: f64 arrays laid out like Result (src/results.jl:73-104); the group
+ * arrays are row-major [n_groups][nbins] (one row per group = one Vector{Float64}). */
+typedef struct cmx_counters {
+    int32_t nbins, n_groups_solute, n_groups_solvent, reserved;
+    double *md_count, *md_count_random;
+    double *rdf_count, *rdf_count_random;
+    double *solute_group_count, *solute_group_count_random;
+    double *solvent_group_count, *solvent_group_count_random;
+    double volume_total;              /* sum_f w_f * det(cell_f), src/mddf.jl:350-352             */
+    double sum_weights;               /* sum of the weights of the frames submitted               */
+} cmx_counters;
+
+/* MinimumDistance (src/minimum_distances.jl:12-19); i, j are 1-based as in the reference
+ * (i within the current solute molecule, j in the solvent selection), 0 when empty. */
+typedef struct cmx_md {
+    int32_t within_cutoff, i, j, ref_atom_within_cutoff;
+    double d, d_ref_atom;
+} cmx_md;
+
+typedef struct cmx_stats {
+    int64_t frames;            /* frames submitted                                               */
+    int64_t kernel_launches;   /* kernels of this library launched so far                        */
+    int64_t deferred;          /* molecules re-evaluated by the exact fp64 resolve kernel
+                                  (fp32 near-ties / cutoff-edge cases), all phases               */
+    int64_t pair_evals;        /* atom-pair distances evaluated by the search kernels (0 unless
+                                  cmx_set_option("count_pairs", 1))                              */
+    int64_t hits_real, hits_random; /* molecules within the cutoff counted so far                 */
+    int64_t h2d_bytes;         /* bytes copied host->device by cmx_submit_frame                  */
+    double gpu_ms_total;       /* device time of all frames (CUDA events on the compute stream)  */
+    double gpu_ms_main;        /* device time spent in the dominant search kernels               */
+} cmx_stats;
+
+const char *cmx_version(void);
+const char *cmx_last_error(cmx_handle *h);   /* h may be NULL: error of the last failed cmx_create */
+
+int32_t cmx_create(const cmx_config *cfg, cmx_handle **out);
+int32_t cmx_destroy(cmx_handle *h);
+
+/* Pointers into the next free pinned staging slot: the host reader writes fp32 xyz triplets in
+ * place (solute_xyz[3*n_solute_atoms], solvent_xyz[3*n_solvent_atoms]); for an autocorrelation
+ * only solvent_xyz is used and *solute_xyz aliases it.  Blocks while the ring is full. */
+int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solvent_xyz);
+
+/* Enqueue the frame in the acquired slot: async H2D + all kernels; returns immediately.
+ * cell: column-major 3x3, columns = lattice vectors (convert_unitcell, src/Trajectory.jl:72-81).
+ * frame_index keys the Philox stream (seed, frame_index, sample, molecule), so results do not
+ * depend on which GPU processes the frame.  weight = 0 frames must not be submitted. */
+int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, const double cell[9]);
+
+/* Same, for coordinates already resident in device memory (device pointers to fp32 xyz). */
+int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const float *d_solvent_xyz,
+                                int64_t frame_index, double weight, const double cell[9]);
+
+int32_t cmx_sync(cmx_handle *h);
+
+/* Device pointer to the contiguous block of integer (uint64) run accumulators, for the single
+ * all-reduce(sum) over the GPUs that shared the frames (src/mddf.jl:336 -> sum!).  Valid after
+ * cmx_sync.  Layout: md, md_random, rdf, rdf_random [nbins each], solute_group,
+ * solute_group_random [n_groups_solute*nbins each], solvent_group, solvent_group_random. */
+int32_t cmx_counters_device(cmx_handle *h, void **device_ptr, int64_t *n_uint64);
+
+/* Syncs and writes the f64 counters (buffers pre-allocated by the caller; NULL members skipped). */
+int32_t cmx_finish(cmx_handle *h, cmx_counters *out);
+
+/* Parity hooks: system.list after minimum_distances! (src/minimum_distances.jl:147) of the LAST
+ * submitted frame (needs keep_lists=1).  isolute is 0-based; sample is the random sample index. */
+int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out /*[solvent_nmols]*/);
+int32_t cmx_read_random_minimum_distances(cmx_handle *h, int32_t sample, cmx_md *out /*[solvent_nmols]*/);
+
+int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out);
+int32_t cmx_reset(cmx_handle *h);                       /* zero all accumulators and statistics */
+int32_t cmx_set_option(cmx_handle *h, const char *name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMX_B200_H */

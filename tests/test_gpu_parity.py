@@ -1,0 +1,189 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the fp64 oracle on the same inputs.
+
+Bars (BASELINE.json north_star): minimum distances within 1e-4 A (here: the counted distances
+are finalised in fp64 with the oracle's arithmetic, so the bar used is 1e-9 A / bit equality),
+integer histogram and contribution counts bit-exact, final mddf/KB within 1e-3 relative.
+"""
+import numpy as np
+import pytest
+
+import cmx_b200 as cm
+from common import Problem, assert_counters_equal, assert_lists_equal, namd, toy
+from oracle import cmx_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+PROTEIN = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+TMAO = cm.AtomSelection(np.arange(1479, 4013), natomspermol=14)
+WATER = cm.AtomSelection(np.arange(4013, 62027), natomspermol=3)
+
+
+def opts(**kw):
+    kw.setdefault("silent", True)
+    kw.setdefault("seed", 321)
+    return cm.Options(**kw)
+
+
+def check(problem, *, lists=True, dtol=1e-9, engine_kw=None, nsolute_lists=1):
+    o, olists = problem.oracle(want_lists=lists)
+    eng = problem.engine(keep_lists=lists, **(engine_kw or {}))
+    nf = len(problem.xv)
+    if lists:
+        # frame by frame so that the per-frame lists can be read back
+        for k in range(nf):
+            problem.run_engine(eng, frames=[k])
+            real, rnd = olists[k]
+            for isol in range(min(nsolute_lists, problem.solute.nmols)):
+                assert_lists_equal(eng.minimum_distances(isol), real[isol], dtol=dtol, what=f"frame {k} real list solute {isol}")
+            if not problem.cn_only:
+                for s in range(problem.options.n_random_samples):
+                    assert_lists_equal(eng.random_minimum_distances(s), rnd[s], dtol=dtol, what=f"frame {k} random sample {s}")
+        dev = eng.finish()
+    else:
+        dev = problem.run_engine(eng)
+    stats = eng.stats()
+    eng.close()
+    assert_counters_equal(dev, o)
+    return dev, o, stats
+
+
+def test_namd_protein_tmao():
+    """C1: protein (1 molecule, 1463 atoms) x TMAO, cubic cell, the reference's test/namd.jl:16-22 setup."""
+    d = namd()
+    p = Problem(PROTEIN, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=10), d["protein"], d["tmao"], d["cells"])
+    assert p.irefatom == 1
+    dev, o, stats = check(p)
+    assert dev["md_count"].sum() > 0 and dev["md_count_random"].sum() > 0
+
+
+def test_namd_kat_coordination_numbers():
+    """src/tools/coordination_number.jl:126-134 on frame 1: CN(d>3)=7, CN(d>5)=14, sum CN(O1)=1171."""
+    d = namd()
+    p = Problem(PROTEIN, TMAO, opts(n_random_samples=1), d["protein"][:1], d["tmao"][:1], d["cells"][:1], coordination_number_only=True)
+    eng = p.engine()
+    c = p.run_engine(eng)
+    eng.close()
+    dd = orc.shellradius(np.arange(1, 501), 0.02)
+    cn = np.cumsum(c["md_count"])
+    assert cn[np.argmax(dd > 3)] == 7.0 and cn[np.argmax(dd > 5)] == 14.0
+    assert np.cumsum(c["solvent_group_count"][4]).sum() == 1171.0
+
+
+@pytest.mark.parametrize("path", [2, 1])
+def test_namd_tmao_water_cross(path):
+    """solute = 181 TMAO molecules, solvent = 19338 waters (water_tmao.json setup)."""
+    d = namd()
+    p = Problem(TMAO, WATER, opts(bulk_range=(8.0, 10.0), n_random_samples=3), d["tmao"][:1], [d["water_frame1"]], d["cells"][:1])
+    assert p.irefatom == 1
+    check(p, lists=(path == 2), engine_kw=dict(path=path), nsolute_lists=3)
+
+
+@pytest.mark.parametrize("path", [2, 1])
+def test_namd_tmao_self(path):
+    """autocorrelation of TMAO (tmao_tmao.json setup), both device paths."""
+    d = namd()
+    p = Problem(TMAO, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=10), d["tmao"], None, d["cells"], autocorrelation=True)
+    check(p, engine_kw=dict(path=path), nsolute_lists=4)
+
+
+def test_namd_water_self():
+    """19338-molecule water autocorrelation, frame 1 (water_water.json setup)."""
+    d = namd()
+    p = Problem(WATER, WATER, opts(bulk_range=(8.0, 10.0), n_random_samples=2), [d["water_frame1"]], None, d["cells"][:1], autocorrelation=True)
+    check(p, lists=False)
+
+
+def test_default_options_no_cutoff():
+    """usecutoff=false: cutoff = dbulk, bulk = molecules outside the cutoff (src/mddf.jl:55-57)."""
+    d = namd()
+    p = Problem(PROTEIN, TMAO, opts(dbulk=8.0, n_random_samples=4), d["protein"][:2], d["tmao"][:2], d["cells"][:2])
+    check(p)
+
+
+@pytest.mark.parametrize("G", [1, 4, 32])
+def test_group_lanes(G):
+    d = namd()
+    p = Problem(PROTEIN, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=2), d["protein"][:1], d["tmao"][:1], d["cells"][:1])
+    check(p, engine_kw=dict(group_lanes=G))
+
+
+def _synthetic(triclinic, seed=7, nprot=400, nwat=600, nco=60):
+    from cmx_b200 import synthetic as syn
+    cell = np.array([[46.0, 9.0, 6.0], [0.0, 44.0, 8.0], [0.0, 0.0, 43.0]]) if triclinic else [44.0, 46.0, 45.0]
+    return syn.make_system("t", cell=cell, solute_atoms=nprot, solvents=[("co", "tmao", nco), ("water", "water", nwat)], seed=seed)
+
+
+@pytest.mark.parametrize("triclinic", [False, True])
+def test_synthetic_protein_water(triclinic):
+    s = _synthetic(triclinic)
+    fr = [s.frame(k)[0] for k in range(3)]
+    sol, wat = s.selections["solute"], s.selections["water"]
+    p = Problem(sol, wat, opts(bulk_range=(6.0, 9.0), n_random_samples=5), [f[sol.indices - 1] for f in fr],
+                [f[wat.indices - 1] for f in fr], s.cell)
+    check(p)
+
+
+@pytest.mark.parametrize("triclinic", [False, True])
+@pytest.mark.parametrize("path", [2, 1])
+def test_synthetic_self_and_cross_small_molecules(triclinic, path):
+    s = _synthetic(triclinic, seed=11)
+    fr = [s.frame(k)[0] for k in range(2)]
+    co, wat = s.selections["co"], s.selections["water"]
+    p = Problem(co, co, opts(bulk_range=(7.0, 10.0), n_random_samples=6), [f[co.indices - 1] for f in fr], None, s.cell, autocorrelation=True)
+    check(p, engine_kw=dict(path=path), nsolute_lists=3)
+    p = Problem(co, wat, opts(bulk_range=(7.0, 10.0), n_random_samples=6), [f[co.indices - 1] for f in fr],
+                [f[wat.indices - 1] for f in fr], s.cell)
+    check(p, engine_kw=dict(path=path), nsolute_lists=3)
+
+
+def test_custom_groups_overlapping():
+    """custom groups on both sides, overlapping (src/update_counters.jl:27-33, contributions.jl:375-386)."""
+    d = namd()
+    g1 = [np.arange(1, 500), np.arange(400, 900), np.arange(1000, 1464)]
+    prot = cm.AtomSelection(np.arange(1, 1464), nmols=1, group_atom_indices=g1, group_names=["a", "b", "c"])
+    tm_idx = np.arange(1479, 4013)
+    g2 = [tm_idx[tm_idx % 14 == 5], tm_idx[:700]]
+    tm = cm.AtomSelection(tm_idx, natomspermol=14, group_atom_indices=g2, group_names=["x", "y"])
+    p = Problem(prot, tm, opts(bulk_range=(8.0, 10.0), n_random_samples=3), d["protein"][:2], d["tmao"][:2], d["cells"][:2])
+    check(p, lists=False)
+    # autocorrelation with custom groups (md.i resolves into the first molecule: update_counters.jl:27)
+    p = Problem(tm, tm, opts(bulk_range=(8.0, 10.0), n_random_samples=3), d["tmao"][:1], None, d["cells"][:1], autocorrelation=True)
+    check(p, lists=False)
+
+
+def test_frame_weights():
+    d = namd()
+    for w in ([2.0, 1.0, 0.5], [0.3, 0.0, 0.7]):
+        p = Problem(PROTEIN, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=2), d["protein"], d["tmao"], d["cells"], weights=w)
+        o, _ = p.oracle()
+        eng = p.engine()
+        dev = p.run_engine(eng)
+        eng.close()
+        dyadic = all(float(x) in (0.0, 0.5, 1.0, 2.0) for x in w)
+        assert_counters_equal(dev, o, exact=dyadic, rtol=1e-12)
+
+
+def test_toy_mddf_cross_and_self():
+    """src/mddf.jl:587-624 through the public mddf()/coordination_number() drivers."""
+    t = toy()
+    allat = np.arange(1, 11)
+    fr = t["cross"]
+    protein = cm.AtomSelection([10], nmols=1)
+    water = cm.AtomSelection(np.arange(1, 10), natomspermol=3)
+    for lastframe in (1, 2):
+        tr = cm.ArrayTrajectory(fr, t["cross_cells"], protein, water)
+        o = cm.Options(seed=321, silent=True, n_random_samples=10 ** 4, lastframe=lastframe)
+        R = cm.mddf(tr, o)
+        assert R.volume.total == 27000.0
+        assert np.isclose(R.volume.domain, R.volume.total - R.volume.bulk)
+        assert np.isclose(R.volume.domain, 4 * np.pi / 3 * R.dbulk ** 3, rtol=0.03)
+        assert np.isclose(R.density.solvent_bulk, 2 / R.volume.bulk)
+        assert np.isclose(R.md_count.sum(), 1.0) and np.isclose(R.coordination_number.sum(), 51.0)
+        tr = cm.ArrayTrajectory(fr, t["cross_cells"], protein, water)
+        Cn = cm.coordination_number(tr, o)
+        assert np.array_equal(Cn.md_count, R.md_count) and Cn.volume.total == R.volume.total
+    atom = cm.AtomSelection([1, 2], natomspermol=1)
+    tr = cm.ArrayTrajectory(t["self_monoatomic"], t["self_monoatomic_cells"], atom, atom)
+    R = cm.mddf(tr, cm.Options(seed=321, silent=True, n_random_samples=10 ** 4, lastframe=1))
+    assert R.volume.total == 27000.0 and np.isclose(R.md_count.sum(), 1.0)
+    assert np.isclose(R.density.solute, 2 / R.volume.total)
