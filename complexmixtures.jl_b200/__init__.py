@@ -6,7 +6,7 @@ module name ``cmx_b200``.  Layout:
 
   csrc/            CUDA kernels (sm_100a) + the C-ABI (include/cmx_b200.h) -> libcmx_b200.so
   engine.py        ctypes binding of the C-ABI (what the Julia shim does with ccall)
-  mddf.py          mddf() / coordination_number() drivers (mirror of src/mddf.jl)
+  driver.py        mddf() / coordination_number() drivers (mirror of src/mddf.jl)
   options.py, selection.py, trajectory.py, results.py, contributions.py   host-side mirrors
   synthetic.py     generators of the synthetic benchmark systems named in BASELINE.json
 """
@@ -23,12 +23,8 @@ __all__ = ["Options", "AtomSelection", "SoluteGroup", "SolventGroup", "Trajector
            "cell_from_lengths_angles"]
 
 
-def __getattr__(name):
-    # engine-backed entry points are imported lazily so that the pure-host modules (and the
-    # CPU test-suite) work on machines where the CUDA library has not been built
-    if name in ("mddf", "coordination_number", "Engine", "engine", "synthetic"):
-        import importlib
-        mod = importlib.import_module(f"{__name__}.mddf" if name in ("mddf", "coordination_number") else
-                                      f"{__name__}.engine" if name in ("Engine", "engine") else f"{__name__}.synthetic")
-        return mod if name in ("engine", "synthetic") else getattr(mod, name)
-    raise AttributeError(name)
+from .driver import coordination_number, mddf  # noqa: E402  (the CUDA library itself is loaded lazily)
+from . import engine, synthetic  # noqa: E402
+from .engine import Engine  # noqa: E402
+
+__all__ += ["mddf", "coordination_number", "Engine", "engine", "synthetic"]

@@ -80,7 +80,8 @@ def contributions(R: Result, group, *, type: str = "mddf") -> np.ndarray:
         return np.cumsum(sel)
     if type == "md_count":
         return sel
-    return ANGS3_TO_CM3_PER_MOL * (1 / R.density.solvent_bulk) * (np.cumsum(sel) - np.cumsum(selr))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return ANGS3_TO_CM3_PER_MOL * (1 / np.float64(R.density.solvent_bulk)) * (np.cumsum(sel) - np.cumsum(selr))
 
 
 def coordination_number_of(R: Result, group=None) -> np.ndarray:

@@ -92,6 +92,7 @@ struct cmx_handle {
     bool count_pairs = false, profile = false;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool ev_first_set = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<int> prof_tags;
     size_t prof_used = 0;
     int64_t last_frame = -1;
     Geom last_g{};
@@ -206,12 +207,13 @@ void launch(cmx_handle *h, K kernel, dim3 grid, dim3 block, Args... args) {
     h->stats.kernel_launches++;
 }
 
-cudaEvent_t prof_begin(cmx_handle *h) {
+cudaEvent_t prof_begin(cmx_handle *h, int tag = 0) {
     if (!h->profile) return nullptr;
     if (h->prof_used == h->prof_events.size()) {
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-        h->prof_events.push_back({a, b});
+        h->prof_events.push_back({a, b}); h->prof_tags.push_back(0);
     }
+    h->prof_tags[h->prof_used] = tag;
     cudaEventRecord(h->prof_events[h->prof_used].first, h->s_comp);
     return h->prof_events[h->prof_used].second;
 }
@@ -223,7 +225,10 @@ void prof_end(cmx_handle *h, cudaEvent_t e) {
 void prof_collect(cmx_handle *h) {
     for (size_t k = 0; k < h->prof_used; ++k) {
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, h->prof_events[k].first, h->prof_events[k].second) == cudaSuccess) h->stats.gpu_ms_main += ms;
+        if (cudaEventElapsedTime(&ms, h->prof_events[k].first, h->prof_events[k].second) == cudaSuccess) {
+            h->stats.gpu_ms_main += ms;
+            (h->prof_tags[k] ? h->stats.gpu_ms_search_random : h->stats.gpu_ms_search_real) += ms;
+        }
     }
     h->prof_used = 0;
 }
@@ -301,7 +306,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         long long total = (long long)nrand * nv_mols;
         launch(h, k_filter_rand, dim3((unsigned)((total + 255) / 256)), dim3(256), g, h->P, frame, isolute, skip,
                (const unsigned char *)h->d_cdist.p, (const int *)(sc + 5), h->d_rand_worklist.p, sc + 1);
-        pe = prof_begin(h);
+        pe = prof_begin(h, 1);
         launch_search<true>(h, g, frame, xs, d_solvent, isolute, h->d_rand_worklist.p, sc + 1,
                             c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_def_rand.p, sc + 3, nblk);
         prof_end(h, pe);

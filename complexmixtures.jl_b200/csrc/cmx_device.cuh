@@ -56,7 +56,7 @@ struct MdRec {
     int pad;
 };
 
-// ---- exact fp64 arithmetic (never contracted; same operation order as oracle/cmx_oracle.c) --
+// ---- exact fp64 arithmetic (never contracted; same operation order as the CPU checker in tests) --
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }

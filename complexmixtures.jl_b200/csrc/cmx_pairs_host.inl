@@ -131,7 +131,7 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch(h, k_ref_lists, dim3((nvm + 127) / 128, nrand), dim3(128), g, pg, h->P, frame, -1, d_solute, d_solvent, S.sol, S.solv, S.ref_lists);
         launch(h, k_bulk_compact, dim3(nrand), dim3(512), h->P, frame, (const MdRec *)S.ref_lists, S.bulk_idx, S.n_bulk);
         long long total = (long long)nrand * nvm;
-        ev = prof_begin(h);
+        ev = prof_begin(h, 1);
         launch(h, k_pair_random, dim3((unsigned)((total + 127) / 128)), dim3(128), g, pg, h->P, frame, d_solute, d_solvent, S.sol,
                (const int *)(S.d_radii + 2), (const int *)S.bulk_idx, (const int *)S.n_bulk,
                c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, S.deferred, S.def_count, S.def_cap);

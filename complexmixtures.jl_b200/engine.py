@@ -56,7 +56,8 @@ class CmxCounters(C.Structure):
 class CmxStats(C.Structure):
     _fields_ = [("frames", C.c_int64), ("kernel_launches", C.c_int64), ("deferred", C.c_int64), ("pair_evals", C.c_int64),
                 ("hits_real", C.c_int64), ("hits_random", C.c_int64), ("h2d_bytes", C.c_int64),
-                ("gpu_ms_total", C.c_double), ("gpu_ms_main", C.c_double)]
+                ("gpu_ms_total", C.c_double), ("gpu_ms_main", C.c_double), ("gpu_ms_search_real", C.c_double),
+                ("gpu_ms_search_random", C.c_double)]
 
 
 MD_DTYPE = np.dtype([("within_cutoff", np.int32), ("i", np.int32), ("j", np.int32),

@@ -176,8 +176,9 @@ def _mddf_final_results(R: Result, options: Options) -> Result:
         R.volume.bulk = float(np.sum(R.volume.shell[ibulk - 1: R.nbins]))
     R.density.solvent = R.solvent.nmols / R.volume.total
     R.density.solute = R.solute.nmols / R.volume.total
-    R.density.solvent_bulk = n_solvent_in_bulk / R.volume.bulk if R.volume.bulk != 0 else float("nan")
-    density_fix = R.density.solvent_bulk / R.density.solvent
+    with np.errstate(divide="ignore", invalid="ignore"):   # IEEE semantics as in Julia (Inf/NaN, no exception)
+        R.density.solvent_bulk = float(np.float64(n_solvent_in_bulk) / np.float64(R.volume.bulk))
+    density_fix = np.float64(R.density.solvent_bulk) / np.float64(R.density.solvent)
     return renormalize_(R, density_fix, silent=options.silent)
 
 
@@ -196,13 +197,13 @@ def renormalize_(R: Result, density_fix: float, *, silent: bool = True) -> Resul
     R.mddf = np.zeros(R.nbins)
     R.mddf[pos] = R.md_count[pos] / R.md_count_random[pos]
     with np.errstate(divide="ignore", invalid="ignore"):
-        R.kb = ANGS3_TO_CM3_PER_MOL * (1 / R.density.solvent_bulk) * (R.coordination_number - R.coordination_number_random)
+        R.kb = ANGS3_TO_CM3_PER_MOL * (1 / np.float64(R.density.solvent_bulk)) * (R.coordination_number - R.coordination_number_random)
         posr = R.rdf_count_random > 0.0
         R.rdf = np.zeros(R.nbins)
         R.rdf[posr] = R.rdf_count[posr] / R.rdf_count_random[posr]
         R.sum_rdf_count = np.cumsum(R.rdf_count)
         R.sum_rdf_count_random = np.cumsum(R.rdf_count_random)
-        R.kb_rdf = ANGS3_TO_CM3_PER_MOL * (1 / R.density.solvent_bulk) * (R.sum_rdf_count - R.sum_rdf_count_random)
+        R.kb_rdf = ANGS3_TO_CM3_PER_MOL * (1 / np.float64(R.density.solvent_bulk)) * (R.sum_rdf_count - R.sum_rdf_count_random)
     return R
 
 

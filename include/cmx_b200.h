@@ -95,7 +95,9 @@ typedef struct cmx_stats {
     int64_t hits_real, hits_random; /* molecules within the cutoff counted so far                 */
     int64_t h2d_bytes;         /* bytes copied host->device by cmx_submit_frame                  */
     double gpu_ms_total;       /* device time of all frames (CUDA events on the compute stream)  */
-    double gpu_ms_main;        /* device time spent in the dominant search kernels               */
+    double gpu_ms_main;        /* device time spent in the search kernels (needs option "profile") */
+    double gpu_ms_search_real;   /* ... of which: real-phase search / pair kernel                  */
+    double gpu_ms_search_random; /* ... of which: random-phase search kernel                       */
 } cmx_stats;
 
 const char *cmx_version(void);

@@ -268,7 +268,8 @@ def finalresults(c: dict, *, nmols_solute, nmols_solvent, autocorrelation, n_ran
     else:
         n_bulk = float(np.sum(r.rdf_count[ibulk - 1:]))
         r.volume_bulk = float(np.sum(r.volume_shell[ibulk - 1:]))
-    r.density_solvent_bulk = n_bulk / r.volume_bulk if r.volume_bulk != 0 else float("nan")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r.density_solvent_bulk = np.float64(n_bulk) / np.float64(r.volume_bulk)   # IEEE semantics as in Julia (Inf/NaN, no exception)
     fix = r.density_solvent_bulk / r.density_solvent
     for k in ("md_count_random", "rdf_count_random", "solute_group_count_random", "solvent_group_count_random"):
         setattr(r, k, getattr(r, k) * fix)

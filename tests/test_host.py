@@ -1,0 +1,203 @@
+"""CPU tests of the host-side mirrors and of the C-ABI library (symbols only: no GPU calls)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cmx_b200 as cm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_options_defaults_and_errors():
+    """src/Options.jl:194-220 (testitem "Options")."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = cm.Options()
+    assert (o.dbulk, o.cutoff, o.usecutoff) == (10.0, 10.0, False)
+    o = cm.Options(bulk_range=(10.0, 14.0))
+    assert (o.dbulk, o.cutoff, o.usecutoff) == (10.0, 14.0, True)
+    o = cm.Options(dbulk=8.0, usecutoff=True, silent=True)
+    assert o.cutoff == 12.0
+    for bad in (dict(stride=0), dict(firstframe=3, lastframe=2), dict(n_random_samples=0), dict(bulk_range=(8.0, 12.0), dbulk=8.0),
+                dict(bulk_range=(12.0, 8.0)), dict(dbulk=8.0, cutoff=12.0), dict(bulk_range=(8.0, 12.01)), dict(bulk_range=(1, 2, 3))):
+        with pytest.raises(ValueError):
+            cm.Options(silent=True, **bad)
+
+
+def test_atom_selection_and_group_csr():
+    s = cm.AtomSelection([1, 2, 3, 4, 5, 6], natomspermol=3)
+    assert (s.nmols, s.natomspermol, s.n_groups, s.custom_groups) == (2, 3, 3, False)
+    assert s.group_csr() == (None, None)
+    with pytest.raises(ValueError):
+        cm.AtomSelection([1, 2, 3, 4], natomspermol=3)
+    with pytest.raises(ValueError):
+        cm.AtomSelection([1, 2, 3], nmols=1, group_atom_indices=[[1, 1]], group_names=["a"])
+    with pytest.raises(ValueError):
+        cm.AtomSelection([1, 2, 3], nmols=1, group_atom_indices=[[7]], group_names=["a"])
+    g = cm.AtomSelection([10, 11, 12, 13], nmols=1, group_atom_indices=[[10, 12], [12, 13], [11]], group_names=["a", "b", "c"])
+    off, ids = g.group_csr()
+    assert off.tolist() == [0, 1, 2, 4, 5] and ids.tolist() == [0, 2, 0, 1, 1]
+    assert g.n_groups == 3
+
+
+def test_frame_selection_and_sharding():
+    from cmx_b200.driver import frames_to_compute, shard
+    o = cm.Options(firstframe=2, lastframe=9, stride=3, silent=True)
+    fr = frames_to_compute(o, 9, [1, 1, 1, 1, 0, 1, 1, 2.5, 1])
+    assert fr == [(2, 1.0), (8, 2.5)]                   # frame 5 has zero weight -> skipped (src/mddf.jl:102)
+    todo = [(k, 1.0) for k in range(1, 12)]
+    parts = [shard(todo, r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == todo and max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_cell_conventions():
+    m = cm.cell_from_lengths_angles(10, 11, 12, 90, 90, 90)
+    assert np.array_equal(m, np.diag([10.0, 11.0, 12.0]))
+    m = cm.cell_from_lengths_angles(10, 11, 12, 0, 0, 0)       # DCD without angles (NamdDCD.jl:182-186)
+    assert np.array_equal(m, np.diag([10.0, 11.0, 12.0]))
+    m = cm.cell_from_lengths_angles(10, 11, 12, 80, 85, 70)
+    a, b, c = m[:, 0], m[:, 1], m[:, 2]
+    ang = lambda u, v: np.degrees(np.arccos(u @ v / np.linalg.norm(u) / np.linalg.norm(v)))
+    assert np.allclose([np.linalg.norm(a), np.linalg.norm(b), np.linalg.norm(c)], [10, 11, 12])
+    assert np.allclose([ang(b, c), ang(a, c), ang(a, b)], [80, 85, 70])
+    from cmx_b200.engine import cell_to_c
+    assert cell_to_c(m).reshape(3, 3)[0].tolist() == a.tolist()   # column-major: first 3 doubles = first lattice vector
+
+
+def test_result_json_roundtrip_and_finalresults(tmp_path):
+    """save/load keep the reference's JSON schema; finalresults == the oracle's independent restatement."""
+    from oracle import cmx_oracle as orc
+    from common import Problem, namd
+    d = namd()
+    protein = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+    tmao = cm.AtomSelection(np.arange(1479, 4013), natomspermol=14)
+    opt = cm.Options(bulk_range=(8.0, 10.0), seed=321, silent=True, n_random_samples=5)
+    p = Problem(protein, tmao, opt, d["protein"], d["tmao"], d["cells"])
+    o, _ = p.oracle()
+    tr = cm.ArrayTrajectory(np.concatenate([d["protein"], d["tmao"]], axis=1), d["cells"],
+                            cm.AtomSelection(np.arange(1, 1464), nmols=1), cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14))
+    meta = cm.trajectory_metadata(tr, opt)
+    assert meta.irefatom == 1 and meta.nframes_read == 3
+    from cmx_b200.results import new_result
+    R = new_result(tr, opt, meta)
+    c = o.counters()
+    for k, v in c.items():
+        if k != "volume_total":
+            setattr(R, k, v.copy())
+    R.volume.total = c["volume_total"]
+    R = cm.finalresults(R, opt)
+    f = orc.finalresults(c, nmols_solute=1, nmols_solvent=181, autocorrelation=False, n_random_samples=5, binstep=0.02,
+                         dbulk=8.0, cutoff=10.0, usecutoff=True, Q=3.0)
+    for a, b in ((R.mddf, f.mddf), (R.kb, f.kb), (R.rdf, f.rdf), (R.kb_rdf, f.kb_rdf), (R.coordination_number, f.coordination_number),
+                 (R.volume.shell, f.volume_shell), (R.md_count_random, f.md_count_random)):
+        assert np.allclose(a, b, rtol=1e-13, atol=0)
+    assert np.isclose(R.volume.bulk, f.volume_bulk) and np.isclose(R.density.solvent_bulk, f.density_solvent_bulk)
+    # contributions: solute rows and solvent rows both sum to the total (src/tools/contributions.jl:320-348)
+    # (atom-index selections of a multi-molecule selection are per molecule: contributions.jl:186-193)
+    tot = sum(cm.contributions(R, cm.SolventGroup([int(i)])) for i in R.solvent.indices[:14]) * R.solvent.nmols
+    assert np.allclose(tot, R.mddf, rtol=1e-12)
+    tot = sum(cm.contributions(R, cm.SoluteGroup([int(i)]), type="md_count") for i in R.solute.indices[:50])
+    assert np.allclose(tot, R.solute_group_count[:50].sum(axis=0), rtol=1e-12)
+    assert np.allclose(np.cumsum(R.solute_group_count.sum(axis=0)), R.coordination_number)
+    fn = cm.save(R, str(tmp_path / "r.json"))
+    R2 = cm.load(fn)
+    assert np.array_equal(R2.mddf, R.mddf) and R2.options.cutoff == 10.0 and R2.solvent.natomspermol == 14
+    assert np.array_equal(R2.solute_group_count, R.solute_group_count)
+
+
+def test_loads_reference_json_schema():
+    """a JSON with exactly the reference's fields (as in test/data/NAMD/tmao_tmao.json) loads."""
+    from common import kat
+    g = kat()["golden_json_sums"]["tmao_tmao"]
+    assert g["nbins"] == 500 and g["solute_nmols"] == 181 and g["solute_first_index"] == 1479
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libcmx_b200.so loads and exports every function include/cmx_b200.h declares (no compute call)."""
+    from cmx_b200 import engine
+    hdr = open(os.path.join(ROOT, "include", "cmx_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cmx_[a-z_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    engine.build()
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(engine.EXPORTS) == declared
+    lib.cmx_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.cmx_version()
+    # struct layouts agree with the header (compiled with the host compiler)
+    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats));}'
+    exe = os.path.join("/tmp", f"cmx_sz_{os.getpid()}")
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
+    os.remove(exe)
+    assert sizes == [ctypes.sizeof(engine.CmxConfig), ctypes.sizeof(engine.CmxCounters), engine.MD_DTYPE.itemsize, ctypes.sizeof(engine.CmxStats)]
+
+
+def test_product_has_no_cpu_fallback_and_never_imports_oracle():
+    """the product package must not reference oracle/ and must fail loudly without its CUDA library."""
+    pkg = os.path.join(ROOT, "complexmixtures.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "cmx_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+    from cmx_b200 import engine
+    with pytest.raises(RuntimeError):
+        saved, engine._lib = engine._lib, None
+        try:
+            engine.load_library("/nonexistent/libcmx_b200.so")
+        finally:
+            engine._lib = saved
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import cmx_b200 as cm
+from cmx_b200.driver import frames_to_compute, shard
+from common import namd
+from oracle import cmx_oracle as orc
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+d = namd()
+protein = cm.AtomSelection(np.arange(1, 1464), nmols=1); tmao = cm.AtomSelection(np.arange(1479, 4013), natomspermol=14)
+opt = cm.Options(bulk_range=(8.0, 10.0), seed=321, silent=True, n_random_samples=3)
+todo = frames_to_compute(opt, 3, [])
+mine = shard(todo, rank, world)
+o = orc.Oracle.from_problem(protein, tmao, opt, 1, False)          # stands in for the per-rank engine (CPU test)
+for f, w in mine:
+    o.frame(d["protein"][f - 1], d["tmao"][f - 1], d["cells"][f - 1], weight=w, frame_index=f)
+c = o.counters()
+flat = torch.from_numpy(np.concatenate([c[k].ravel() for k in sorted(c) if k != "volume_total"]).astype(np.int64))
+dist.all_reduce(flat)                                              # the single exchange step (integer sum)
+vol = torch.tensor([c["volume_total"]], dtype=torch.float64); dist.all_reduce(vol)
+if rank == 0:
+    ref = orc.Oracle.from_problem(protein, tmao, opt, 1, False)
+    for f, w in todo:
+        ref.frame(d["protein"][f - 1], d["tmao"][f - 1], d["cells"][f - 1], weight=w, frame_index=f)
+    r = ref.counters()
+    want = np.concatenate([r[k].ravel() for k in sorted(r) if k != "volume_total"]).astype(np.int64)
+    assert np.array_equal(flat.numpy(), want), "sharded + all-reduced counters differ from the single-rank run"
+    assert np.isclose(float(vol[0]), r["volume_total"])
+    print("GLOO_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_frame_sharding_allreduce_gloo_world2(tmp_path):
+    """N>1 host logic on CPU: frames dealt round-robin to 2 ranks, integer counters all-reduced (gloo);
+    the Philox stream is keyed by the global frame index so the result equals the single-rank run."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
