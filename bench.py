@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--n-random-samples", type=int, default=10)
+    ap.add_argument("--group-lanes", type=int, default=0)
     return ap.parse_args()
 
 
@@ -204,7 +205,7 @@ def main():
     iref = irefatom_of(w, xv[0])
     cell = w["system"].cell
     eng = Engine(solute=w["solute"], solvent=w["solvent"], options=opt, irefatom=iref, autocorrelation=w["auto"],
-                 device=local_rank, ring_slots=fps)
+                 device=local_rank, ring_slots=fps, group_lanes=args.group_lanes)
     lib, h = eng.lib, eng.h
     cellc = cm.engine.cell_to_c(cell)
     cellp = cellc.ctypes.data_as(C.POINTER(C.c_double))
@@ -283,6 +284,7 @@ def main():
     total_frames = fps * args.steps * world
     value = total_frames / t_used
     launches = st1["kernel_launches"] - st0["kernel_launches"]
+    deferred = (st1["deferred"] - st0["deferred"]) / max(1, fps * args.steps)
     counters_check = eng.finish()
     hits = float(counters_check["md_count"].sum())
 
@@ -356,7 +358,8 @@ def main():
                 "config": {"workload": w["desc"], "frames_per_step": fps, "frames_per_step_total": fps * world, "scale": args.scale,
                            "n_random_samples": opt.n_random_samples, "bulk_range": [opt.dbulk, opt.cutoff], "nbins": eng.nbins,
                            "l2": f"distinct inputs per step = {fps * (xv[0].nbytes + (0 if w['auto'] else xs[0].nbytes)) / 1e6:.0f} MB (> 126 MB L2)",
-                           "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps)},
+                           "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps),
+                           "deferred_to_exact_per_frame": deferred},
                 "device_ms_per_step": 1e3 * t_dev / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))

@@ -58,8 +58,8 @@ struct cmx_handle {
     int nbins = 0;
     size_t ns_atoms = 0, nv_atoms = 0, in_floats = 0;
     double cut_eff = 0;
-    int Kdiv = 4;
-    double side = 0, cside = 0;
+    int Kdiv = 2;
+    double side = 0, sidex = 0, cside = 0;
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
     std::vector<Slot> ring;
     int next_slot = 0, acquired = -1;
@@ -73,8 +73,12 @@ struct cmx_handle {
     // per-frame scratch (grid path)
     DevBuf<int> d_cell_count, d_cell_start;
     DevBuf<float4> d_sorted;
-    DevBuf<u64> d_occ;
-    DevBuf<unsigned char> d_cdist, d_bulk_flags;
+    DevBuf<u64> d_occ, d_rowmask;
+    DevBuf<float4> d_qpos_real, d_qpos_rand;
+    DevBuf<double> d_xexact;
+    DevBuf<unsigned char> d_edt_x, d_bulk_flags;
+    DevBuf<unsigned short> d_edt_xy;
+    DevBuf<float> d_lbd2;
     DevBuf<MdRec> d_list, d_rand_list, d_list_all;
     DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
     DevBuf<u64> d_def_real, d_def_rand;
@@ -185,8 +189,10 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
         g.gmin[k] = (float)(g.elo[k] - g.ctr[k]);
     }
     g.side = (float)h->side; g.inv_side = (float)(1.0 / h->side);
+    g.sidex = (float)h->sidex; g.inv_sidex = (float)(1.0 / h->sidex);
+    g.cut_hi2 = g.cut_hi * g.cut_hi * (1.0f + 1e-6f);
     g.K = h->Kdiv; g.nrows_tab = (2 * g.K + 1) * (2 * g.K + 1);
-    g.nx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->side) + 1;
+    g.nx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->sidex) + 1;
     g.ny = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->side) + 1;
     g.nz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->side) + 1;
     g.cside = (float)h->cside; g.inv_cside = (float)(1.0 / h->cside);
@@ -194,9 +200,9 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
     g.ncy = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->cside) + 1;
     g.ncz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->cside) + 1;
     g.cw = (g.ncx + 63) / 64;
-    g.d_real = 2;
+    g.rw = (g.nx + 63) / 64;
     g.rmax_bound = h->rmax_bound;
-    g.d_rand_cap = std::min(15, std::max(2, (int)std::ceil((h->cut_eff + tau + h->rmax_bound + 1e-3) / h->cside)));
+    g.dwin = std::min(15, (int)std::ceil((h->cut_eff + tau + h->rmax_bound + 1e-3) / h->cside) + 2);
     if ((double)g.nx * g.ny * g.nz > 2.0e8) return fail(h, CMX_ERR_CELL, "search grid too large for this cell/cutoff");
     return CMX_OK;
 }
@@ -234,20 +240,21 @@ void prof_collect(cmx_handle *h) {
 }
 
 template <bool RANDOM>
-void launch_search(cmx_handle *h, const Geom &g, uint32_t frame, const float *xs, const float *xv, int isolute,
+void launch_search(cmx_handle *h, const Geom &g, const float *xs, const float *xv, const float4 *qpos, const double *xexact,
                    const int *worklist, const int *work_count, MdRec *list, u64 *deferred, int *def_count, int nblocks) {
     u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
     dim3 grid(nblocks), block(256);
 #define CMX_LAUNCH_G(GG)                                                                                             \
-    launch(h, k_search<GG, RANDOM>, grid, block, g, h->P, frame, xs, xv, isolute, h->d_cell_start.p, h->d_sorted.p,  \
-           h->d_cdist.p, worklist, work_count, h->d_bulk_idx.p, h->d_scalars.p + 4, list, deferred, def_count, pe)
+    launch(h, k_search<GG, RANDOM>, grid, block, g, h->P, xs, xv, (const int *)h->d_cell_start.p,                    \
+           (const float4 *)h->d_sorted.p, (const u64 *)h->d_rowmask.p, qpos, xexact, worklist, work_count, list,     \
+           deferred, def_count, pe)
     switch (h->G) {
         case 1: CMX_LAUNCH_G(1); break;
         case 2: CMX_LAUNCH_G(2); break;
         case 4: CMX_LAUNCH_G(4); break;
+        case 8: CMX_LAUNCH_G(8); break;
         case 16: CMX_LAUNCH_G(16); break;
-        case 32: CMX_LAUNCH_G(32); break;
-        default: CMX_LAUNCH_G(8); break;
+        default: CMX_LAUNCH_G(32); break;
     }
 #undef CMX_LAUNCH_G
 }
@@ -261,7 +268,9 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     CK(h->d_cell_count.ensure(ncells + 1, true));
     CK(h->d_cell_start.ensure(ncells + 1));
     CK(h->d_occ.ensure(occ_words));
-    CK(h->d_cdist.ensure(ncc));
+    CK(h->d_edt_x.ensure(ncc)); CK(h->d_edt_xy.ensure(ncc)); CK(h->d_lbd2.ensure(ncc));
+    size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
+    CK(h->d_rowmask.ensure(rowmask_words));
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
     int *sc = h->d_scalars.p;
     for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
@@ -272,24 +281,31 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         else for (int s = 0; s < nrand; ++s) nrand_k += (ref_solute_host(h, frame, (uint32_t)s) == isolute);
         CK(cudaMemsetAsync(sc, 0, 8 * sizeof(int), h->s_comp));
         CK(cudaMemsetAsync(h->d_occ.p, 0, occ_words * sizeof(u64), h->s_comp));
+        CK(cudaMemsetAsync(h->d_rowmask.p, 0, rowmask_words * sizeof(u64), h->s_comp));
         int tb = 128;
         launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->d_cell_count.p,
-               (const int *)nullptr, h->d_occ.p, (float4 *)nullptr);
+               (const int *)nullptr, h->d_occ.p, h->d_rowmask.p, (float4 *)nullptr);
         size_t tmp_bytes = h->d_cub_tmp.n;
         CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp_bytes, h->d_cell_count.p, h->d_cell_start.p, (int)(ncells + 1), h->s_comp));
         h->stats.kernel_launches += 2;
         launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->d_cell_count.p,
-               (const int *)h->d_cell_start.p, h->d_occ.p, h->d_sorted.p);
-        launch(h, k_coarse_dist, dim3((unsigned)((ncc + 127) / 128)), dim3(128), g, (const u64 *)h->d_occ.p, h->d_cdist.p);
+               (const int *)h->d_cell_start.p, h->d_occ.p, h->d_rowmask.p, h->d_sorted.p);
+        launch(h, k_edt_x, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)h->d_occ.p, h->d_edt_x.p);
+        launch(h, k_edt_y, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned char *)h->d_edt_x.p, h->d_edt_xy.p);
+        launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->d_edt_xy.p, h->d_lbd2.p);
         launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
-               (const unsigned char *)h->d_cdist.p, h->d_list.p, h->d_worklist.p, sc + 0, sc + 5);
+               (const float *)h->d_lbd2.p, h->d_list.p, h->d_worklist.p, sc + 0, sc + 5);
         CK(cudaMemcpyAsync(h->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
-        cudaEvent_t pe = prof_begin(h);
         int nblk = h->num_sms * 8;
-        launch_search<false>(h, g, frame, xs, d_solvent, isolute, h->d_worklist.p, sc + 0, h->d_list.p, h->d_def_real.p, sc + 2, nblk);
+        launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->d_lbd2.p,
+               (const int *)h->d_worklist.p, (const int *)(sc + 0), h->d_qpos_real.p);
+        cudaEvent_t pe = prof_begin(h);
+        launch_search<false>(h, g, xs, d_solvent, (const float4 *)h->d_qpos_real.p, (const double *)nullptr, h->d_worklist.p, sc + 0,
+                             h->d_list.p, h->d_def_real.p, sc + 2, nblk);
         prof_end(h, pe);
-        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const int *)h->d_bulk_idx.p,
-               (const int *)(sc + 4), (const u64 *)h->d_def_real.p, (const int *)(sc + 2), h->d_list.p, (MdRec *)nullptr);
+        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
+               (const int *)h->d_cell_start.p, (int)ncells, (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
+               (const u64 *)h->d_def_real.p, (const int *)(sc + 2), h->d_list.p, (MdRec *)nullptr);
         if (c.keep_lists)
             CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
                                cudaMemcpyDeviceToDevice, h->s_comp));
@@ -305,13 +321,17 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         h->stats.kernel_launches += 2;
         long long total = (long long)nrand * nv_mols;
         launch(h, k_filter_rand, dim3((unsigned)((total + 255) / 256)), dim3(256), g, h->P, frame, isolute, skip,
-               (const unsigned char *)h->d_cdist.p, (const int *)(sc + 5), h->d_rand_worklist.p, sc + 1);
+               (const float *)h->d_lbd2.p, (const int *)(sc + 5), h->d_rand_worklist.p, sc + 1);
+        launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, d_solvent, (const float *)h->d_lbd2.p,
+               (const int *)h->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
+               h->d_qpos_rand.p, h->d_xexact.p);
         pe = prof_begin(h, 1);
-        launch_search<true>(h, g, frame, xs, d_solvent, isolute, h->d_rand_worklist.p, sc + 1,
-                            c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_def_rand.p, sc + 3, nblk);
+        launch_search<true>(h, g, xs, d_solvent, (const float4 *)h->d_qpos_rand.p, (const double *)h->d_xexact.p, h->d_rand_worklist.p,
+                            sc + 1, c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_def_rand.p, sc + 3, nblk);
         prof_end(h, pe);
-        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const int *)h->d_bulk_idx.p,
-               (const int *)(sc + 4), (const u64 *)h->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
+        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
+               (const int *)h->d_cell_start.p, (int)ncells, (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
+               (const u64 *)h->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
                c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
         launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)(sc + 3), h->d_stats.p);
     }
@@ -353,7 +373,9 @@ int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, 
     if (seen > 0.f && seen * 1.25f + 0.1f > h->rmax_bound && seen > h->rmax_bound * 0.999f)
         h->rmax_bound = std::max(h->rmax_bound, seen * 1.25f + 0.1f);
     g.rmax_bound = h->rmax_bound;
-    g.d_rand_cap = std::min(15, std::max(2, (int)std::ceil((h->cut_eff + g.tau + h->rmax_bound + 1e-3) / h->cside)));
+    g.dwin = std::min(15, (int)std::ceil((h->cut_eff + g.tau + h->rmax_bound + 1e-3) / h->cside) + 2);
+    // the transform marks everything at >= (dwin-1) cells as "far": only valid while that exceeds the thresholds
+    if ((g.dwin - 1) * h->cside < h->cut_eff + g.tau + h->rmax_bound + 1e-3) g.rmax_bound = -1.f;   // random cull disabled
     if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, h->s_comp)); h->ev_first_set = true; }
     uint32_t frame = (uint32_t)(frame_index & 0xffffffffll);
     if (h->cfg.keep_lists && h->d_rand_list.p) CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, h->s_comp));
@@ -398,7 +420,7 @@ int32_t cmx_destroy(cmx_handle *h) {
     }
     h->d_sol_off.release(); h->d_sol_ids.release(); h->d_solv_off.release(); h->d_solv_ids.release();
     h->d_cnt.release(); h->d_acc.release(); h->d_cell_count.release(); h->d_cell_start.release(); h->d_sorted.release();
-    h->d_occ.release(); h->d_cdist.release(); h->d_bulk_flags.release(); h->d_list.release(); h->d_rand_list.release();
+    h->d_occ.release(); h->d_rowmask.release(); h->d_qpos_real.release(); h->d_qpos_rand.release(); h->d_xexact.release(); h->d_edt_x.release(); h->d_edt_xy.release(); h->d_lbd2.release(); h->d_bulk_flags.release(); h->d_list.release(); h->d_rand_list.release();
     h->d_list_all.release(); h->d_worklist.release(); h->d_rand_worklist.release(); h->d_bulk_idx.release();
     h->d_def_real.release(); h->d_def_rand.release(); h->d_scalars.release(); h->d_stats.release(); h->d_cub_tmp.release();
     pairs_release(h);
@@ -440,13 +462,16 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     h->in_floats = 3 * (c.autocorrelation ? h->nv_atoms : h->ns_atoms + h->nv_atoms);
     h->path = c.path ? c.path : ((c.solute_nmols == 1 || c.solute_natomspermol > 64) ? 1 : 2);
     if (h->path != 1 && h->path != 2) return fail(h, CMX_ERR_ARG, "path must be 0 (auto), 1 (grid) or 2 (molecule pairs)");
-    int G = c.group_lanes ? c.group_lanes : 8;
+    int G = c.group_lanes ? c.group_lanes : 32;
     if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");
     h->G = G;
-    // fine grid: side ~ 3.5 A, K = reach in cells
-    h->Kdiv = std::min(8, std::max(2, (int)std::lround(h->cut_eff / 3.5)));
+    // search grid: rows are (y,z) columns of cells cut/2 wide (25 rows reach the cutoff: one 32-lane probe
+    // batch); along x the cells are ~2.5 A so that a row is scanned over a tight x-span
+    h->Kdiv = 2;
     h->side = (h->cut_eff + 0.02) / h->Kdiv;
-    h->cside = (h->cut_eff + 0.02) / 2.0;
+    h->sidex = (h->cut_eff + 0.02) / std::max(2, (int)std::lround(h->cut_eff / 2.5));
+    // cull grid (distance transform): cut/5
+    h->cside = (h->cut_eff + 0.02) / 5.0;
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_last));
@@ -509,6 +534,9 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     }
     if (h->path == 1) {
         CK(h->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
+        CK(h->d_qpos_real.ensure(h->nv_atoms));
+        CK(h->d_qpos_rand.ensure(std::max<size_t>(nrand * h->nv_atoms, 1)));
+        CK(h->d_xexact.ensure(std::max<size_t>(3 * nrand * h->nv_atoms, 1)));
         // row traversal table: (dy,dz) offsets ordered by a lower bound of the row distance
         int K = h->Kdiv, n = 0;
         struct Row { short dy, dz; float lb; };

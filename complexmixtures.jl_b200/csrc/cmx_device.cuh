@@ -22,13 +22,16 @@ struct Geom {
     int ortho;
     // fine grid over the extended AABB (solute atoms + their periodic images)
     float gmin[3];            // elo - ctr
-    float side, inv_side;
+    float side, inv_side;     // cell size along y and z (a "row" is one (y,z) column of cells)
+    float sidex, inv_sidex;   // cell size along x (finer: rows are scanned over x-spans)
     int nx, ny, nz, K, nrows_tab;
-    // coarse occupancy grid (same box)
+    int rw;                   // 64-bit words per fine-grid row of the occupancy bitmask
+    // cull grid (same box, isotropic): occupancy bitmap -> lower bound of the distance to the solute
     float cside, inv_cside;
-    int ncx, ncy, ncz, cw;    // cw = 64-bit words per coarse x-row
-    int d_real, d_rand_cap;   // Chebyshev dilation radii (coarse cells)
-    float rmax_bound;         // molecule radius bound the coarse distance map was built for
+    int ncx, ncy, ncz, cw;    // cw = 64-bit words per cull-grid x-row
+    int dwin;                 // window (cells) of the distance transform
+    float rmax_bound;         // molecule radius bound the distance transform window was sized for
+    float cut_hi2;            // (cut + tau)^2
     // cutoffs (effective cutoff = usecutoff ? cutoff : dbulk, src/minimum_distances.jl:168)
     float cut, tau;           // tau: fp32 distance uncertainty used to flag near-ties / edge cases
     float cut_lo, cut_hi;     // cut - tau, cut + tau
