@@ -68,6 +68,7 @@ struct cmx_handle {
     DevBuf<int> d_sol_off, d_sol_ids, d_solv_off, d_solv_ids;
     DevBuf<u64> d_cnt;              // integer run accumulators (contiguous block)
     DevBuf<double> d_acc;           // fp64 accumulators, only once the frame weight changes
+    DevBuf<double> d_emit;          // staging of cmx_finish
     size_t cnt_len = 0;
     bool acc_used = false;
     // per-frame scratch (grid path)
@@ -244,10 +245,12 @@ void launch_search(cmx_handle *h, const Geom &g, const float *xs, const float *x
                    const int *worklist, const int *work_count, MdRec *list, u64 *deferred, int *def_count, int nblocks) {
     u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
     dim3 grid(nblocks), block(256);
-#define CMX_LAUNCH_G(GG)                                                                                             \
-    launch(h, k_search<GG, RANDOM>, grid, block, g, h->P, xs, xv, (const int *)h->d_cell_start.p,                    \
+#define CMX_LAUNCH_GC(GG, CC)                                                                                        \
+    launch(h, k_search<GG, RANDOM, CC>, grid, block, g, h->P, xs, xv, (const int *)h->d_cell_start.p,                \
            (const float4 *)h->d_sorted.p, (const u64 *)h->d_rowmask.p, qpos, xexact, worklist, work_count, list,     \
            deferred, def_count, pe)
+#define CMX_LAUNCH_G(GG)                                                                                             \
+    do { if (pe) CMX_LAUNCH_GC(GG, true); else CMX_LAUNCH_GC(GG, false); } while (0)
     switch (h->G) {
         case 1: CMX_LAUNCH_G(1); break;
         case 2: CMX_LAUNCH_G(2); break;
@@ -257,6 +260,7 @@ void launch_search(cmx_handle *h, const Geom &g, const float *xs, const float *x
         default: CMX_LAUNCH_G(32); break;
     }
 #undef CMX_LAUNCH_G
+#undef CMX_LAUNCH_GC
 }
 
 // ---- one frame on the grid path (mddf_frame!, src/mddf.jl:361-429) --------------------------------
@@ -303,7 +307,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch_search<false>(h, g, xs, d_solvent, (const float4 *)h->d_qpos_real.p, (const double *)nullptr, h->d_worklist.p, sc + 0,
                              h->d_list.p, h->d_def_real.p, sc + 2, nblk);
         prof_end(h, pe);
-        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
+        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
                (const int *)h->d_cell_start.p, (int)ncells, (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
                (const u64 *)h->d_def_real.p, (const int *)(sc + 2), h->d_list.p, (MdRec *)nullptr);
         if (c.keep_lists)
@@ -329,7 +333,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch_search<true>(h, g, xs, d_solvent, (const float4 *)h->d_qpos_rand.p, (const double *)h->d_xexact.p, h->d_rand_worklist.p,
                             sc + 1, c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_def_rand.p, sc + 3, nblk);
         prof_end(h, pe);
-        launch(h, k_resolve, dim3(h->num_sms * 4), dim3(128), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
+        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
                (const int *)h->d_cell_start.p, (int)ncells, (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
                (const u64 *)h->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
                c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
@@ -340,6 +344,13 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
 
 __global__ void k_check_overflow(const int *flag, int *sticky) {
     if (threadIdx.x == 0 && *flag) *sticky = 1;
+}
+
+__global__ void k_emit(const u64 *cnt, const double *acc, double *out, size_t n, size_t half_lo, size_t half_hi, double w) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = (k >= half_lo && k < half_hi) ? w / 2 : w;   // src/update_counters.jl:52-53
+    out[k] = (acc ? acc[k] : 0.0) + s * (double)cnt[k];
 }
 
 __global__ void k_fold(const u64 *cnt, double *acc, size_t n, size_t half_lo, size_t half_hi, double w) {
@@ -419,7 +430,7 @@ int32_t cmx_destroy(cmx_handle *h) {
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
     h->d_sol_off.release(); h->d_sol_ids.release(); h->d_solv_off.release(); h->d_solv_ids.release();
-    h->d_cnt.release(); h->d_acc.release(); h->d_cell_count.release(); h->d_cell_start.release(); h->d_sorted.release();
+    h->d_cnt.release(); h->d_acc.release(); h->d_emit.release(); h->d_cell_count.release(); h->d_cell_start.release(); h->d_sorted.release();
     h->d_occ.release(); h->d_rowmask.release(); h->d_qpos_real.release(); h->d_qpos_rand.release(); h->d_xexact.release(); h->d_edt_x.release(); h->d_edt_xy.release(); h->d_lbd2.release(); h->d_bulk_flags.release(); h->d_list.release(); h->d_rand_list.release();
     h->d_list_all.release(); h->d_worklist.release(); h->d_rand_worklist.release(); h->d_bulk_idx.release();
     h->d_def_real.release(); h->d_def_rand.release(); h->d_scalars.release(); h->d_stats.release(); h->d_cub_tmp.release();
@@ -646,21 +657,22 @@ int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
     if (!h || !out) return CMX_ERR_ARG;
     int rc = cmx_sync(h); if (rc) return rc;
     size_t n = h->cnt_len, nb = h->nbins;
-    std::vector<u64> cnt(n);
-    CK(cudaMemcpy(cnt.data(), h->d_cnt.p, sizeof(u64) * n, cudaMemcpyDeviceToHost));
-    std::vector<double> acc;
-    if (h->acc_used) { acc.resize(n); CK(cudaMemcpy(acc.data(), h->d_acc.p, sizeof(double) * n, cudaMemcpyDeviceToHost)); }
     const double w = h->have_weight ? h->cur_weight : 1.0;
     const size_t gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
-    auto emit = [&](double *dst, size_t off, size_t len, double scale) {
-        if (!dst) return;
-        for (size_t k = 0; k < len; ++k) dst[k] = (h->acc_used ? acc[off + k] : 0.0) + scale * (double)cnt[off + k];
+    size_t lo = 4 * nb, hi = 4 * nb + 2 * gs;
+    if (!h->cfg.autocorrelation) lo = hi = 0;
+    CK(h->d_emit.ensure(n));
+    launch(h, k_emit, dim3((unsigned)((n + 255) / 256)), dim3(256), (const u64 *)h->d_cnt.p,
+           (const double *)(h->acc_used ? h->d_acc.p : nullptr), h->d_emit.p, n, lo, hi, w);
+    CK(cudaStreamSynchronize(h->s_comp));
+    auto emit = [&](double *dst, size_t off, size_t len) -> cudaError_t {
+        if (!dst || !len) return cudaSuccess;
+        return cudaMemcpy(dst, h->d_emit.p + off, sizeof(double) * len, cudaMemcpyDeviceToHost);
     };
-    const double wg = h->cfg.autocorrelation ? w / 2 : w;   // src/update_counters.jl:52-53
-    emit(out->md_count, 0, nb, w); emit(out->md_count_random, nb, nb, w);
-    emit(out->rdf_count, 2 * nb, nb, w); emit(out->rdf_count_random, 3 * nb, nb, w);
-    emit(out->solute_group_count, 4 * nb, gs, wg); emit(out->solute_group_count_random, 4 * nb + gs, gs, wg);
-    emit(out->solvent_group_count, 4 * nb + 2 * gs, gv, w); emit(out->solvent_group_count_random, 4 * nb + 2 * gs + gv, gv, w);
+    CK(emit(out->md_count, 0, nb)); CK(emit(out->md_count_random, nb, nb));
+    CK(emit(out->rdf_count, 2 * nb, nb)); CK(emit(out->rdf_count_random, 3 * nb, nb));
+    CK(emit(out->solute_group_count, 4 * nb, gs)); CK(emit(out->solute_group_count_random, 4 * nb + gs, gs));
+    CK(emit(out->solvent_group_count, 4 * nb + 2 * gs, gv)); CK(emit(out->solvent_group_count_random, 4 * nb + 2 * gs + gv, gv));
     out->nbins = h->nbins; out->n_groups_solute = h->cfg.n_groups_solute; out->n_groups_solvent = h->cfg.n_groups_solvent;
     out->volume_total = h->volume_total; out->sum_weights = h->sum_weights;
     return CMX_OK;

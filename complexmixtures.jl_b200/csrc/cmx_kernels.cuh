@@ -267,7 +267,7 @@ __device__ __forceinline__ float group_min(float v, unsigned mask) {
 // the occupied span -- so a batch costs two dependent load latencies instead of two per row.
 // The occupied rows of the batch are then scanned by the whole group with coalesced 16-byte
 // loads of the cell-sorted solute, nearest row first, shrinking the bound after every row.
-template <int G>
+template <int G, bool COUNT>
 __device__ __forceinline__ void search_atom(const Geom &g, const u64 *__restrict__ rowmask,
                                             const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
                                             float px, float py, float pz, int k, float &bound, LaneBest &lb,
@@ -325,7 +325,7 @@ __device__ __forceinline__ void search_atom(const Geom &g, const u64 *__restrict
                 if (d2 < lb.b1) { lb.b2 = lb.b1; lb.b1 = d2; lb.i = __float_as_int(s.w); lb.k = k; }
                 else lb.b2 = fminf(lb.b2, d2);
             }
-            npairs += (unsigned long long)((rb - ra - gl + G - 1) / G);
+            if (COUNT) npairs += (unsigned long long)((rb - ra - gl + G - 1) / G);
             float gb = group_min<G>(lb.b1, mask);
             bound = fminf(bound, gb + g.tol_d2);
         }
@@ -362,7 +362,7 @@ __device__ __forceinline__ int classify(const Geom &g, float b1, float b2) {
     return 1;
 }
 
-template <int G, bool RANDOM>
+template <int G, bool RANDOM, bool COUNT>
 __global__ void __launch_bounds__(256)
 k_search(Geom g, Prob P, const float *__restrict__ xs /* solute molecule, fp32 as read */,
          const float *__restrict__ xv /* solvent of the frame, fp32 as read */,
@@ -387,7 +387,7 @@ k_search(Geom g, Prob P, const float *__restrict__ xs /* solute molecule, fp32 a
         for (int kk = 0; kk < P.nv_apm; ++kk) {
             int k = kk == 0 ? P.iref : (kk <= P.iref ? kk - 1 : kk);
             float4 p = __ldg(&q[k]);
-            if (p.w <= bound) search_atom<G>(g, rowmask, cell_start, sorted, p.x, p.y, p.z, k, bound, lb, mask, gl, npairs);
+            if (p.w <= bound) search_atom<G, COUNT>(g, rowmask, cell_start, sorted, p.x, p.y, p.z, k, bound, lb, mask, gl, npairs);
             if (kk == 0) { int tk; group_combine<G>(lb, mask, gl, F.r1, F.r2, F.ri, tk); }
         }
         group_combine<G>(lb, mask, gl, F.b1, F.b2, F.i, F.k);
@@ -431,7 +431,7 @@ k_search(Geom g, Prob P, const float *__restrict__ xs /* solute molecule, fp32 a
         if (e.flags & 2) count_ref(P, RANDOM, e.dref);
         if (list) list[RANDOM ? (size_t)sample * P.nv_mols + mol : (size_t)mol] = e;
     }
-    if (pair_evals) {
+    if (COUNT && pair_evals) {
         for (int o = 16; o; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
         if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(pair_evals, npairs);
     }
@@ -504,8 +504,9 @@ __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const 
         double ex, ey, ez; mol.get(g, k, ex, ey, ez);
         double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
         float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
+#pragma unroll 4
         for (int p = threadIdx.x; p < nsorted; p += blockDim.x) {
-            float4 s = sorted[p];
+            float4 s = __ldg(&sorted[p]);
             float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
             float d2 = dx * dx + dy * dy + dz * dz;
             mb = fminf(mb, d2);
@@ -530,8 +531,9 @@ __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const 
         double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
         float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
         int j = molidx * P.nv_apm + k;
+#pragma unroll 4
         for (int p = threadIdx.x; p < nsorted; p += blockDim.x) {
-            float4 s = sorted[p];
+            float4 s = __ldg(&sorted[p]);
             float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
             float d2 = dx * dx + dy * dy + dz * dz;
             if (!(d2 <= lim_m || (k == P.iref && d2 <= lim_r))) continue;
@@ -569,12 +571,13 @@ __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(128)
+#define CMX_RESOLVE_THREADS 256
+__global__ void __launch_bounds__(CMX_RESOLVE_THREADS)
 k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const float *__restrict__ xv,
           const float4 *__restrict__ sorted, const int *__restrict__ cell_start, int ncells, const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk_ptr, const u64 *__restrict__ deferred,
           const int *__restrict__ deferred_count, MdRec *__restrict__ list, MdRec *__restrict__ rand_list) {
-    __shared__ ExactBest sh[128];
-    __shared__ float shf[256];
+    __shared__ ExactBest sh[CMX_RESOLVE_THREADS];
+    __shared__ float shf[2 * CMX_RESOLVE_THREADS];
     int count = *deferred_count;
     const int nsorted = cell_start[ncells];
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
