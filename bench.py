@@ -115,7 +115,7 @@ def build_workload(args, rank, world):
     fps = args.frames_per_step
     if fps <= 0:
         in_bytes = 12 * (solvent.natoms if auto else solute.natoms + solvent.natoms)
-        fps = max(16, int(np.ceil(150e6 / in_bytes)))      # > 126 MB of distinct input per step (larger than L2)
+        fps = max(64, int(np.ceil(150e6 / in_bytes)))      # > 126 MB of distinct input per step (larger than L2)
         fps = min(fps, 256)
     # weak scaling: every rank gets its own `fps` frames per step (frame ids interleaved as in the sharded driver)
     frame_ids = [1 + rank + world * k for k in range(fps)]

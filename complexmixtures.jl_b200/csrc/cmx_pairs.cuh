@@ -210,6 +210,9 @@ k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *
         const double ax = sol.anchor[3 * (size_t)a], ay = sol.anchor[3 * (size_t)a + 1], az = sol.anchor[3 * (size_t)a + 2];
         const float ra = sol.rad[a];
         const float reach = pg.cut_hi + ra + ra_solv_max + 1e-3f;
+        // single-image regime: every candidate's atom-pair vectors built from ONE image of the anchor
+        // difference are shorter than half the smallest cell width, hence true minimum images
+        const bool regime = pg.cut_hi + 2.f * (ra + ra_solv_max) + 2e-3f < pg.half_wmin;
         int c0[3]; { double aa[3] = {ax, ay, az}; anchor_cell(g, pg, aa, c0[0], c0[1], c0[2]); }
         int lo[3], cnt[3];
         for (int k = 0; k < 3; ++k) {
@@ -224,8 +227,7 @@ k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *
                    dz = dsub(s_anchor[3 * (size_t)sidx + 2], az);
             min_image64(g, dx, dy, dz);
             float Dx = (float)dx, Dy = (float)dy, Dz = (float)dz;
-            float dn = sqrtf(Dx * Dx + Dy * Dy + Dz * Dz);
-            bool ok = dn + ra + s_rad[sidx] < pg.half_wmin;
+            bool ok = regime;
             PairFound F = eval_pair<SYM>(offa, P.ns_apm, solv.off + (size_t)b * 3 * P.nv_apm, P.nv_apm, Dx, Dy, Dz, P.iref, P.iref);
             npairs += (unsigned long long)P.ns_apm * P.nv_apm;
             finish_pair<SYM>(g, pg, P, F, ok, xs, xv, a, b, deferred, def_count, def_cap);
@@ -308,8 +310,9 @@ __global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fix
         min_image64(g, dx, dy, dz);
         double lim = g.cutd + sol.rad[a] + solv.rad[b] + 1e-3;
         double dn = sqrt(dx * dx + dy * dy + dz * dz);
-        // beyond the single-image regime the anchor test is not a valid bound: evaluate everything
-        if (dn <= lim || dn + sol.rad[a] + solv.rad[b] >= pg.half_wmin)
+        // |v0| > lim implies the true anchor distance > lim whenever lim < half the smallest width;
+        // otherwise the anchor test is not a valid bound: evaluate everything
+        if (dn <= lim || lim >= pg.half_wmin)
             e = exact_list_entry(g, P, xs + (size_t)3 * P.ns_apm * a, xv + (size_t)3 * P.nv_apm * b, b);
     }
     lists[(size_t)s * P.nv_mols + b] = e;
@@ -365,7 +368,7 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, const float *__restri
         min_image64(g, dx, dy, dz);
         double lim = (double)pg.cut_hi + ra + rc + 1e-3;
         double dn2 = dx * dx + dy * dy + dz * dz;
-        if (dn2 > lim * lim && sqrt(dn2) + ra + rc < pg.half_wmin) return;
+        if (dn2 > lim * lim && lim < pg.half_wmin) return;   // true centre distance > lim as well
     }
     uint4 r1 = philox4x32((uint32_t)slot, (uint32_t)s, frame, 1u, P.seed_lo, P.seed_hi);
     int nb = n_bulk[s];
@@ -374,13 +377,15 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, const float *__restri
     const float *offa = sol.off + (size_t)a * 3 * P.ns_apm;
     float b1 = CUDART_INF_F, b2 = CUDART_INF_F, r1_ = CUDART_INF_F, r2_ = CUDART_INF_F;
     int bi = -1, bk = -1, ri = -1;
-    bool ok = true;
+    // single-image regime for atom-to-anchor vectors (see k_pairs)
+    const bool ok = pg.cut_hi + 2.f * ra + 2e-3f < pg.half_wmin;
+    const float skip2 = (pg.cut_hi + ra + 1e-3f) * (pg.cut_hi + ra + 1e-3f);
     for (int k = 0; k < P.nv_apm; ++k) {
         double ex, ey, ez; rm.get(g, k, ex, ey, ez);
         double dx = dsub(ex, ax), dy = dsub(ey, ay), dz = dsub(ez, az);
         min_image64(g, dx, dy, dz);
         float vx = (float)dx, vy = (float)dy, vz = (float)dz;
-        ok &= sqrtf(vx * vx + vy * vy + vz * vz) + ra < pg.half_wmin;
+        if (ok && vx * vx + vy * vy + vz * vz > skip2) continue;   // this atom is beyond the cutoff of every solute atom
         for (int i = 0; i < P.ns_apm; ++i) {
             float qx = vx - offa[3 * i], qy = vy - offa[3 * i + 1], qz = vz - offa[3 * i + 2];
             float d2 = fmaf(qx, qx, fmaf(qy, qy, qz * qz));

@@ -187,3 +187,93 @@ def test_toy_mddf_cross_and_self():
     R = cm.mddf(tr, cm.Options(seed=321, silent=True, n_random_samples=10 ** 4, lastframe=1))
     assert R.volume.total == 27000.0 and np.isclose(R.md_count.sum(), 1.0)
     assert np.isclose(R.density.solute, 2 / R.volume.total)
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the full size of the bench configuration (C2: 100k atoms)
+# ---------------------------------------------------------------------------------------------
+def _c2_problem(nframes=4, nrand=10):
+    from cmx_b200 import synthetic as syn
+    s = syn.config_c2()
+    sol, wat = s.selections["solute"], s.selections["water"]
+    fr = [s.frame(k + 1)[0] for k in range(nframes)]
+    p = Problem(sol, wat, opts(bulk_range=(10.0, 15.0), n_random_samples=nrand), [f[sol.indices - 1] for f in fr],
+                [f[wat.indices - 1] for f in fr], s.cell)
+    return s, p
+
+
+def test_full_size_properties_c2():
+    s, p = _c2_problem()
+    eng = p.engine()
+    full = p.run_engine(eng)
+    # (1) every hit credits exactly one solute atom and one solvent atom type (src/tools/contributions.jl:320-348)
+    assert np.array_equal(full["solute_group_count"].sum(axis=0), full["md_count"])
+    assert np.array_equal(full["solvent_group_count"].sum(axis=0), full["md_count"])
+    assert np.array_equal(full["solute_group_count_random"].sum(axis=0), full["md_count_random"])
+    assert np.array_equal(full["solvent_group_count_random"].sum(axis=0), full["md_count_random"])
+    # (2) a molecule's reference atom is within the cutoff at most as often as the molecule itself
+    assert full["rdf_count"].sum() <= full["md_count"].sum() and np.all(np.cumsum(full["rdf_count"]) <= np.cumsum(full["md_count"]))
+    # (3) additivity over frames / order independence / sharding: two engines with disjoint frame sets sum to the full run
+    eng.reset()
+    a = p.run_engine(eng, frames=[0, 2]); eng.reset()
+    b = p.run_engine(eng, frames=[3, 1]); eng.reset()
+    for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count", "solvent_group_count_random"):
+        assert np.array_equal(a[k] + b[k], full[k]), k
+    # (4) linearity in the frame weight: weight 2 on every frame doubles every counter
+    p2 = Problem(p.solute, p.solvent, p.options, p.xs, p.xv, s.cell, weights=[2.0] * 4)
+    d2 = p2.run_engine(eng)
+    for k in ("md_count", "md_count_random", "solute_group_count"):
+        assert np.array_equal(d2[k], 2 * full[k]), k
+    assert np.isclose(d2["volume_total"], 2 * full["volume_total"])
+    eng.close()
+    # (5) the oracle agrees on one of the frames at this size (bit-exact counters)
+    p1 = Problem(p.solute, p.solvent, p.options, p.xs[:1], p.xv[:1], s.cell)
+    check(p1, lists=False)
+
+
+def test_full_size_residue_groups_c2():
+    """C2's 375-residue custom-group run: group rows are sums of the per-atom rows."""
+    from cmx_b200 import synthetic as syn
+    s, p = _c2_problem(nframes=2, nrand=2)
+    eng = p.engine()
+    per_atom = p.run_engine(eng); eng.close()
+    res = syn.residue_groups(p.solute, 16)
+    pr = Problem(res, p.solvent, p.options, p.xs, p.xv, s.cell)
+    eng = pr.engine()
+    grouped = pr.run_engine(eng); eng.close()
+    assert grouped["solute_group_count"].shape[0] == 375
+    want = per_atom["solute_group_count"].reshape(375, 16, -1).sum(axis=1)
+    assert np.array_equal(grouped["solute_group_count"], want)
+    assert np.array_equal(grouped["md_count"], per_atom["md_count"])
+
+
+def test_final_mddf_and_kb_within_tolerance():
+    """final mddf / KB / random normalisation within 1e-3 relative of the oracle (BASELINE.json north_star)."""
+    d = namd()
+    opt = opts(bulk_range=(8.0, 10.0), n_random_samples=10)
+    p = Problem(PROTEIN, TMAO, opt, d["protein"], d["tmao"], d["cells"])
+    o, _ = p.oracle()
+    ref = orc.finalresults(o.counters(), nmols_solute=1, nmols_solvent=181, autocorrelation=False, n_random_samples=10,
+                           binstep=0.02, dbulk=8.0, cutoff=10.0, usecutoff=True, Q=3.0)
+    tr = cm.ArrayTrajectory(np.concatenate([d["protein"], d["tmao"]], axis=1), d["cells"],
+                            cm.AtomSelection(np.arange(1, 1464), nmols=1), cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14))
+    R = cm.mddf(tr, opt)
+    for a, b in ((R.mddf, ref.mddf), (R.kb, ref.kb), (R.rdf, ref.rdf), (R.kb_rdf, ref.kb_rdf), (R.md_count_random, ref.md_count_random)):
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-12)
+    assert np.isclose(R.volume.total, ref.volume_total) and np.isclose(R.density.solvent_bulk, ref.density_solvent_bulk, rtol=1e-3)
+
+
+def test_error_paths():
+    from cmx_b200.engine import CmxError
+    d = namd()
+    with pytest.raises(CmxError):     # irefatom larger than the molecule (src/Trajectory.jl:191-193)
+        Problem(PROTEIN, TMAO, opts(n_random_samples=1), d["protein"][:1], d["tmao"][:1], d["cells"][:1], irefatom=15).engine()
+    p = Problem(PROTEIN, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=1), d["protein"][:1], d["tmao"][:1], d["cells"][:1])
+    eng = p.engine()
+    with pytest.raises(CmxError):     # cell narrower than 2*cutoff (CellListMap's requirement)
+        eng.submit_arrays(p.xs[0], p.xv[0], np.diag([19.0, 84.0, 84.0]), frame_index=1)
+    with pytest.raises(CmxError):     # zero-weight frames are skipped by the driver, never submitted
+        eng.submit_arrays(p.xs[0], p.xv[0], p.cells[0], frame_index=1, weight=0.0)
+    eng.submit_arrays(p.xs[0], p.xv[0], p.cells[0], frame_index=1)   # the handle is still usable
+    assert eng.finish()["md_count"].sum() == 24.0                    # 24 of 181 TMAO within 10 A (SURVEY section 8c)
+    eng.close()
