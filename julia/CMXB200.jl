@@ -1,0 +1,116 @@
+# CMXB200.jl -- reference-side binding of libcmx_b200.so (what a ComplexMixtures.jl maintainer adds).
+#
+# NOT exercised in this repository's CI: Julia is not available in the build image.  The Python
+# ctypes binding (complexmixtures.jl_b200/engine.py) drives exactly the same C ABI and is what the
+# tests run; this file shows the `ccall` stubs and the replacement of the chunk loop of
+# `mddf(trajectory, options; ...)` (ComplexMixtures.jl src/mddf.jl:263-339).  Everything before the
+# loop (TrajectoryMetaData, Result construction, frame selection) and after it (finalresults!,
+# contributions, ...) is the unmodified reference code.
+module CMXB200
+
+using ComplexMixtures
+import ComplexMixtures: Trajectory, Options, Result, TrajectoryMetaData, opentraj!, closetraj!, firstframe!,
+    nextframe!, getunitcell, convert_unitcell, finalresults!, isautocorrelation
+
+const libcmx = get(ENV, "CMX_B200_LIB", "libcmx_b200.so")
+
+# struct cmx_config (include/cmx_b200.h) -- field order and types must match exactly
+struct CmxConfig
+    struct_size::Int32; device::Int32
+    solute_nmols::Int32; solute_natomspermol::Int32; solvent_nmols::Int32; solvent_natomspermol::Int32
+    autocorrelation::Int32; irefatom::Int32; usecutoff::Int32; n_random_samples::Int32
+    coordination_number_only::Int32; lcell::Int32; n_groups_solute::Int32; n_groups_solvent::Int32
+    path::Int32; ring_slots::Int32; keep_lists::Int32; group_lanes::Int32
+    cutoff::Float64; dbulk::Float64; binstep::Float64; seed::UInt64
+    solute_group_offsets::Ptr{Int32}; solute_group_ids::Ptr{Int32}
+    solvent_group_offsets::Ptr{Int32}; solvent_group_ids::Ptr{Int32}
+end
+
+mutable struct CmxCounters
+    nbins::Int32; n_groups_solute::Int32; n_groups_solvent::Int32; reserved::Int32
+    md_count::Ptr{Float64}; md_count_random::Ptr{Float64}; rdf_count::Ptr{Float64}; rdf_count_random::Ptr{Float64}
+    solute_group_count::Ptr{Float64}; solute_group_count_random::Ptr{Float64}
+    solvent_group_count::Ptr{Float64}; solvent_group_count_random::Ptr{Float64}
+    volume_total::Float64; sum_weights::Float64
+end
+
+check(h, rc) = rc == 0 || error("libcmx_b200: " * unsafe_string(ccall((:cmx_last_error, libcmx), Cstring, (Ptr{Cvoid},), h)))
+
+# CSR "position in the selection -> groups" (restates the search in update_group_count!, src/update_counters.jl:27-33)
+function group_csr(sel::AtomSelection)
+    sel.custom_groups || return (Int32[], Int32[])
+    pos = Dict(a => p for (p, a) in enumerate(sel.indices))
+    per = [Int32[] for _ in sel.indices]
+    for (g, inds) in enumerate(sel.group_atom_indices), a in inds
+        push!(per[pos[a]], Int32(g - 1))
+    end
+    off = Int32[0; cumsum(length.(per))]
+    return off, isempty(per) ? Int32[0] : reduce(vcat, per; init=Int32[])
+end
+
+"""
+    mddf_b200(trajectory, options; frame_weights, coordination_number_only, device=0)
+
+Drop-in for `ComplexMixtures.mddf(trajectory, options; ...)`: same arguments, same `Result`.
+"""
+function mddf_b200(trajectory::Trajectory, options::Options=Options();
+                   frame_weights=Float64[], coordination_number_only=false, low_memory=false, device::Integer=0)
+    tmeta = TrajectoryMetaData(trajectory, options)
+    R = Result(trajectory, options; trajectory_data=tmeta, frame_weights)
+    sol, solv = trajectory.solute, trajectory.solvent
+    soff, sids = group_csr(sol); voff, vids = group_csr(solv)
+    GC.@preserve soff sids voff vids begin
+        cfg = Ref(CmxConfig(sizeof(CmxConfig), device, sol.nmols, sol.natomspermol, solv.nmols, solv.natomspermol,
+            R.autocorrelation, tmeta.irefatom, options.usecutoff, options.n_random_samples, coordination_number_only,
+            options.lcell, tmeta.n_groups_solute, tmeta.n_groups_solvent, 0, 0, 0, 0,
+            options.cutoff, options.dbulk, options.binstep, UInt64(max(options.seed, 0)),
+            sol.custom_groups ? pointer(soff) : C_NULL, sol.custom_groups ? pointer(sids) : C_NULL,
+            solv.custom_groups ? pointer(voff) : C_NULL, solv.custom_groups ? pointer(vids) : C_NULL))
+        href = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:cmx_create, libcmx), Int32, (Ref{CmxConfig}, Ref{Ptr{Cvoid}}), cfg, href)
+        rc == 0 || error(unsafe_string(ccall((:cmx_last_error, libcmx), Cstring, (Ptr{Cvoid},), C_NULL)))
+    end
+    h = href[]
+    ns, nv = sol.nmols * sol.natomspermol, solv.nmols * solv.natomspermol
+    opentraj!(trajectory); firstframe!(trajectory)
+    try
+        for iframe in 1:R.files[1].lastframe_read          # src/mddf.jl:285-338 without threads/locks
+            isfile("stop_complexmixtures") && break        # src/mddf.jl:301-304
+            nextframe!(trajectory)
+            w = R.files[1].frame_weights[iframe]
+            (iframe in options.firstframe:options.stride:R.files[1].lastframe_read && !iszero(w)) || continue
+            ps = Ref{Ptr{Float32}}(); pv = Ref{Ptr{Float32}}()
+            check(h, ccall((:cmx_acquire_frame_buffer, libcmx), Int32, (Ptr{Cvoid}, Ref{Ptr{Float32}}, Ref{Ptr{Float32}}), h, ps, pv))
+            xv = unsafe_wrap(Array, pv[], (3, nv))         # pinned staging slot: fp32, written in place
+            @inbounds for i in 1:nv, k in 1:3; xv[k, i] = trajectory.x_solvent[i][k]; end
+            if !R.autocorrelation
+                xs = unsafe_wrap(Array, ps[], (3, ns))
+                @inbounds for i in 1:ns, k in 1:3; xs[k, i] = trajectory.x_solute[i][k]; end
+            end
+            uc = getunitcell(trajectory)                    # 3x3, columns = lattice vectors -> column-major double[9]
+            cell = Float64[uc[i, j] for i in 1:3, j in 1:3]
+            check(h, ccall((:cmx_submit_frame, libcmx), Int32, (Ptr{Cvoid}, Int64, Float64, Ptr{Float64}), h, iframe, w, cell))
+        end
+    finally
+        closetraj!(trajectory)
+    end
+    # sum!(R, r_chunk) (src/mddf.jl:336): the library writes Float64 arrays laid out like Result; the
+    # Vector{Vector{Float64}} group arrays are filled row by row from one contiguous buffer
+    nb = R.nbins
+    gs = zeros(nb, tmeta.n_groups_solute); gsr = zeros(nb, tmeta.n_groups_solute)
+    gv = zeros(nb, tmeta.n_groups_solvent); gvr = zeros(nb, tmeta.n_groups_solvent)
+    c = CmxCounters(0, 0, 0, 0, pointer(R.md_count), pointer(R.md_count_random), pointer(R.rdf_count), pointer(R.rdf_count_random),
+                    pointer(gs), pointer(gsr), pointer(gv), pointer(gvr), 0.0, 0.0)
+    GC.@preserve R gs gsr gv gvr check(h, ccall((:cmx_finish, libcmx), Int32, (Ptr{Cvoid}, Ref{CmxCounters}), h, c))
+    for g in 1:tmeta.n_groups_solute
+        R.solute_group_count[g] .= @view gs[:, g]; R.solute_group_count_random[g] .= @view gsr[:, g]
+    end
+    for g in 1:tmeta.n_groups_solvent
+        R.solvent_group_count[g] .= @view gv[:, g]; R.solvent_group_count_random[g] .= @view gvr[:, g]
+    end
+    R.volume.total = c.volume_total
+    ccall((:cmx_destroy, libcmx), Int32, (Ptr{Cvoid},), h)
+    return finalresults!(R, options; coordination_number_only)   # unmodified reference normalisation
+end
+
+end # module
