@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--n-random-samples", type=int, default=10)
     ap.add_argument("--group-lanes", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=0)
     return ap.parse_args()
 
 
@@ -206,7 +207,7 @@ def main():
     iref = irefatom_of(w, xv[0])
     cell = w["system"].cell
     eng = Engine(solute=w["solute"], solvent=w["solvent"], options=opt, irefatom=iref, autocorrelation=w["auto"],
-                 device=local_rank, ring_slots=fps, group_lanes=args.group_lanes)
+                 device=local_rank, ring_slots=fps, group_lanes=args.group_lanes, n_streams=args.streams)
     lib, h = eng.lib, eng.h
     cellc = cm.engine.cell_to_c(cell)
     cellp = cellc.ctypes.data_as(C.POINTER(C.c_double))
@@ -259,7 +260,7 @@ def main():
                 raise RuntimeError(lib.cmx_last_error(h).decode())
         eng.sync()
         allreduce_counts()
-        return eng.finish()          # D2H read of the step's result
+        return eng.finish(copy=False)          # D2H read of the step's result (into the engine's pinned result arrays)
 
     # ---- value: frames resident in HBM, device-timed ----
     for _ in range(max(args.warmup, 3)):
@@ -314,7 +315,7 @@ def main():
     # ---- roofline of the dominant kernel (separate profiled pass: CUDA events around the search kernels) ----
     roof = None
     if rank == 0:
-        eng.reset(); eng.set_option("profile", 1)
+        eng.reset(); eng.set_option("active_streams", 1); eng.set_option("profile", 1)   # one frame at a time: clean per-kernel times
         s0 = eng.stats()
         step_device(collective=False)
         s1 = eng.stats()
@@ -329,7 +330,7 @@ def main():
         eng.reset(); eng.set_option("count_pairs", 1)
         step_device(collective=False)
         pe = eng.stats()["pair_evals"] / fps
-        eng.set_option("count_pairs", 0)
+        eng.set_option("count_pairs", 0); eng.set_option("active_streams", 0)
         roof = {"bound": "hbm", "kernel": f"k_search ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": dom_ms / ms_frame if ms_frame > 0 else None,
@@ -360,7 +361,7 @@ def main():
                 "config": {"workload": w["desc"], "frames_per_step": fps, "frames_per_step_total": fps * world, "scale": args.scale,
                            "n_random_samples": opt.n_random_samples, "bulk_range": [opt.dbulk, opt.cutoff], "nbins": eng.nbins,
                            "l2": f"distinct inputs per step = {fps * (xv[0].nbytes + (0 if w['auto'] else xs[0].nbytes)) / 1e6:.0f} MB (> 126 MB L2)",
-                           "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps),
+                           "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps * world),
                            "deferred_to_exact_per_frame": deferred},
                 "device_ms_per_step": 1e3 * t_dev / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}

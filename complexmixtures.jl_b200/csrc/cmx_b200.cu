@@ -49,6 +49,36 @@ struct DevBuf {
 
 }  // namespace
 
+// Everything one in-flight frame needs: its compute stream and scratch buffers.
+struct FrameCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_end = nullptr;
+    DevBuf<int> d_cell_count, d_cell_start;
+    DevBuf<float4> d_sorted;
+    DevBuf<u64> d_occ, d_rowmask;
+    DevBuf<float4> d_qpos_real, d_qpos_rand;
+    DevBuf<double> d_xexact;
+    DevBuf<unsigned char> d_edt_x, d_bulk_flags;
+    DevBuf<unsigned short> d_edt_xy;
+    DevBuf<float> d_lbd2;
+    DevBuf<MdRec> d_list;
+    DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
+    DevBuf<u64> d_def_real, d_def_rand;
+    DevBuf<int> d_scalars;          // [0] work_count, [1] rand_work_count, [2] def_real, [3] def_rand, [4] n_bulk, [5] rmax bits, [8] sticky overflow
+    DevBuf<unsigned char> d_cub_tmp;
+    PairScratch pairs;
+    int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
+    void release() {
+        d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release(); d_rowmask.release();
+        d_qpos_real.release(); d_qpos_rand.release(); d_xexact.release(); d_edt_x.release(); d_bulk_flags.release();
+        d_edt_xy.release(); d_lbd2.release(); d_list.release(); d_worklist.release(); d_rand_worklist.release();
+        d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_scalars.release(); d_cub_tmp.release();
+        if (h_scalars) cudaFreeHost(h_scalars);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
 struct cmx_handle {
     cmx_config cfg{};
     std::string err;
@@ -60,7 +90,8 @@ struct cmx_handle {
     double cut_eff = 0;
     int Kdiv = 2;
     double side = 0, sidex = 0, cside = 0;
-    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaStream_t s_copy = nullptr;
+    int64_t submitted = 0;
     std::vector<Slot> ring;
     int next_slot = 0, acquired = -1;
     // static device data
@@ -71,24 +102,12 @@ struct cmx_handle {
     DevBuf<double> d_emit;          // staging of cmx_finish
     size_t cnt_len = 0;
     bool acc_used = false;
-    // per-frame scratch (grid path)
-    DevBuf<int> d_cell_count, d_cell_start;
-    DevBuf<float4> d_sorted;
-    DevBuf<u64> d_occ, d_rowmask;
-    DevBuf<float4> d_qpos_real, d_qpos_rand;
-    DevBuf<double> d_xexact;
-    DevBuf<unsigned char> d_edt_x, d_bulk_flags;
-    DevBuf<unsigned short> d_edt_xy;
-    DevBuf<float> d_lbd2;
-    DevBuf<MdRec> d_list, d_rand_list, d_list_all;
-    DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
-    DevBuf<u64> d_def_real, d_def_rand;
-    DevBuf<int> d_scalars;          // [0] work_count, [1] rand_work_count, [2] def_real, [3] def_rand, [4] n_bulk, [5] rmax bits, [6..7] spare
+    // per-frame scratch lives in FrameCtx (one per compute stream)
+    DevBuf<MdRec> d_rand_list, d_list_all;   // parity hooks (keep_lists => one stream)
     DevBuf<u64> d_stats;            // [0] pair_evals, [1] deferred total
-    DevBuf<unsigned char> d_cub_tmp;
-    // pair path scratch
-    PairScratch pairs;
-    int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
+    std::vector<FrameCtx *> ctx;    // frames are dealt round-robin to the contexts; kernels of different frames overlap
+    FrameCtx *cur = nullptr;
+    int active_ctx = 0;             // contexts actually used (option "active_streams"; 0 = all)
     float rmax_bound = 0.f;
     // bookkeeping
     double cur_weight = 1.0; bool have_weight = false;
@@ -210,7 +229,7 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
 
 template <class K, class... Args>
 void launch(cmx_handle *h, K kernel, dim3 grid, dim3 block, Args... args) {
-    kernel<<<grid, block, 0, h->s_comp>>>(args...);
+    kernel<<<grid, block, 0, h->cur->stream>>>(args...);
     h->stats.kernel_launches++;
 }
 
@@ -221,12 +240,12 @@ cudaEvent_t prof_begin(cmx_handle *h, int tag = 0) {
         h->prof_events.push_back({a, b}); h->prof_tags.push_back(0);
     }
     h->prof_tags[h->prof_used] = tag;
-    cudaEventRecord(h->prof_events[h->prof_used].first, h->s_comp);
+    cudaEventRecord(h->prof_events[h->prof_used].first, h->cur->stream);
     return h->prof_events[h->prof_used].second;
 }
 void prof_end(cmx_handle *h, cudaEvent_t e) {
     if (!e) return;
-    cudaEventRecord(e, h->s_comp);
+    cudaEventRecord(e, h->cur->stream);
     h->prof_used++;
 }
 void prof_collect(cmx_handle *h) {
@@ -246,8 +265,8 @@ void launch_search(cmx_handle *h, const Geom &g, const float *xs, const float *x
     u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
     dim3 grid(nblocks), block(256);
 #define CMX_LAUNCH_GC(GG, CC)                                                                                        \
-    launch(h, k_search<GG, RANDOM, CC>, grid, block, g, h->P, xs, xv, (const int *)h->d_cell_start.p,                \
-           (const float4 *)h->d_sorted.p, (const u64 *)h->d_rowmask.p, qpos, xexact, worklist, work_count, list,     \
+    launch(h, k_search<GG, RANDOM, CC>, grid, block, g, h->P, xs, xv, (const int *)h->cur->d_cell_start.p,                \
+           (const float4 *)h->cur->d_sorted.p, (const u64 *)h->cur->d_rowmask.p, qpos, xexact, worklist, work_count, list,     \
            deferred, def_count, pe)
 #define CMX_LAUNCH_G(GG)                                                                                             \
     do { if (pe) CMX_LAUNCH_GC(GG, true); else CMX_LAUNCH_GC(GG, false); } while (0)
@@ -269,73 +288,73 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     const int ns_apm = c.solute_natomspermol, nv_mols = c.solvent_nmols;
     size_t ncells = (size_t)g.nx * g.ny * g.nz, ncc = (size_t)g.ncx * g.ncy * g.ncz;
     size_t occ_words = (size_t)g.ncy * g.ncz * g.cw;
-    CK(h->d_cell_count.ensure(ncells + 1, true));
-    CK(h->d_cell_start.ensure(ncells + 1));
-    CK(h->d_occ.ensure(occ_words));
-    CK(h->d_edt_x.ensure(ncc)); CK(h->d_edt_xy.ensure(ncc)); CK(h->d_lbd2.ensure(ncc));
+    CK(h->cur->d_cell_count.ensure(ncells + 1, true));
+    CK(h->cur->d_cell_start.ensure(ncells + 1));
+    CK(h->cur->d_occ.ensure(occ_words));
+    CK(h->cur->d_edt_x.ensure(ncc)); CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
     size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
-    CK(h->d_rowmask.ensure(rowmask_words));
+    CK(h->cur->d_rowmask.ensure(rowmask_words));
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
-    int *sc = h->d_scalars.p;
+    int *sc = h->cur->d_scalars.p;
     for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
         const float *xs = d_solute + (size_t)3 * ns_apm * isolute;
         const int skip = c.autocorrelation ? isolute : -1;
         int nrand_k = 0;
         if (c.solute_nmols == 1) nrand_k = nrand;
         else for (int s = 0; s < nrand; ++s) nrand_k += (ref_solute_host(h, frame, (uint32_t)s) == isolute);
-        CK(cudaMemsetAsync(sc, 0, 8 * sizeof(int), h->s_comp));
-        CK(cudaMemsetAsync(h->d_occ.p, 0, occ_words * sizeof(u64), h->s_comp));
-        CK(cudaMemsetAsync(h->d_rowmask.p, 0, rowmask_words * sizeof(u64), h->s_comp));
+        CK(cudaMemsetAsync(sc, 0, 8 * sizeof(int), h->cur->stream));
+        CK(cudaMemsetAsync(h->cur->d_occ.p, 0, occ_words * sizeof(u64), h->cur->stream));
+        CK(cudaMemsetAsync(h->cur->d_rowmask.p, 0, rowmask_words * sizeof(u64), h->cur->stream));
         int tb = 128;
-        launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->d_cell_count.p,
-               (const int *)nullptr, h->d_occ.p, h->d_rowmask.p, (float4 *)nullptr);
-        size_t tmp_bytes = h->d_cub_tmp.n;
-        CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp_bytes, h->d_cell_count.p, h->d_cell_start.p, (int)(ncells + 1), h->s_comp));
+        launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
+               (const int *)nullptr, h->cur->d_occ.p, h->cur->d_rowmask.p, (float4 *)nullptr);
+        size_t tmp_bytes = h->cur->d_cub_tmp.n;
+        CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), h->cur->stream));
         h->stats.kernel_launches += 2;
-        launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->d_cell_count.p,
-               (const int *)h->d_cell_start.p, h->d_occ.p, h->d_rowmask.p, h->d_sorted.p);
-        launch(h, k_edt_x, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)h->d_occ.p, h->d_edt_x.p);
-        launch(h, k_edt_y, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned char *)h->d_edt_x.p, h->d_edt_xy.p);
-        launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->d_edt_xy.p, h->d_lbd2.p);
+        launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
+               (const int *)h->cur->d_cell_start.p, h->cur->d_occ.p, h->cur->d_rowmask.p, h->cur->d_sorted.p);
+        launch(h, k_edt_x, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)h->cur->d_occ.p, h->cur->d_edt_x.p);
+        launch(h, k_edt_y, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned char *)h->cur->d_edt_x.p, h->cur->d_edt_xy.p);
+        launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->cur->d_edt_xy.p, h->cur->d_lbd2.p);
         launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
-               (const float *)h->d_lbd2.p, h->d_list.p, h->d_worklist.p, sc + 0, sc + 5);
-        CK(cudaMemcpyAsync(h->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->s_comp));
+               (const float *)h->cur->d_lbd2.p, h->cur->d_list.p, h->cur->d_worklist.p, sc + 0, sc + 5);
+        CK(cudaMemcpyAsync(h->cur->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->cur->stream));
         int nblk = h->num_sms * 8;
-        launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->d_lbd2.p,
-               (const int *)h->d_worklist.p, (const int *)(sc + 0), h->d_qpos_real.p);
+        launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->cur->d_lbd2.p,
+               (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos_real.p);
         cudaEvent_t pe = prof_begin(h);
-        launch_search<false>(h, g, xs, d_solvent, (const float4 *)h->d_qpos_real.p, (const double *)nullptr, h->d_worklist.p, sc + 0,
-                             h->d_list.p, h->d_def_real.p, sc + 2, nblk);
+        launch_search<false>(h, g, xs, d_solvent, (const float4 *)h->cur->d_qpos_real.p, (const double *)nullptr, h->cur->d_worklist.p, sc + 0,
+                             h->cur->d_list.p, h->cur->d_def_real.p, sc + 2, nblk);
         prof_end(h, pe);
-        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
-               (const int *)h->d_cell_start.p, (int)ncells, (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->d_def_real.p, (const int *)(sc + 2), h->d_list.p, (MdRec *)nullptr);
+        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
+               (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
+               (const u64 *)h->cur->d_def_real.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr);
         if (c.keep_lists)
-            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
-                               cudaMemcpyDeviceToDevice, h->s_comp));
+            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->cur->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
+                               cudaMemcpyDeviceToDevice, h->cur->stream));
         if (nrand_k == 0) {
             launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)nullptr, h->d_stats.p);
             continue;
         }
         // bulk list of this solute molecule, ascending molecule index (src/mddf.jl:406-415)
-        launch(h, k_bulk_flags, dim3((nv_mols + 255) / 256), dim3(256), h->P, (const MdRec *)h->d_list.p, skip, h->d_bulk_flags.p);
-        tmp_bytes = h->d_cub_tmp.n;
-        CK(cub::DeviceSelect::Flagged(h->d_cub_tmp.p, tmp_bytes, cub::CountingInputIterator<int>(0), h->d_bulk_flags.p,
-                                      h->d_bulk_idx.p, sc + 4, nv_mols, h->s_comp));
+        launch(h, k_bulk_flags, dim3((nv_mols + 255) / 256), dim3(256), h->P, (const MdRec *)h->cur->d_list.p, skip, h->cur->d_bulk_flags.p);
+        tmp_bytes = h->cur->d_cub_tmp.n;
+        CK(cub::DeviceSelect::Flagged(h->cur->d_cub_tmp.p, tmp_bytes, cub::CountingInputIterator<int>(0), h->cur->d_bulk_flags.p,
+                                      h->cur->d_bulk_idx.p, sc + 4, nv_mols, h->cur->stream));
         h->stats.kernel_launches += 2;
         long long total = (long long)nrand * nv_mols;
         launch(h, k_filter_rand, dim3((unsigned)((total + 255) / 256)), dim3(256), g, h->P, frame, isolute, skip,
-               (const float *)h->d_lbd2.p, (const int *)(sc + 5), h->d_rand_worklist.p, sc + 1);
-        launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, d_solvent, (const float *)h->d_lbd2.p,
-               (const int *)h->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
-               h->d_qpos_rand.p, h->d_xexact.p);
+               (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
+        launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, d_solvent, (const float *)h->cur->d_lbd2.p,
+               (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
+               h->cur->d_qpos_rand.p, h->cur->d_xexact.p);
         pe = prof_begin(h, 1);
-        launch_search<true>(h, g, xs, d_solvent, (const float4 *)h->d_qpos_rand.p, (const double *)h->d_xexact.p, h->d_rand_worklist.p,
-                            sc + 1, c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_def_rand.p, sc + 3, nblk);
+        launch_search<true>(h, g, xs, d_solvent, (const float4 *)h->cur->d_qpos_rand.p, (const double *)h->cur->d_xexact.p, h->cur->d_rand_worklist.p,
+                            sc + 1, c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, sc + 3, nblk);
         prof_end(h, pe);
-        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->d_sorted.p,
-               (const int *)h->d_cell_start.p, (int)ncells, (const int *)h->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
+        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
+               (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
+               (const u64 *)h->cur->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
                c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
         launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)(sc + 3), h->d_stats.p);
     }
@@ -360,13 +379,21 @@ __global__ void k_fold(const u64 *cnt, double *acc, size_t n, size_t half_lo, si
     acc[k] += s * (double)cnt[k];
 }
 
+int sync_all(cmx_handle *h) {
+    CK(cudaStreamSynchronize(h->s_copy));
+    for (FrameCtx *x : h->ctx) CK(cudaStreamSynchronize(x->stream));
+    return CMX_OK;
+}
+
 int fold_weight(cmx_handle *h) {
+    { int rc = sync_all(h); if (rc) return rc; }   // every stream adds into the same integer block
     // acc += w * cnt ; cnt = 0  (the counters are sums of frame weights, src/update_counters.jl:47,60)
-    if (!h->acc_used) { CK(h->d_acc.ensure(h->cnt_len, true)); CK(cudaMemsetAsync(h->d_acc.p, 0, sizeof(double) * h->cnt_len, h->s_comp)); h->acc_used = true; }
+    if (!h->acc_used) { CK(h->d_acc.ensure(h->cnt_len, true)); CK(cudaMemsetAsync(h->d_acc.p, 0, sizeof(double) * h->cnt_len, h->cur->stream)); h->acc_used = true; }
     size_t nb = h->nbins, lo = 4 * nb, hi = 4 * nb + 2 * nb * h->cfg.n_groups_solute;
     if (!h->cfg.autocorrelation) lo = hi = 0;
     launch(h, k_fold, dim3((unsigned)((h->cnt_len + 255) / 256)), dim3(256), (const u64 *)h->d_cnt.p, h->d_acc.p, h->cnt_len, lo, hi, h->cur_weight);
-    CK(cudaMemsetAsync(h->d_cnt.p, 0, sizeof(u64) * h->cnt_len, h->s_comp));
+    CK(cudaMemsetAsync(h->d_cnt.p, 0, sizeof(u64) * h->cnt_len, h->cur->stream));
+    CK(cudaStreamSynchronize(h->cur->stream));
     return CMX_OK;
 }
 
@@ -377,19 +404,21 @@ int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, 
     Geom g;
     int rc = build_geom(h, cell, g);
     if (rc) return rc;
+    h->cur = h->ctx[(size_t)(h->submitted++ % (int64_t)(h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size()))];
     if (h->have_weight && weight != h->cur_weight) { rc = fold_weight(h); if (rc) return rc; }
     h->cur_weight = weight; h->have_weight = true;
     // rmax feedback from earlier frames (pinned mirror, may lag)
-    float seen = 0.f; std::memcpy(&seen, h->h_scalars + 5, sizeof(float));
+    float seen = 0.f;
+    for (FrameCtx *x : h->ctx) { float v = 0.f; std::memcpy(&v, x->h_scalars + 5, sizeof(float)); seen = std::max(seen, v); }
     if (seen > 0.f && seen * 1.25f + 0.1f > h->rmax_bound && seen > h->rmax_bound * 0.999f)
         h->rmax_bound = std::max(h->rmax_bound, seen * 1.25f + 0.1f);
     g.rmax_bound = h->rmax_bound;
     g.dwin = std::min(15, (int)std::ceil((h->cut_eff + g.tau + h->rmax_bound + 1e-3) / h->cside) + 2);
     // the transform marks everything at >= (dwin-1) cells as "far": only valid while that exceeds the thresholds
     if ((g.dwin - 1) * h->cside < h->cut_eff + g.tau + h->rmax_bound + 1e-3) g.rmax_bound = -1.f;   // random cull disabled
-    if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, h->s_comp)); h->ev_first_set = true; }
+    if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, h->cur->stream)); h->ev_first_set = true; }
     uint32_t frame = (uint32_t)(frame_index & 0xffffffffll);
-    if (h->cfg.keep_lists && h->d_rand_list.p) CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, h->s_comp));
+    if (h->cfg.keep_lists && h->d_rand_list.p) CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, h->cur->stream));
     h->last_g = g; h->last_dsol = d_solute; h->last_dsolv = d_solvent;
     rc = h->path == 1 ? frame_grid_path(h, d_solute, d_solvent, frame, g)
                       : frame_pair_path(h, d_solute, d_solvent, frame, g);
@@ -421,7 +450,7 @@ const char *cmx_last_error(cmx_handle *h) { return h ? h->err.c_str() : g_create
 int32_t cmx_destroy(cmx_handle *h) {
     if (!h) return CMX_OK;
     cudaSetDevice(h->device);
-    if (h->s_comp) cudaStreamSynchronize(h->s_comp);
+    for (FrameCtx *x : h->ctx) if (x->stream) cudaStreamSynchronize(x->stream);
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
     for (auto &s : h->ring) {
         if (s.h_in) cudaFreeHost(s.h_in);
@@ -430,16 +459,12 @@ int32_t cmx_destroy(cmx_handle *h) {
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
     h->d_sol_off.release(); h->d_sol_ids.release(); h->d_solv_off.release(); h->d_solv_ids.release();
-    h->d_cnt.release(); h->d_acc.release(); h->d_emit.release(); h->d_cell_count.release(); h->d_cell_start.release(); h->d_sorted.release();
-    h->d_occ.release(); h->d_rowmask.release(); h->d_qpos_real.release(); h->d_qpos_rand.release(); h->d_xexact.release(); h->d_edt_x.release(); h->d_edt_xy.release(); h->d_lbd2.release(); h->d_bulk_flags.release(); h->d_list.release(); h->d_rand_list.release();
-    h->d_list_all.release(); h->d_worklist.release(); h->d_rand_worklist.release(); h->d_bulk_idx.release();
-    h->d_def_real.release(); h->d_def_rand.release(); h->d_scalars.release(); h->d_stats.release(); h->d_cub_tmp.release();
-    pairs_release(h);
-    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    h->d_cnt.release(); h->d_acc.release(); h->d_emit.release(); h->d_rand_list.release(); h->d_list_all.release(); h->d_stats.release();
+    for (FrameCtx *x : h->ctx) { h->cur = x; pairs_release(h); x->release(); delete x; }
+    h->ctx.clear(); h->cur = nullptr;
     for (auto &p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (h->ev_first) cudaEventDestroy(h->ev_first);
     if (h->ev_last) cudaEventDestroy(h->ev_last);
-    if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     delete h;
     return CMX_OK;
@@ -484,7 +509,18 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     // cull grid (distance transform): cut/5
     h->cside = (h->cut_eff + 0.02) / 5.0;
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    int nctx = c.n_streams > 0 ? c.n_streams : (h->nv_atoms + h->ns_atoms > 2000000 ? 4 : 8);
+    if (c.keep_lists) nctx = 1;                  // the parity hooks read the scratch of the last frame
+    if (nctx > 16) return fail(h, CMX_ERR_ARG, "n_streams must be <= 16");
+    for (int k = 0; k < nctx; ++k) {
+        FrameCtx *x = new FrameCtx();
+        h->ctx.push_back(x);
+        CK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&x->ev_end));
+        CK(cudaHostAlloc(&x->h_scalars, sizeof(int) * 8, cudaHostAllocDefault));
+        std::memset(x->h_scalars, 0, sizeof(int) * 8);
+    }
+    h->cur = h->ctx[0];
     CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_last));
     int slots = c.ring_slots > 0 ? c.ring_slots : 3;
     h->ring.resize(slots);
@@ -494,8 +530,6 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
     }
-    CK(cudaHostAlloc(&h->h_scalars, sizeof(int) * 8, cudaHostAllocDefault));
-    std::memset(h->h_scalars, 0, sizeof(int) * 8);
     // problem description
     Prob &P = h->P;
     P.ns_mols = c.solute_nmols; P.ns_apm = c.solute_natomspermol; P.nv_mols = c.solvent_nmols; P.nv_apm = c.solvent_natomspermol;
@@ -534,47 +568,52 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     P.gsolv = q; q += nb * c.n_groups_solvent; P.gsolv_r = q;
     // scratch common to both paths
     size_t nvm = c.solvent_nmols, nrand = (size_t)P.nrand;
-    CK(h->d_scalars.ensure(16, true)); CK(h->d_stats.ensure(8, true));
-    CK(h->d_list.ensure(nvm));
-    CK(h->d_bulk_flags.ensure(nvm)); CK(h->d_bulk_idx.ensure(nvm));
-    CK(h->d_worklist.ensure(nvm)); CK(h->d_rand_worklist.ensure(std::max<size_t>(nrand * nvm, 1)));
-    CK(h->d_def_real.ensure(nvm)); CK(h->d_def_rand.ensure(std::max<size_t>(nrand * nvm, 1)));
-    if (c.keep_lists) {
-        if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
-        CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));
+    CK(h->d_stats.ensure(8, true));
+    for (FrameCtx *x_ : h->ctx) {
+        h->cur = x_;
+        CK(h->cur->d_scalars.ensure(16, true)); 
+        CK(h->cur->d_list.ensure(nvm));
+        CK(h->cur->d_bulk_flags.ensure(nvm)); CK(h->cur->d_bulk_idx.ensure(nvm));
+        CK(h->cur->d_worklist.ensure(nvm)); CK(h->cur->d_rand_worklist.ensure(std::max<size_t>(nrand * nvm, 1)));
+        CK(h->cur->d_def_real.ensure(nvm)); CK(h->cur->d_def_rand.ensure(std::max<size_t>(nrand * nvm, 1)));
+        if (c.keep_lists) {
+            if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
+            CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));
+        }
+        if (h->path == 1) {
+            CK(h->cur->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
+            CK(h->cur->d_qpos_real.ensure(h->nv_atoms));
+            CK(h->cur->d_qpos_rand.ensure(std::max<size_t>(nrand * h->nv_atoms, 1)));
+            CK(h->cur->d_xexact.ensure(std::max<size_t>(3 * nrand * h->nv_atoms, 1)));
+            // row traversal table: (dy,dz) offsets ordered by a lower bound of the row distance
+            int K = h->Kdiv, n = 0;
+            struct Row { short dy, dz; float lb; };
+            std::vector<Row> rows;
+            for (int dz = -K; dz <= K; ++dz)
+                for (int dy = -K; dy <= K; ++dy) {
+                    int ay = std::max(std::abs(dy) - 1, 0), az = std::max(std::abs(dz) - 1, 0);
+                    rows.push_back({(short)dy, (short)dz, (float)(ay * ay + az * az)});
+                }
+            std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+                if (a.lb != b.lb) return a.lb < b.lb;
+                return (a.dy * a.dy + a.dz * a.dz) < (b.dy * b.dy + b.dz * b.dz); });
+            n = (int)rows.size();
+            std::vector<short> dy(n), dz(n); std::vector<float> lb(n);
+            // keep a tiny safety factor on the lower bound (the search compares it with slack-free bounds)
+            for (int k = 0; k < n; ++k) { dy[k] = rows[k].dy; dz[k] = rows[k].dz; lb[k] = rows[k].lb * 0.998f; }
+            CK(cudaMemcpyToSymbol(c_row_dy, dy.data(), sizeof(short) * n));
+            CK(cudaMemcpyToSymbol(c_row_dz, dz.data(), sizeof(short) * n));
+            CK(cudaMemcpyToSymbol(c_row_lb, lb.data(), sizeof(float) * n));
+        } else {
+            int rc = pairs_create(h); if (rc) return rc;
+        }
     }
-    if (h->path == 1) {
-        CK(h->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
-        CK(h->d_qpos_real.ensure(h->nv_atoms));
-        CK(h->d_qpos_rand.ensure(std::max<size_t>(nrand * h->nv_atoms, 1)));
-        CK(h->d_xexact.ensure(std::max<size_t>(3 * nrand * h->nv_atoms, 1)));
-        // row traversal table: (dy,dz) offsets ordered by a lower bound of the row distance
-        int K = h->Kdiv, n = 0;
-        struct Row { short dy, dz; float lb; };
-        std::vector<Row> rows;
-        for (int dz = -K; dz <= K; ++dz)
-            for (int dy = -K; dy <= K; ++dy) {
-                int ay = std::max(std::abs(dy) - 1, 0), az = std::max(std::abs(dz) - 1, 0);
-                rows.push_back({(short)dy, (short)dz, (float)(ay * ay + az * az)});
-            }
-        std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
-            if (a.lb != b.lb) return a.lb < b.lb;
-            return (a.dy * a.dy + a.dz * a.dz) < (b.dy * b.dy + b.dz * b.dz); });
-        n = (int)rows.size();
-        std::vector<short> dy(n), dz(n); std::vector<float> lb(n);
-        // keep a tiny safety factor on the lower bound (the search compares it with slack-free bounds)
-        for (int k = 0; k < n; ++k) { dy[k] = rows[k].dy; dz[k] = rows[k].dz; lb[k] = rows[k].lb * 0.998f; }
-        CK(cudaMemcpyToSymbol(c_row_dy, dy.data(), sizeof(short) * n));
-        CK(cudaMemcpyToSymbol(c_row_dz, dz.data(), sizeof(short) * n));
-        CK(cudaMemcpyToSymbol(c_row_lb, lb.data(), sizeof(float) * n));
-    } else {
-        int rc = pairs_create(h); if (rc) return rc;
-    }
+    h->cur = h->ctx[0];
     // cub temp storage sized for the largest call we make
     size_t t1 = 0, t2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, t1, (int *)nullptr, (int *)nullptr, 1 << 28);
     cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, (int)std::max<size_t>(nvm, 1));
-    CK(h->d_cub_tmp.ensure(std::max(t1, t2) + 1024));
+    for (FrameCtx *x_ : h->ctx) CK(x_->d_cub_tmp.ensure(std::max(t1, t2) + 1024));
     CK(cudaDeviceSynchronize());
     return CMX_OK;
 }
@@ -609,12 +648,13 @@ int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, cons
     h->acquired = -1;
     CK(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * h->in_floats, cudaMemcpyHostToDevice, h->s_copy));
     CK(cudaEventRecord(s.h2d_done, h->s_copy));
-    CK(cudaStreamWaitEvent(h->s_comp, s.h2d_done, 0));
+    FrameCtx *next = h->ctx[(size_t)(h->submitted % (int64_t)(h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size()))];
+    CK(cudaStreamWaitEvent(next->stream, s.h2d_done, 0));
     h->stats.h2d_bytes += (int64_t)(sizeof(float) * h->in_floats);
     const float *dsol = s.d_in, *dsolv = h->cfg.autocorrelation ? s.d_in : s.d_in + 3 * h->ns_atoms;
     int rc = submit_common(h, dsol, dsolv, frame_index, weight, cell);
     // the slot is reusable once the frame's kernels are done (even on error, to keep the ring consistent)
-    cudaEventRecord(s.consumed, h->s_comp);
+    cudaEventRecord(s.consumed, next->stream);
     s.in_flight = true;
     return rc;
 }
@@ -631,17 +671,18 @@ int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const 
 int32_t cmx_sync(cmx_handle *h) {
     if (!h) return CMX_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    if (h->ev_first_set) CK(cudaEventRecord(h->ev_last, h->s_comp));
-    CK(cudaStreamSynchronize(h->s_copy));
-    CK(cudaStreamSynchronize(h->s_comp));
+    if (h->ev_first_set) for (FrameCtx *x : h->ctx) CK(cudaEventRecord(x->ev_end, x->stream));
+    { int rc = sync_all(h); if (rc) return rc; }
     if (h->ev_first_set) {
-        float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev_first, h->ev_last));
-        h->stats.gpu_ms_total += ms; h->ev_first_set = false;
+        float best = 0;
+        for (FrameCtx *x : h->ctx) { float ms = 0; if (cudaEventElapsedTime(&ms, h->ev_first, x->ev_end) == cudaSuccess) best = std::max(best, ms); }
+        (void)cudaGetLastError();
+        h->stats.gpu_ms_total += best; h->ev_first_set = false;
     }
     prof_collect(h);
     for (auto &s : h->ring) s.in_flight = false;
     int sticky = 0;
-    CK(cudaMemcpy(&sticky, h->d_scalars.p + 8, sizeof(int), cudaMemcpyDeviceToHost));
+    for (FrameCtx *x : h->ctx) { int v = 0; CK(cudaMemcpy(&v, x->d_scalars.p + 8, sizeof(int), cudaMemcpyDeviceToHost)); sticky |= v; }
     if (sticky) return fail(h, CMX_ERR_STATE, "deferred-pair buffer overflow: too many exactly tied / cutoff-edge pairs in one frame");
     return CMX_OK;
 }
@@ -664,7 +705,7 @@ int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
     CK(h->d_emit.ensure(n));
     launch(h, k_emit, dim3((unsigned)((n + 255) / 256)), dim3(256), (const u64 *)h->d_cnt.p,
            (const double *)(h->acc_used ? h->d_acc.p : nullptr), h->d_emit.p, n, lo, hi, w);
-    CK(cudaStreamSynchronize(h->s_comp));
+    CK(cudaStreamSynchronize(h->cur->stream));
     auto emit = [&](double *dst, size_t off, size_t len) -> cudaError_t {
         if (!dst || !len) return cudaSuccess;
         return cudaMemcpy(dst, h->d_emit.p + off, sizeof(double) * len, cudaMemcpyDeviceToHost);
@@ -697,9 +738,9 @@ int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out) 
         if (!h->last_dsolv) return fail(h, CMX_ERR_STATE, "no frame submitted yet");
         PairGeom pg = make_pair_geom(h, h->last_g);
         launch(h, k_ref_lists, dim3((unsigned)((nvm + 127) / 128), 1), dim3(128), h->last_g, pg, h->P, (uint32_t)h->last_frame, (int)isolute,
-               h->last_dsol, h->last_dsolv, h->pairs.sol, h->pairs.solv, h->d_list.p);
-        CK(cudaStreamSynchronize(h->s_comp));
-        CK(cudaMemcpy(tmp.data(), h->d_list.p, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
+               h->last_dsol, h->last_dsolv, h->cur->pairs.sol, h->cur->pairs.solv, h->cur->d_list.p);
+        CK(cudaStreamSynchronize(h->cur->stream));
+        CK(cudaMemcpy(tmp.data(), h->cur->d_list.p, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
     } else
     CK(cudaMemcpy(tmp.data(), h->d_list_all.p + (size_t)isolute * nvm, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
     for (size_t m = 0; m < nvm; ++m) md_to_abi(tmp[m], out[m]);
@@ -717,6 +758,12 @@ int32_t cmx_read_random_minimum_distances(cmx_handle *h, int32_t sample, cmx_md 
     for (size_t m = 0; m < nvm; ++m) md_to_abi(tmp[m], out[m]);
     return CMX_OK;
 }
+
+int32_t cmx_alloc_pinned(void **ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return CMX_ERR_ARG;
+    return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? CMX_OK : CMX_ERR_CUDA;
+}
+int32_t cmx_free_pinned(void *ptr) { return (!ptr || cudaFreeHost(ptr) == cudaSuccess) ? CMX_OK : CMX_ERR_CUDA; }
 
 int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out) {
     if (!h || !out) return CMX_ERR_ARG;
@@ -745,6 +792,12 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
     std::string n(name);
     if (n == "count_pairs") h->count_pairs = value != 0;
     else if (n == "profile") h->profile = value != 0;
+    else if (n == "active_streams") {
+        int rc = cmx_sync(h); if (rc) return rc;
+        int v = (int)value;
+        if (v < 0 || v > (int)h->ctx.size()) return fail(h, CMX_ERR_ARG, "active_streams out of range");
+        h->active_ctx = v;
+    }
     else if (n == "group_lanes") {
         int G = (int)value;
         if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");

@@ -457,7 +457,7 @@ __global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, const float *__re
 }
 
 __global__ void k_accumulate_stats(const int *__restrict__ a, const int *__restrict__ b, u64 *__restrict__ stats) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) stats[1] += (u64)(a ? *a : 0) + (u64)(b ? *b : 0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&stats[1], (u64)(a ? *a : 0) + (u64)(b ? *b : 0));   // frames overlap on several streams
 }
 
 }  // namespace cmx

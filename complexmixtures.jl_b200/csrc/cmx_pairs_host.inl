@@ -19,14 +19,14 @@ PairGeom make_pair_geom(cmx_handle *h, const Geom &g) {
     pg.tau = (float)tau; pg.cut = (float)h->cut_eff;
     pg.cut_lo = (float)(h->cut_eff - tau); pg.cut_hi = (float)(h->cut_eff + tau);
     // anchor cells: about one reach wide (big cells keep the 32 lanes of a warp busy)
-    double reach = h->cut_eff + h->pairs.ra_sol_bound + h->pairs.ra_solv_bound + 0.05;
+    double reach = h->cut_eff + h->cur->pairs.ra_sol_bound + h->cur->pairs.ra_solv_bound + 0.05;
     for (int k = 0; k < 3; ++k) pg.n[k] = std::min(64, std::max(1, (int)std::floor(pg.w[k] / reach)));
     return pg;
 }
 
 int pairs_create(cmx_handle *h) {
     const cmx_config &c = h->cfg;
-    PairScratch &S = h->pairs;
+    PairScratch &S = h->cur->pairs;
     if (c.solute_natomspermol > 1024) return fail(h, CMX_ERR_ARG, "molecule-pair path: solute_natomspermol > 1024 (use path=1)");
     if (c.solute_nmols >= (1 << 24) || c.solvent_nmols >= (1 << 24) || c.n_random_samples >= 65535)
         return fail(h, CMX_ERR_ARG, "molecule-pair path: too many molecules/samples for the deferred-item encoding");
@@ -63,7 +63,7 @@ int pairs_create(cmx_handle *h) {
 }
 
 void pairs_release(cmx_handle *h) {
-    PairScratch &S = h->pairs;
+    PairScratch &S = h->cur->pairs;
     bool shared = S.sol.anchor == S.solv.anchor;
     if (S.solv.anchor) cudaFree(S.solv.anchor);
     if (S.solv.off) cudaFree(S.solv.off);
@@ -78,25 +78,25 @@ void pairs_release(cmx_handle *h) {
 // molecule preparation of the frame (anchors, offsets, radii); returns after enqueueing
 int pairs_prep(cmx_handle *h, const float *d_solute, const float *d_solvent, const Geom &g) {
     const cmx_config &c = h->cfg;
-    PairScratch &S = h->pairs;
-    CK(cudaMemsetAsync(S.d_radii, 0, sizeof(int) * 4, h->s_comp));
+    PairScratch &S = h->cur->pairs;
+    CK(cudaMemsetAsync(S.d_radii, 0, sizeof(int) * 4, h->cur->stream));
     launch(h, k_mol_prep, dim3((c.solvent_nmols + 127) / 128), dim3(128), g, d_solvent, c.solvent_nmols, c.solvent_natomspermol,
            c.irefatom - 1, S.solv, S.d_radii + 1, S.d_radii + 2);
     if (!c.autocorrelation)
         launch(h, k_mol_prep, dim3((c.solute_nmols + 127) / 128), dim3(128), g, d_solute, c.solute_nmols, c.solute_natomspermol, 0,
                S.sol, S.d_radii + 0, (int *)nullptr);
-    CK(cudaMemcpyAsync(S.h_radii, S.d_radii, sizeof(float) * 4, cudaMemcpyDeviceToHost, h->s_comp));
+    CK(cudaMemcpyAsync(S.h_radii, S.d_radii, sizeof(float) * 4, cudaMemcpyDeviceToHost, h->cur->stream));
     return CMX_OK;
 }
 
 int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent, uint32_t frame, const Geom &g) {
     const cmx_config &c = h->cfg;
-    PairScratch &S = h->pairs;
+    PairScratch &S = h->cur->pairs;
     int rc = pairs_prep(h, d_solute, d_solvent, g);
     if (rc) return rc;
     if (!S.primed) {
         // first frame: the molecule radii are needed to size the anchor cells (one-time sync)
-        CK(cudaStreamSynchronize(h->s_comp));
+        CK(cudaStreamSynchronize(h->cur->stream));
         S.primed = true;
     }
     // radii feedback (pinned mirror; may lag one frame, the kernels use the exact device values)
@@ -104,12 +104,12 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     S.ra_sol_bound = std::max(S.ra_sol_bound, ra_sol); S.ra_solv_bound = std::max(S.ra_solv_bound, ra_solv);
     PairGeom pg = make_pair_geom(h, g);
     size_t ncells = (size_t)pg.n[0] * pg.n[1] * pg.n[2];
-    CK(cudaMemsetAsync(S.def_count, 0, sizeof(int) * 1, h->s_comp));
+    CK(cudaMemsetAsync(S.def_count, 0, sizeof(int) * 1, h->cur->stream));
     int nvm = c.solvent_nmols;
     launch(h, k_anchor_bin<false>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)nullptr,
            (int *)nullptr, (double *)nullptr, (float *)nullptr);
-    size_t tmp_bytes = h->d_cub_tmp.n;
-    CK(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp_bytes, S.cell_count, S.cell_start, (int)(ncells + 1), h->s_comp));
+    size_t tmp_bytes = h->cur->d_cub_tmp.n;
+    CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, S.cell_count, S.cell_start, (int)(ncells + 1), h->cur->stream));
     h->stats.kernel_launches += 2;
     launch(h, k_anchor_bin<true>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)S.cell_start,
            S.sorted_id, S.s_anchor, S.s_rad);
@@ -118,10 +118,10 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
     cudaEvent_t ev = prof_begin(h);
     if (c.autocorrelation) {
-        k_pairs<true><<<nblk, CMX_PAIR_WARPS * 32, smem, h->s_comp>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
+        k_pairs<true><<<nblk, CMX_PAIR_WARPS * 32, smem, h->cur->stream>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
             S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe);
     } else {
-        k_pairs<false><<<nblk, CMX_PAIR_WARPS * 32, smem, h->s_comp>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
+        k_pairs<false><<<nblk, CMX_PAIR_WARPS * 32, smem, h->cur->stream>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
             S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe);
     }
     h->stats.kernel_launches++;
@@ -141,7 +141,7 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
            (const int *)S.n_bulk, (const u64 *)S.deferred, (const int *)S.def_count, S.def_cap,
            c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
     launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)S.def_count, (const int *)nullptr, h->d_stats.p);
-    launch(h, k_check_overflow, dim3(1), dim3(32), (const int *)(S.def_count + 1), h->d_scalars.p + 8);
+    launch(h, k_check_overflow, dim3(1), dim3(32), (const int *)(S.def_count + 1), h->cur->d_scalars.p + 8);
     return CMX_OK;
 }
 

@@ -40,6 +40,7 @@ class CmxConfig(C.Structure):
                 ("n_random_samples", C.c_int32), ("coordination_number_only", C.c_int32), ("lcell", C.c_int32),
                 ("n_groups_solute", C.c_int32), ("n_groups_solvent", C.c_int32), ("path", C.c_int32),
                 ("ring_slots", C.c_int32), ("keep_lists", C.c_int32), ("group_lanes", C.c_int32),
+                ("n_streams", C.c_int32), ("reserved0", C.c_int32),
                 ("cutoff", C.c_double), ("dbulk", C.c_double), ("binstep", C.c_double), ("seed", C.c_uint64),
                 ("solute_group_offsets", C.c_void_p), ("solute_group_ids", C.c_void_p),
                 ("solvent_group_offsets", C.c_void_p), ("solvent_group_ids", C.c_void_p)]
@@ -65,7 +66,8 @@ MD_DTYPE = np.dtype([("within_cutoff", np.int32), ("i", np.int32), ("j", np.int3
 
 EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_acquire_frame_buffer", "cmx_submit_frame",
            "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_finish", "cmx_read_minimum_distances",
-           "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option"]
+           "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option", "cmx_alloc_pinned",
+           "cmx_free_pinned"]
 
 _lib = None
 
@@ -95,6 +97,8 @@ def load_library(path: str = LIB_PATH):
     lib.cmx_get_stats.argtypes = [vp, C.POINTER(CmxStats)]
     lib.cmx_reset.argtypes = [vp]
     lib.cmx_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.cmx_alloc_pinned.argtypes = [C.POINTER(vp), C.c_int64]
+    lib.cmx_free_pinned.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("cmx_version", "cmx_last_error"):
             getattr(lib, name).restype = C.c_int32
@@ -121,7 +125,7 @@ class Engine:
 
     def __init__(self, *, solute, solvent, options, irefatom: int, autocorrelation: bool,
                  coordination_number_only: bool = False, device: int = 0, path: int = 0, keep_lists: bool = False,
-                 ring_slots: int = 3, group_lanes: int = 0):
+                 ring_slots: int = 3, group_lanes: int = 0, n_streams: int = 0):
         self.lib = load_library()
         cfg = CmxConfig()
         cfg.struct_size = C.sizeof(CmxConfig)
@@ -136,6 +140,7 @@ class Engine:
         cfg.lcell = options.lcell
         cfg.n_groups_solute, cfg.n_groups_solvent = solute.n_groups, solvent.n_groups
         cfg.path, cfg.ring_slots, cfg.keep_lists, cfg.group_lanes = path, ring_slots, int(keep_lists), group_lanes
+        cfg.n_streams = n_streams
         cfg.cutoff, cfg.dbulk, cfg.binstep = options.cutoff, options.dbulk, options.binstep
         cfg.seed = options.seed if options.seed > 0 else 0
         self._keep = []
@@ -161,6 +166,9 @@ class Engine:
             raise CmxError(rc, self.lib.cmx_last_error(self.h).decode())
 
     def close(self):
+        if getattr(self, "_pinned", None):
+            self.lib.cmx_free_pinned(self._pinned)
+            self._pinned, self._out = None, None
         if getattr(self, "h", None) is not None and self.h:
             self.lib.cmx_destroy(self.h)
             self.h = None
@@ -211,18 +219,39 @@ class Engine:
         self._ck(self.lib.cmx_counters_device(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def finish(self) -> dict:
-        nb, gs, gv = self.nbins, self.cfg.n_groups_solute, self.cfg.n_groups_solvent
-        out = dict(md_count=np.zeros(nb), md_count_random=np.zeros(nb), rdf_count=np.zeros(nb), rdf_count_random=np.zeros(nb),
-                   solute_group_count=np.zeros((gs, nb)), solute_group_count_random=np.zeros((gs, nb)),
-                   solvent_group_count=np.zeros((gv, nb)), solvent_group_count_random=np.zeros((gv, nb)))
+    def _result_arrays(self):
+        """Result arrays in page-locked memory, allocated once per engine."""
+        if getattr(self, "_out", None) is None:
+            nb, gs, gv = self.nbins, self.cfg.n_groups_solute, self.cfg.n_groups_solvent
+            shapes = dict(md_count=(nb,), md_count_random=(nb,), rdf_count=(nb,), rdf_count_random=(nb,),
+                          solute_group_count=(gs, nb), solute_group_count_random=(gs, nb),
+                          solvent_group_count=(gv, nb), solvent_group_count_random=(gv, nb))
+            total = sum(int(np.prod(sh)) for sh in shapes.values())
+            p = C.c_void_p()
+            if self.lib.cmx_alloc_pinned(C.byref(p), total * 8):
+                raise CmxError(2, "cudaHostAlloc failed")
+            self._pinned = p
+            flat = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(total,))
+            self._out, off = {}, 0
+            for k, sh in shapes.items():
+                n = int(np.prod(sh))
+                self._out[k] = flat[off:off + n].reshape(sh)
+                off += n
+        return self._out
+
+    def finish(self, copy: bool = True) -> dict:
+        """cmx_finish: sync, (all-reduced) counters -> f64 arrays laid out like Result.  With
+        copy=False the returned arrays are views of the engine's pinned buffers (valid until the
+        next finish/close)."""
+        out = self._result_arrays()
         c = CmxCounters()
         for k, v in out.items():
             setattr(c, k, v.ctypes.data)
         self._ck(self.lib.cmx_finish(self.h, C.byref(c)))
-        out["volume_total"] = c.volume_total
-        out["sum_weights"] = c.sum_weights
-        return out
+        res = {k: (v.copy() if copy else v) for k, v in out.items()}
+        res["volume_total"] = c.volume_total
+        res["sum_weights"] = c.sum_weights
+        return res
 
     def minimum_distances(self, isolute: int = 0) -> np.ndarray:
         out = np.zeros(self.nmols_solvent, dtype=MD_DTYPE)

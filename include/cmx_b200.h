@@ -56,6 +56,8 @@ typedef struct cmx_config {
     int32_t ring_slots;               /* pinned staging slots (0 -> 3)                           */
     int32_t keep_lists;               /* keep per-frame minimum-distance lists for cmx_read_*    */
     int32_t group_lanes;              /* lanes cooperating on one solvent molecule (0 -> auto)   */
+    int32_t n_streams;                /* frames in flight on separate compute streams (0 -> 4)   */
+    int32_t reserved0;
     double cutoff;                    /* Options.cutoff                                          */
     double dbulk;                     /* Options.dbulk                                           */
     double binstep;                   /* Options.binstep                                         */
@@ -136,6 +138,10 @@ int32_t cmx_finish(cmx_handle *h, cmx_counters *out);
  * submitted frame (needs keep_lists=1).  isolute is 0-based; sample is the random sample index. */
 int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out /*[solvent_nmols]*/);
 int32_t cmx_read_random_minimum_distances(cmx_handle *h, int32_t sample, cmx_md *out /*[solvent_nmols]*/);
+
+/* Page-locked host memory for the caller's result arrays (cmx_finish then copies at full PCIe speed). */
+int32_t cmx_alloc_pinned(void **ptr, int64_t bytes);
+int32_t cmx_free_pinned(void *ptr);
 
 int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out);
 int32_t cmx_reset(cmx_handle *h);                       /* zero all accumulators and statistics */
