@@ -56,7 +56,8 @@ struct FrameCtx {
     DevBuf<int> d_cell_count, d_cell_start;
     DevBuf<float4> d_sorted;
     DevBuf<u64> d_occ, d_rowmask;
-    DevBuf<float4> d_qpos_real, d_qpos_rand;
+    DevBuf<float4> d_qpos, d_qsorted, d_res;   // query atoms of the current phase: positions, tile order, results
+    DevBuf<int> d_qcell_count, d_qcell_start, d_tile_count;
     DevBuf<double> d_xexact;
     DevBuf<unsigned char> d_edt_x, d_bulk_flags;
     DevBuf<unsigned short> d_edt_xy;
@@ -70,7 +71,7 @@ struct FrameCtx {
     int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
     void release() {
         d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release(); d_rowmask.release();
-        d_qpos_real.release(); d_qpos_rand.release(); d_xexact.release(); d_edt_x.release(); d_bulk_flags.release();
+        d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_tile_count.release(); d_xexact.release(); d_edt_x.release(); d_bulk_flags.release();
         d_edt_xy.release(); d_lbd2.release(); d_list.release(); d_worklist.release(); d_rand_worklist.release();
         d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_scalars.release(); d_cub_tmp.release();
         if (h_scalars) cudaFreeHost(h_scalars);
@@ -89,7 +90,7 @@ struct cmx_handle {
     size_t ns_atoms = 0, nv_atoms = 0, in_floats = 0;
     double cut_eff = 0;
     int Kdiv = 2;
-    double side = 0, sidex = 0, cside = 0;
+    double side = 0, sidex = 0, cside = 0, qside = 0;
     cudaStream_t s_copy = nullptr;
     int64_t submitted = 0;
     std::vector<Slot> ring;
@@ -211,7 +212,7 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
     g.side = (float)h->side; g.inv_side = (float)(1.0 / h->side);
     g.sidex = (float)h->sidex; g.inv_sidex = (float)(1.0 / h->sidex);
     g.cut_hi2 = g.cut_hi * g.cut_hi * (1.0f + 1e-6f);
-    g.K = h->Kdiv; g.nrows_tab = (2 * g.K + 1) * (2 * g.K + 1);
+    g.K = h->Kdiv; g.nrows_tab = 0;
     g.nx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->sidex) + 1;
     g.ny = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->side) + 1;
     g.nz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->side) + 1;
@@ -221,6 +222,10 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
     g.ncz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->cside) + 1;
     g.cw = (g.ncx + 63) / 64;
     g.rw = (g.nx + 63) / 64;
+    g.qside = (float)h->qside; g.inv_qside = (float)(1.0 / h->qside);
+    g.nqx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->qside) + 1;
+    g.nqy = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->qside) + 1;
+    g.nqz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->qside) + 1;
     g.rmax_bound = h->rmax_bound;
     g.dwin = std::min(15, (int)std::ceil((h->cut_eff + tau + h->rmax_bound + 1e-3) / h->cside) + 2);
     if ((double)g.nx * g.ny * g.nz > 2.0e8) return fail(h, CMX_ERR_CELL, "search grid too large for this cell/cutoff");
@@ -259,27 +264,33 @@ void prof_collect(cmx_handle *h) {
     h->prof_used = 0;
 }
 
+// one search phase (real or random) over the molecules of a work list: tile the query atoms, search, combine
 template <bool RANDOM>
-void launch_search(cmx_handle *h, const Geom &g, const float *xs, const float *xv, const float4 *qpos, const double *xexact,
-                   const int *worklist, const int *work_count, MdRec *list, u64 *deferred, int *def_count, int nblocks) {
-    u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
-    dim3 grid(nblocks), block(256);
-#define CMX_LAUNCH_GC(GG, CC)                                                                                        \
-    launch(h, k_search<GG, RANDOM, CC>, grid, block, g, h->P, xs, xv, (const int *)h->cur->d_cell_start.p,                \
-           (const float4 *)h->cur->d_sorted.p, (const u64 *)h->cur->d_rowmask.p, qpos, xexact, worklist, work_count, list,     \
-           deferred, def_count, pe)
-#define CMX_LAUNCH_G(GG)                                                                                             \
-    do { if (pe) CMX_LAUNCH_GC(GG, true); else CMX_LAUNCH_GC(GG, false); } while (0)
-    switch (h->G) {
-        case 1: CMX_LAUNCH_G(1); break;
-        case 2: CMX_LAUNCH_G(2); break;
-        case 4: CMX_LAUNCH_G(4); break;
-        case 8: CMX_LAUNCH_G(8); break;
-        case 16: CMX_LAUNCH_G(16); break;
-        default: CMX_LAUNCH_G(32); break;
-    }
-#undef CMX_LAUNCH_G
-#undef CMX_LAUNCH_GC
+int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv, const int *worklist, const int *work_count,
+                 size_t max_atoms, MdRec *list, u64 *deferred, int *def_count, int tag) {
+    FrameCtx &x = *h->cur;
+    size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
+    // (query positions, res and the per-cell counts were produced by k_gen_*)
+    launch(h, k_tile_count, dim3((unsigned)((nqc + 1 + 255) / 256)), dim3(256), (int)nqc, (const int *)x.d_qcell_count.p, x.d_tile_count.p);
+    size_t tmp_bytes = x.d_cub_tmp.n;
+    CK(cub::DeviceScan::ExclusiveSum(x.d_cub_tmp.p, tmp_bytes, x.d_tile_count.p, x.d_qcell_start.p, (int)(nqc + 1), x.stream));
+    h->stats.kernel_launches += 2;
+    // worst case: every atom in a tile of its own cell's last, partially filled tile
+    size_t slots = std::min(max_atoms + 32 * nqc, x.d_qsorted.n);
+    CK(cudaMemsetAsync(x.d_qsorted.p, 0xff, sizeof(float4) * slots, x.stream));
+    int nb = (int)std::min<size_t>((max_atoms + 255) / 256, (size_t)h->num_sms * 8);
+    launch(h, k_qscatter, dim3(std::max(nb, 1)), dim3(256), g, h->P, work_count, (const float4 *)x.d_qpos.p, x.d_qcell_count.p,
+           (const int *)x.d_qcell_start.p, x.d_qsorted.p);
+    cudaEvent_t pe = prof_begin(h, tag);
+    u64 *pev = h->count_pairs ? h->d_stats.p : nullptr;
+    if (pev) launch(h, k_tile_search<true>, dim3(h->num_sms * 8), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
+                    (const u64 *)x.d_rowmask.p, (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
+    else launch(h, k_tile_search<false>, dim3(h->num_sms * 8), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
+                (const u64 *)x.d_rowmask.p, (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
+    prof_end(h, pe);
+    launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
+           (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_count);
+    return CMX_OK;
 }
 
 // ---- one frame on the grid path (mddf_frame!, src/mddf.jl:361-429) --------------------------------
@@ -294,6 +305,12 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     CK(h->cur->d_edt_x.ensure(ncc)); CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
     size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
     CK(h->cur->d_rowmask.ensure(rowmask_words));
+    size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
+    CK(h->cur->d_qcell_count.ensure(nqc + 1, true)); CK(h->cur->d_qcell_start.ensure(nqc + 1)); CK(h->cur->d_tile_count.ensure(nqc + 1));
+    {   // tile array: atoms + padding of each cell's last tile
+        size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(c.coordination_number_only ? 0 : c.n_random_samples) * h->nv_atoms);
+        CK(h->cur->d_qsorted.ensure(maxq + 32 * nqc));
+    }
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
     int *sc = h->cur->d_scalars.p;
     for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
@@ -319,13 +336,10 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
                (const float *)h->cur->d_lbd2.p, h->cur->d_list.p, h->cur->d_worklist.p, sc + 0, sc + 5);
         CK(cudaMemcpyAsync(h->cur->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->cur->stream));
-        int nblk = h->num_sms * 8;
         launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->cur->d_lbd2.p,
-               (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos_real.p);
-        cudaEvent_t pe = prof_begin(h);
-        launch_search<false>(h, g, xs, d_solvent, (const float4 *)h->cur->d_qpos_real.p, (const double *)nullptr, h->cur->d_worklist.p, sc + 0,
-                             h->cur->d_list.p, h->cur->d_def_real.p, sc + 2, nblk);
-        prof_end(h, pe);
+               (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
+        { int rc = search_phase<false>(h, g, xs, d_solvent, h->cur->d_worklist.p, sc + 0, h->nv_atoms, h->cur->d_list.p,
+                                       h->cur->d_def_real.p, sc + 2, 0); if (rc) return rc; }
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
                (const u64 *)h->cur->d_def_real.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr);
@@ -347,11 +361,9 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
                (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
         launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, d_solvent, (const float *)h->cur->d_lbd2.p,
                (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               h->cur->d_qpos_rand.p, h->cur->d_xexact.p);
-        pe = prof_begin(h, 1);
-        launch_search<true>(h, g, xs, d_solvent, (const float4 *)h->cur->d_qpos_rand.p, (const double *)h->cur->d_xexact.p, h->cur->d_rand_worklist.p,
-                            sc + 1, c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, sc + 3, nblk);
-        prof_end(h, pe);
+               h->cur->d_qpos.p, h->cur->d_xexact.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
+        { int rc = search_phase<true>(h, g, xs, d_solvent, h->cur->d_rand_worklist.p, sc + 1, (size_t)nrand * h->nv_atoms,
+                                      c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, sc + 3, 1); if (rc) return rc; }
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
                (const u64 *)h->cur->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
@@ -501,11 +513,13 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     int G = c.group_lanes ? c.group_lanes : 32;
     if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");
     h->G = G;
-    // search grid: rows are (y,z) columns of cells cut/2 wide (25 rows reach the cutoff: one 32-lane probe
-    // batch); along x the cells are ~2.5 A so that a row is scanned over a tight x-span
-    h->Kdiv = 2;
+    // search grid: a "row" is a (y,z) column of cells cut/4 wide; along x the cells are ~2.5 A so that
+    // a row is scanned over a tight x-span.  Query atoms are tiled in cubic cells of ~6 A (about 20-30
+    // solvent atoms, one warp).
+    h->Kdiv = 4;
     h->side = (h->cut_eff + 0.02) / h->Kdiv;
     h->sidex = (h->cut_eff + 0.02) / std::max(2, (int)std::lround(h->cut_eff / 2.5));
+    h->qside = std::min(8.0, std::max(5.0, h->cut_eff / 2.5));
     // cull grid (distance transform): cut/5
     h->cside = (h->cut_eff + 0.02) / 5.0;
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
@@ -582,28 +596,9 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         }
         if (h->path == 1) {
             CK(h->cur->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
-            CK(h->cur->d_qpos_real.ensure(h->nv_atoms));
-            CK(h->cur->d_qpos_rand.ensure(std::max<size_t>(nrand * h->nv_atoms, 1)));
+            size_t maxq = std::max<size_t>(h->nv_atoms, nrand * h->nv_atoms);
+            CK(h->cur->d_qpos.ensure(maxq)); CK(h->cur->d_qsorted.ensure(maxq)); CK(h->cur->d_res.ensure(maxq));
             CK(h->cur->d_xexact.ensure(std::max<size_t>(3 * nrand * h->nv_atoms, 1)));
-            // row traversal table: (dy,dz) offsets ordered by a lower bound of the row distance
-            int K = h->Kdiv, n = 0;
-            struct Row { short dy, dz; float lb; };
-            std::vector<Row> rows;
-            for (int dz = -K; dz <= K; ++dz)
-                for (int dy = -K; dy <= K; ++dy) {
-                    int ay = std::max(std::abs(dy) - 1, 0), az = std::max(std::abs(dz) - 1, 0);
-                    rows.push_back({(short)dy, (short)dz, (float)(ay * ay + az * az)});
-                }
-            std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
-                if (a.lb != b.lb) return a.lb < b.lb;
-                return (a.dy * a.dy + a.dz * a.dz) < (b.dy * b.dy + b.dz * b.dz); });
-            n = (int)rows.size();
-            std::vector<short> dy(n), dz(n); std::vector<float> lb(n);
-            // keep a tiny safety factor on the lower bound (the search compares it with slack-free bounds)
-            for (int k = 0; k < n; ++k) { dy[k] = rows[k].dy; dz[k] = rows[k].dz; lb[k] = rows[k].lb * 0.998f; }
-            CK(cudaMemcpyToSymbol(c_row_dy, dy.data(), sizeof(short) * n));
-            CK(cudaMemcpyToSymbol(c_row_dz, dz.data(), sizeof(short) * n));
-            CK(cudaMemcpyToSymbol(c_row_lb, lb.data(), sizeof(float) * n));
         } else {
             int rc = pairs_create(h); if (rc) return rc;
         }

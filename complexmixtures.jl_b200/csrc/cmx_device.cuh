@@ -26,6 +26,9 @@ struct Geom {
     float sidex, inv_sidex;   // cell size along x (finer: rows are scanned over x-spans)
     int nx, ny, nz, K, nrows_tab;
     int rw;                   // 64-bit words per fine-grid row of the occupancy bitmask
+    // query cells (cubic): tiles of 32 query atoms are consecutive runs in this order
+    float qside, inv_qside;
+    int nqx, nqy, nqz;
     // cull grid (same box, isotropic): occupancy bitmap -> lower bound of the distance to the solute
     float cside, inv_cside;
     int ncx, ncy, ncz, cw;    // cw = 64-bit words per cull-grid x-row

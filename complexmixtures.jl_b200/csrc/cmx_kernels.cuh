@@ -11,23 +11,20 @@
 //      (cell-sorted float4 {x,y,z,index}); a coarse bitmap of occupied cells is turned into a
 //      Chebyshev distance map;
 //   2. solvent molecules are culled with the distance map; survivors go to a work list;
-//   3. a group of G lanes owns one surviving molecule and runs, atom by atom, a pruned
-//      nearest-neighbour search over grid rows ordered by distance (fp32, vector loads of the
-//      cell-sorted solute), keeping best / second-best squared distances;
+//   3. the atoms of the surviving molecules are binned into compact tiles of 32 query atoms; one
+//      warp owns a tile, every lane one query, and all lanes walk the same solute atoms of the
+//      occupied grid rows nearest-first (fp32, broadcast vector loads of the cell-sorted solute),
+//      keeping best / second-best squared distances; a per-molecule kernel combines the atoms;
 //   4. the winning pair is re-evaluated in fp64 with the reference's minimum-image arithmetic and
 //      histogrammed; molecules whose fp32 result is ambiguous (near-tie, cutoff edge) are deferred to
 //      an exact fp64 resolve kernel, so the counts equal the fp64 oracle's bit for bit.
-//   The random phase regenerates every random molecule from Philox counters inside the same
-//   search kernel; the random box is never materialised.
+//   The random phase generates a random molecule from its Philox counters only if its centre
+//   survives the cull; the random box as a whole is never materialised.
 #pragma once
 #include "cmx_device.cuh"
 
 namespace cmx {
 
-#define CMX_MAX_ROWTAB 289   // (2*8+1)^2
-__constant__ short c_row_dy[CMX_MAX_ROWTAB];
-__constant__ short c_row_dz[CMX_MAX_ROWTAB];
-__constant__ float c_row_lb[CMX_MAX_ROWTAB];   // lower bound of the row distance^2, in units of side^2
 
 // ---------------------------------------------------------------------------------------------
 // K1/K3: bin the solute molecule (plus periodic images inside the extended box) into the grid
@@ -193,33 +190,48 @@ __global__ void k_filter_real(Geom g, Prob P, const float *__restrict__ xv, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6a: query positions of the work-list molecules.  Real phase: wrapped fp32 positions of the
-// frame's atoms.  Random phase: the random molecules that survived the centre cull are generated
-// (Philox + rigid move, fp64) and stored as exact fp64 + wrapped fp32 positions; culled placements
-// are never materialised.
+// K6a: query atoms of the work-list molecules.  Real phase: wrapped fp32 positions of the frame's
+// atoms.  Random phase: the random molecules that survived the centre cull are generated (Philox +
+// rigid move, fp64) and stored as exact fp64 + wrapped fp32 positions; culled placements are never
+// materialised.  Every query atom that can be within the cutoff (distance-transform bound) is
+// counted into a cubic "query cell" so that the search can work on spatially compact tiles.
 // ---------------------------------------------------------------------------------------------
-// .w carries the lower bound (squared) of the distance from the atom to the solute
-__device__ __forceinline__ float4 query_pos(const Geom &g, const float *__restrict__ lbd2, double ex, double ey, double ez) {
-    double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
-    float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
-    return make_float4(px, py, pz, cull_lb2(g, lbd2, px, py, pz));
+__device__ __forceinline__ int query_cell_of(const Geom &g, float px, float py, float pz) {
+    int cx = min(max((int)floorf((px - g.gmin[0]) * g.inv_qside), 0), g.nqx - 1);
+    int cy = min(max((int)floorf((py - g.gmin[1]) * g.inv_qside), 0), g.nqy - 1);
+    int cz = min(max((int)floorf((pz - g.gmin[2]) * g.inv_qside), 0), g.nqz - 1);
+    return (cz * g.nqy + cy) * g.nqx + cx;
 }
 
-__global__ void k_gen_real(Geom g, Prob P, const float *__restrict__ xv, const float *__restrict__ cdist,
-                           const int *__restrict__ worklist, const int *__restrict__ work_count, float4 *__restrict__ qpos) {
+// position (fp32, grid-relative) + lower bound of its squared distance to the solute; results reset
+__device__ __forceinline__ void emit_query(const Geom &g, const float *__restrict__ lbd2, double ex, double ey, double ez,
+                                           size_t qid, float4 *__restrict__ qpos, float4 *__restrict__ res,
+                                           int *__restrict__ qcell_count) {
+    double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
+    float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
+    float lb = cull_lb2(g, lbd2, px, py, pz);
+    qpos[qid] = make_float4(px, py, pz, lb);
+    res[qid] = make_float4(CUDART_INF_F, CUDART_INF_F, __int_as_float(-1), 0.f);
+    if (lb <= g.cut_hi2) atomicAdd(&qcell_count[query_cell_of(g, px, py, pz)], 1);
+}
+
+__global__ void k_gen_real(Geom g, Prob P, const float *__restrict__ xv, const float *__restrict__ lbd2,
+                           const int *__restrict__ worklist, const int *__restrict__ work_count, float4 *__restrict__ qpos,
+                           float4 *__restrict__ res, int *__restrict__ qcell_count) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)(*work_count) * P.nv_apm;
     for (; t < total; t += (long long)gridDim.x * blockDim.x) {
         int w = (int)(t / P.nv_apm), k = (int)(t - (long long)w * P.nv_apm);
         const float *x = xv + ((size_t)worklist[w] * P.nv_apm + k) * 3;
-        qpos[t] = query_pos(g, cdist, (double)x[0], (double)x[1], (double)x[2]);
+        emit_query(g, lbd2, (double)x[0], (double)x[1], (double)x[2], (size_t)t, qpos, res, qcell_count);
     }
 }
 
 __global__ void __launch_bounds__(128)
-k_gen_rand(Geom g, Prob P, uint32_t frame, const float *__restrict__ xv, const float *__restrict__ cdist,
+k_gen_rand(Geom g, Prob P, uint32_t frame, const float *__restrict__ xv, const float *__restrict__ lbd2,
            const int *__restrict__ worklist, const int *__restrict__ work_count, const int *__restrict__ bulk_idx,
-           const int *__restrict__ n_bulk_ptr, float4 *__restrict__ qpos, double *__restrict__ xexact) {
+           const int *__restrict__ n_bulk_ptr, float4 *__restrict__ qpos, double *__restrict__ xexact,
+           float4 *__restrict__ res, int *__restrict__ qcell_count) {
     const int count = *work_count;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
         int item = worklist[w];
@@ -233,123 +245,157 @@ k_gen_rand(Geom g, Prob P, uint32_t frame, const float *__restrict__ xv, const f
             double ex, ey, ez; rm.get(g, k, ex, ey, ez);
             size_t o = (size_t)w * P.nv_apm + k;
             xexact[3 * o] = ex; xexact[3 * o + 1] = ey; xexact[3 * o + 2] = ez;
-            qpos[o] = query_pos(g, cdist, ex, ey, ez);
+            emit_query(g, lbd2, ex, ey, ez, o, qpos, res, qcell_count);
+        }
+    }
+}
+
+// tiles never straddle query cells: a cell with n query atoms owns ceil(n/32) tiles
+__global__ void k_tile_count(int nqcells, const int *__restrict__ qcell_count, int *__restrict__ tile_count) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= nqcells) tile_count[c] = c < nqcells ? (qcell_count[c] + 31) >> 5 : 0;
+}
+
+// scatter the counted query atoms into their cell's tiles: qsorted[tile*32 + rank] = {x, y, z, query id};
+// the unused slots of a cell's last tile keep the id -1 (the array is pre-filled with 0xff bytes)
+__global__ void k_qscatter(Geom g, Prob P, const int *__restrict__ work_count, const float4 *__restrict__ qpos,
+                           int *__restrict__ qcell_count, const int *__restrict__ tile_start, float4 *__restrict__ qsorted) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)(*work_count) * P.nv_apm;
+    for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+        float4 q = qpos[t];
+        if (q.w <= g.cut_hi2) {
+            int c = query_cell_of(g, q.x, q.y, q.z);
+            size_t slot = (size_t)tile_start[c] * 32 + (size_t)(atomicSub(&qcell_count[c], 1) - 1);
+            qsorted[slot] = make_float4(q.x, q.y, q.z, __int_as_float((int)t));
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6: the search.  G lanes per molecule.
+// K6: the search.  One warp per tile of 32 query atoms that are neighbours in space (consecutive in
+// query-cell order).  Every lane owns one query; all lanes walk the SAME solute atoms (broadcast
+// 16-byte loads of the cell-sorted solute), so there is no divergence and one row probe serves 32
+// queries.  Rows of the solute grid inside the tile's reach are probed in lane-parallel (occupancy
+// bitmask), then visited nearest-first; after every row the tile bound shrinks to the largest
+// best-distance of its lanes.  Each lane keeps best / second-best squared distance and the solute
+// atom of the best: res[query] = {b1, b2, atom}.
 // ---------------------------------------------------------------------------------------------
-struct LaneBest {
-    float b1, b2;   // best and second-best squared distance seen by this lane
-    int i, k;       // solute atom index and solvent-molecule atom of b1
-};
+__device__ __forceinline__ int fkey(float x) { int i = __float_as_int(x); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float warp_minf(float x) { return fkey_inv(__reduce_min_sync(0xffffffffu, fkey(x))); }
+__device__ __forceinline__ float warp_maxf(float x) { return fkey_inv(__reduce_max_sync(0xffffffffu, fkey(x))); }
 
-template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    if constexpr (G == 32) return 0xffffffffu;
-    else {
-        int lane = threadIdx.x & 31;
-        return ((1u << G) - 1u) << (lane & ~(G - 1));
-    }
-}
-template <int G>
-__device__ __forceinline__ float group_min(float v, unsigned mask) {
-#pragma unroll
-    for (int o = G / 2; o; o >>= 1) v = fminf(v, __shfl_xor_sync(mask, v, o));
-    return v;
-}
-
-// Nearest solute atoms of one query atom.  The (dy,dz) rows of the fine grid are taken in batches
-// of G in order of increasing distance: every lane probes ONE row of the batch -- occupancy
-// bitmask (one 8-byte load tells which cells of the row hold atoms), then the cell_start pair of
-// the occupied span -- so a batch costs two dependent load latencies instead of two per row.
-// The occupied rows of the batch are then scanned by the whole group with coalesced 16-byte
-// loads of the cell-sorted solute, nearest row first, shrinking the bound after every row.
-template <int G, bool COUNT>
-__device__ __forceinline__ void search_atom(const Geom &g, const u64 *__restrict__ rowmask,
-                                            const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-                                            float px, float py, float pz, int k, float &bound, LaneBest &lb,
-                                            unsigned mask, int gl, unsigned long long &npairs) {
+#define CMX_ROWS_PER_LANE 4
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
+              const u64 *__restrict__ rowmask, const float4 *__restrict__ qsorted, const int *__restrict__ qcell_start,
+              int nqcells, float4 *__restrict__ res, u64 *__restrict__ pair_evals) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int ntiles = qcell_start[nqcells];     // exclusive scan of the per-cell tile counts
     const float slack = 2e-3f;
-    int cy0 = (int)floorf((py - g.gmin[1]) * g.inv_side), cz0 = (int)floorf((pz - g.gmin[2]) * g.inv_side);
-    cy0 = min(max(cy0, 0), g.ny - 1); cz0 = min(max(cz0, 0), g.nz - 1);
-    const float side2 = g.side * g.side;
-    const int gbase = (threadIdx.x & 31) & ~(G - 1);
-    for (int t0 = 0; t0 < g.nrows_tab; t0 += G) {
-        if (c_row_lb[t0] * side2 > bound) break;   // table sorted: every later row is farther
-        int a = 0, b = 0; float rd2 = CUDART_INF_F;
-        int t = t0 + gl;
-        if (t < g.nrows_tab) {
-            int ry = cy0 + c_row_dy[t], rz = cz0 + c_row_dz[t];
-            if (ry >= 0 && ry < g.ny && rz >= 0 && rz < g.nz) {
-                float y0 = g.gmin[1] + ry * g.side, z0 = g.gmin[2] + rz * g.side;
-                float gy = fmaxf(fmaxf(y0 - py, py - (y0 + g.side)) - slack, 0.f);
-                float gz = fmaxf(fmaxf(z0 - pz, pz - (z0 + g.side)) - slack, 0.f);
-                float r2 = gy * gy + gz * gz;
-                if (r2 <= bound) {
-                    float hx = sqrtf(bound - r2) + slack;
-                    int cxl = max((int)floorf((px - hx - g.gmin[0]) * g.inv_sidex), 0);
-                    int cxh = min((int)floorf((px + hx - g.gmin[0]) * g.inv_sidex), g.nx - 1);
-                    if (cxl <= cxh) {
-                        int row = rz * g.ny + ry;
-                        int w0 = cxl >> 6, w1 = cxh >> 6;
-                        u64 m0 = __ldg(&rowmask[(size_t)row * g.rw + w0]) & (~0ull << (cxl & 63));
-                        u64 m1 = 0;
-                        if (w1 == w0) m0 &= (~0ull >> (63 - (cxh & 63)));
-                        else m1 = __ldg(&rowmask[(size_t)row * g.rw + w1]) & (~0ull >> (63 - (cxh & 63)));
-                        if (m0 | m1) {
-                            int first = m0 ? (w0 << 6) + __ffsll((long long)m0) - 1 : (w1 << 6) + __ffsll((long long)m1) - 1;
-                            int last = m1 ? (w1 << 6) + 63 - __clzll((long long)m1) : (w0 << 6) + 63 - __clzll((long long)m0);
-                            a = __ldg(&cell_start[row * g.nx + first]);
-                            b = __ldg(&cell_start[row * g.nx + last + 1]);
-                            rd2 = r2;
+    unsigned long long npairs = 0;
+    __shared__ float4 stage[8][32];               // per warp: one chunk of solute atoms
+    float4 *st = stage[threadIdx.x >> 5];
+    for (int tile = warp; tile < ntiles; tile += nwarps) {
+        float4 q = __ldg(&qsorted[(size_t)tile * 32 + lane]);
+        const bool valid = __float_as_int(q.w) >= 0;
+        {   // unused slots shadow the tile's first query (always present)
+            float x0 = __shfl_sync(0xffffffffu, q.x, 0), y0 = __shfl_sync(0xffffffffu, q.y, 0), z0 = __shfl_sync(0xffffffffu, q.z, 0);
+            if (!valid) { q.x = x0; q.y = y0; q.z = z0; }
+        }
+        const float xmin = warp_minf(q.x), xmax = warp_maxf(q.x), ymin = warp_minf(q.y), ymax = warp_maxf(q.y),
+                    zmin = warp_minf(q.z), zmax = warp_maxf(q.z);
+        float b1 = CUDART_INF_F, b2 = CUDART_INF_F; int bi = -1;
+        float bound = g.search2;
+        const float reach = sqrtf(bound) + slack;
+        const int ry_lo = max((int)floorf((ymin - reach - g.gmin[1]) * g.inv_side), 0);
+        const int ry_hi = min((int)floorf((ymax + reach - g.gmin[1]) * g.inv_side), g.ny - 1);
+        const int rz_lo = max((int)floorf((zmin - reach - g.gmin[2]) * g.inv_side), 0);
+        const int rz_hi = min((int)floorf((zmax + reach - g.gmin[2]) * g.inv_side), g.nz - 1);
+        const int nry = ry_hi - ry_lo + 1, nrows = nry * (rz_hi - rz_lo + 1);
+        for (int chunk = 0; chunk < nrows; chunk += 32 * CMX_ROWS_PER_LANE) {
+            // ---- probe: lane handles rows chunk + u*32 + lane
+            float rd[CMX_ROWS_PER_LANE];
+#pragma unroll
+            for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
+                rd[u] = CUDART_INF_F;
+                int r = chunk + u * 32 + lane;
+                if (r < nrows) {
+                    int ry = ry_lo + r % nry, rz = rz_lo + r / nry;
+                    float y0 = g.gmin[1] + ry * g.side, z0 = g.gmin[2] + rz * g.side;
+                    float gy = fmaxf(fmaxf(y0 - ymax, ymin - (y0 + g.side)) - slack, 0.f);
+                    float gz = fmaxf(fmaxf(z0 - zmax, zmin - (z0 + g.side)) - slack, 0.f);
+                    float r2 = gy * gy + gz * gz;
+                    if (r2 <= bound) {
+                        float hx = sqrtf(bound - r2) + slack;
+                        int cxl = max((int)floorf((xmin - hx - g.gmin[0]) * g.inv_sidex), 0);
+                        int cxh = min((int)floorf((xmax + hx - g.gmin[0]) * g.inv_sidex), g.nx - 1);
+                        const u64 *mrow = rowmask + (size_t)(rz * g.ny + ry) * g.rw;
+                        bool any = false;
+                        for (int w = cxl >> 6; w <= (cxh >> 6) && cxl <= cxh; ++w) {
+                            u64 m = __ldg(&mrow[w]);
+                            if (w == (cxl >> 6)) m &= (~0ull << (cxl & 63));
+                            if (w == (cxh >> 6)) m &= (~0ull >> (63 - (cxh & 63)));
+                            any |= m != 0ull;
                         }
+                        if (any) rd[u] = r2;
                     }
                 }
             }
-        }
-        unsigned ball = __ballot_sync(mask, b > a);
-        unsigned sub = (G == 32) ? ball : ((ball >> gbase) & ((1u << (G & 31)) - 1u));
-        while (sub) {
-            int r = __ffs(sub) - 1;
-            sub &= sub - 1;
-            int ra = __shfl_sync(mask, a, gbase + r), rb = __shfl_sync(mask, b, gbase + r);
-            float rr = __shfl_sync(mask, rd2, gbase + r);
-            if (rr > bound) continue;
-            for (int p = ra + gl; p < rb; p += G) {
-                float4 s = __ldg(&sorted[p]);
-                float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
-                float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                if (d2 < lb.b1) { lb.b2 = lb.b1; lb.b1 = d2; lb.i = __float_as_int(s.w); lb.k = k; }
-                else lb.b2 = fminf(lb.b2, d2);
+            // ---- visit the occupied rows nearest-first
+            while (true) {
+                float m = rd[0]; int um = 0;
+#pragma unroll
+                for (int u = 1; u < CMX_ROWS_PER_LANE; ++u) if (rd[u] < m) { m = rd[u]; um = u; }
+                float wm = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(m)));   // rd >= 0: bit order == value order
+                if (!(wm <= bound)) break;
+                int wl = __ffs(__ballot_sync(0xffffffffu, m == wm)) - 1;
+                int ru = __shfl_sync(0xffffffffu, um, wl);
+                if (lane == wl) {
+#pragma unroll
+                    for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) if (u == um) rd[u] = CUDART_INF_F;
+                }
+                int r = chunk + ru * 32 + wl;
+                int ry = ry_lo + r % nry, rz = rz_lo + r / nry;
+                float hx = sqrtf(bound - wm) + slack;
+                int cxl = max((int)floorf((xmin - hx - g.gmin[0]) * g.inv_sidex), 0);
+                int cxh = min((int)floorf((xmax + hx - g.gmin[0]) * g.inv_sidex), g.nx - 1);
+                if (cxl > cxh) continue;
+                int rowbase = (rz * g.ny + ry) * g.nx;
+                int a = __ldg(&cell_start[rowbase + cxl]), b = __ldg(&cell_start[rowbase + cxh + 1]);
+                // the row's atoms are fetched 32 at a time with one coalesced load (next chunk prefetched into
+                // registers), staged in shared memory and then read by every lane as broadcasts
+                float4 nxt = (a + lane < b) ? __ldg(&sorted[a + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int base = a; base < b; base += 32) {
+                    __syncwarp();
+                    st[lane] = nxt;
+                    __syncwarp();
+                    int nb = base + 32;
+                    if (nb + lane < b) nxt = __ldg(&sorted[nb + lane]);
+                    int n = min(32, b - base);
+#pragma unroll 4
+                    for (int j = 0; j < n; ++j) {
+                        float4 s = st[j];
+                        float dx = s.x - q.x, dy = s.y - q.y, dz = s.z - q.z;
+                        float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        b2 = fminf(b2, fmaxf(d2, b1));
+                        if (d2 < b1) { b1 = d2; bi = __float_as_int(s.w); }
+                    }
+                }
+                if (COUNT) npairs += (unsigned long long)(b - a);
+                float mine = valid ? fminf(b1 + g.tol_d2, g.search2) : 0.f;
+                bound = fminf(bound, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mine))));
             }
-            if (COUNT) npairs += (unsigned long long)((rb - ra - gl + G - 1) / G);
-            float gb = group_min<G>(lb.b1, mask);
-            bound = fminf(bound, gb + g.tol_d2);
         }
+        if (valid) res[__float_as_int(q.w)] = make_float4(b1, b2, __int_as_float(bi), 0.f);
     }
-}
-
-// Result of the fp32 search of one molecule, identical in all lanes of the group
-struct Found {
-    float b1, b2; int i, k;       // molecule: best, second best, winning pair
-    float r1, r2; int ri;         // reference atom: best, second best, winning solute atom
-};
-
-template <int G>
-__device__ __forceinline__ void group_combine(LaneBest lb, unsigned mask, int gl, float &b1, float &b2, int &bi, int &bk) {
-    b1 = group_min<G>(lb.b1, mask);
-    unsigned ball = __ballot_sync(mask, lb.b1 == b1);
-    int lane = threadIdx.x & 31;
-    int gbase = lane & ~(G - 1);
-    unsigned sub = (G == 32) ? ball : ((ball >> gbase) & ((1u << (G & 31)) - 1u));
-    int wl = __ffs(sub) - 1;   // winning lane within the group
-    float cand = (gl == wl) ? lb.b2 : lb.b1;
-    b2 = group_min<G>(cand, mask);
-    bi = __shfl_sync(mask, lb.i, gbase + wl);
-    bk = __shfl_sync(mask, lb.k, gbase + wl);
+    if (COUNT && pair_evals) {
+        npairs *= 32ull;
+        if (lane == 0 && npairs) atomicAdd(pair_evals, npairs);
+    }
 }
 
 // classification of the fp32 result: 0 = certainly outside, 1 = certainly inside and unambiguous,
@@ -362,78 +408,55 @@ __device__ __forceinline__ int classify(const Geom &g, float b1, float b2) {
     return 1;
 }
 
-template <int G, bool RANDOM, bool COUNT>
-__global__ void __launch_bounds__(256)
-k_search(Geom g, Prob P, const float *__restrict__ xs /* solute molecule, fp32 as read */,
-         const float *__restrict__ xv /* solvent of the frame, fp32 as read */,
-         const int *__restrict__ cell_start, const float4 *__restrict__ sorted, const u64 *__restrict__ rowmask,
-         const float4 *__restrict__ qpos, const double *__restrict__ xexact,
-         const int *__restrict__ worklist, const int *__restrict__ work_count,
-         MdRec *__restrict__ list /* real: [nv_mols]; random: debug [nrand][nv_mols] or NULL */,
-         u64 *__restrict__ deferred, int *__restrict__ deferred_count, u64 *__restrict__ pair_evals) {
-    const int gl = threadIdx.x & (G - 1);
-    const unsigned mask = group_mask<G>();
-    const int ngroups = (gridDim.x * blockDim.x) / G;
+// ---------------------------------------------------------------------------------------------
+// K6b: per molecule, combine its atoms' results (update_md, src/minimum_distances.jl:30-39), finalise
+// the winning pair and the reference-atom pair in fp64 with the reference's arithmetic, histogram
+// (update_counters!, src/update_counters.jl:43-88) -- or defer an ambiguous molecule to the exact kernel.
+// ---------------------------------------------------------------------------------------------
+template <bool RANDOM>
+__global__ void __launch_bounds__(128)
+k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict__ xv, const float4 *__restrict__ res,
+           const double *__restrict__ xexact, const int *__restrict__ worklist, const int *__restrict__ work_count,
+           MdRec *__restrict__ list, u64 *__restrict__ deferred, int *__restrict__ deferred_count) {
     const int count = *work_count;
-    unsigned long long npairs = 0;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) / G; w < count; w += ngroups) {
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
         const int item = worklist[w];
-        const float4 *q = qpos + (size_t)w * P.nv_apm;
-        LaneBest lb; lb.b1 = CUDART_INF_F; lb.b2 = CUDART_INF_F; lb.i = -1; lb.k = -1;
-        Found F; F.r1 = CUDART_INF_F; F.r2 = CUDART_INF_F; F.ri = -1;
-        float bound = g.search2;
-        // reference atom first: its own nearest solute atom is needed exactly (rdf_count), and it
-        // seeds the bound for the other atoms
-        for (int kk = 0; kk < P.nv_apm; ++kk) {
-            int k = kk == 0 ? P.iref : (kk <= P.iref ? kk - 1 : kk);
-            float4 p = __ldg(&q[k]);
-            if (p.w <= bound) search_atom<G, COUNT>(g, rowmask, cell_start, sorted, p.x, p.y, p.z, k, bound, lb, mask, gl, npairs);
-            if (kk == 0) { int tk; group_combine<G>(lb, mask, gl, F.r1, F.r2, F.ri, tk); }
-        }
-        group_combine<G>(lb, mask, gl, F.b1, F.b2, F.i, F.k);
         int sample = 0, mol = item;
         if (RANDOM) { sample = item / P.nv_mols; mol = item - sample * P.nv_mols; }
-        int cls = classify(g, F.b1, F.b2);
+        const float4 *r = res + (size_t)w * P.nv_apm;
+        float best = CUDART_INF_F, second = CUDART_INF_F; int bi = -1, bk = -1;
+        for (int k = 0; k < P.nv_apm; ++k) {
+            float4 a = __ldg(&r[k]);
+            if (a.x < best) { second = fminf(fminf(second, best), a.y); best = a.x; bi = __float_as_int(a.z); bk = k; }
+            else second = fminf(second, a.x);
+        }
+        int cls = classify(g, best, second);
         if (cls == 0) continue;   // list entry stays "not within"
-        int rcls = classify(g, F.r1, F.r2);
-        // the reference atom only matters when the molecule is inside
+        float4 rr = __ldg(&r[P.iref]);
+        int rcls = classify(g, rr.x, rr.y);
         if (cls == 2 || rcls == 2) {
-            if (gl == 0) {
-                int slot = atomicAdd(deferred_count, 1);
-                deferred[slot] = ((u64)(RANDOM ? 1 + sample : 0) << 32) | (u64)(uint32_t)mol;
-            }
+            int slot = atomicAdd(deferred_count, 1);
+            deferred[slot] = ((u64)(RANDOM ? 1 + sample : 0) << 32) | (u64)(uint32_t)mol;
             continue;
         }
-        // exact fp64 finalisation: lane 0 the winning pair, lane 1 (same instruction stream) the
-        // reference-atom pair
-        const bool second = (G > 1) && gl == 1;
-        const int fi = second ? F.ri : F.i, fk = second ? P.iref : F.k;
-        double dd = 0;
-        if (gl == 0 || (second && rcls == 1)) {
-            double ex, ey, ez;
-            if (RANDOM) { const double *xe = xexact + ((size_t)P.nv_apm * w + fk) * 3; ex = xe[0]; ey = xe[1]; ez = xe[2]; }
-            else { const float *xr = xv + ((size_t)P.nv_apm * mol + fk) * 3; ex = (double)xr[0]; ey = (double)xr[1]; ez = (double)xr[2]; }
-            dd = dist_pbc64(g, (double)xs[3 * fi], (double)xs[3 * fi + 1], (double)xs[3 * fi + 2], ex, ey, ez);
-        }
-        double dref = CUDART_INF;
-        if (G > 1) dref = __shfl_sync(mask, dd, ((threadIdx.x & 31) & ~(G - 1)) + 1);
-        if (gl != 0) continue;
-        if (G == 1 && rcls == 1) {
-            double ex, ey, ez;
-            if (RANDOM) { const double *xe = xexact + ((size_t)P.nv_apm * w + P.iref) * 3; ex = xe[0]; ey = xe[1]; ez = xe[2]; }
-            else { const float *xr = xv + ((size_t)P.nv_apm * mol + P.iref) * 3; ex = (double)xr[0]; ey = (double)xr[1]; ez = (double)xr[2]; }
-            dref = dist_pbc64(g, (double)xs[3 * F.ri], (double)xs[3 * F.ri + 1], (double)xs[3 * F.ri + 2], ex, ey, ez);
-        }
+        auto pos = [&](int k, double &ex, double &ey, double &ez) {
+            if (RANDOM) { const double *xe = xexact + ((size_t)P.nv_apm * w + k) * 3; ex = xe[0]; ey = xe[1]; ez = xe[2]; }
+            else { const float *xr = xv + ((size_t)P.nv_apm * mol + k) * 3; ex = (double)xr[0]; ey = (double)xr[1]; ez = (double)xr[2]; }
+        };
+        double ex, ey, ez;
+        pos(bk, ex, ey, ez);
         MdRec e;
-        e.d = dd; e.i = F.i; e.j = mol * P.nv_apm + F.k; e.flags = 1; e.dref = CUDART_INF; e.pad = 0;
-        if (rcls == 1) { e.dref = dref; e.flags |= 2; }
+        e.d = dist_pbc64(g, (double)xs[3 * bi], (double)xs[3 * bi + 1], (double)xs[3 * bi + 2], ex, ey, ez);
+        e.i = bi; e.j = mol * P.nv_apm + bk; e.flags = 1; e.dref = CUDART_INF; e.pad = 0;
+        if (rcls == 1) {
+            int ri = __float_as_int(rr.z);
+            pos(P.iref, ex, ey, ez);
+            e.dref = dist_pbc64(g, (double)xs[3 * ri], (double)xs[3 * ri + 1], (double)xs[3 * ri + 2], ex, ey, ez);
+            e.flags |= 2;
+        }
         count_hit(P, RANDOM, e.d, e.i, e.j, 1ull);
         if (e.flags & 2) count_ref(P, RANDOM, e.dref);
         if (list) list[RANDOM ? (size_t)sample * P.nv_mols + mol : (size_t)mol] = e;
-    }
-    if (COUNT && pair_evals) {
-        for (int o = 16; o; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
-        if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(pair_evals, npairs);
     }
 }
 
