@@ -65,6 +65,7 @@ struct FrameCtx {
     DevBuf<MdRec> d_list;
     DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
     DevBuf<u64> d_def_real, d_def_rand;
+    DevBuf<float2> d_def_real_info, d_def_rand_info;
     DevBuf<int> d_scalars;          // [0] work_count, [1] rand_work_count, [2] def_real, [3] def_rand, [4] n_bulk, [5] rmax bits, [8] sticky overflow
     DevBuf<unsigned char> d_cub_tmp;
     PairScratch pairs;
@@ -73,7 +74,7 @@ struct FrameCtx {
         d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release(); d_rowmask.release();
         d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_tile_count.release(); d_xexact.release(); d_edt_x.release(); d_bulk_flags.release();
         d_edt_xy.release(); d_lbd2.release(); d_list.release(); d_worklist.release(); d_rand_worklist.release();
-        d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_scalars.release(); d_cub_tmp.release();
+        d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_def_real_info.release(); d_def_rand_info.release(); d_scalars.release(); d_cub_tmp.release();
         if (h_scalars) cudaFreeHost(h_scalars);
         if (ev_end) cudaEventDestroy(ev_end);
         if (stream) cudaStreamDestroy(stream);
@@ -267,7 +268,7 @@ void prof_collect(cmx_handle *h) {
 // one search phase (real or random) over the molecules of a work list: tile the query atoms, search, combine
 template <bool RANDOM>
 int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv, const int *worklist, const int *work_count,
-                 size_t max_atoms, MdRec *list, u64 *deferred, int *def_count, int tag) {
+                 size_t max_atoms, MdRec *list, u64 *deferred, float2 *def_info, int *def_count, int tag) {
     FrameCtx &x = *h->cur;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
     // (query positions, res and the per-cell counts were produced by k_gen_*)
@@ -289,7 +290,7 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
                 (const u64 *)x.d_rowmask.p, (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
     prof_end(h, pe);
     launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
-           (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_count);
+           (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count);
     return CMX_OK;
 }
 
@@ -339,10 +340,10 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->cur->d_lbd2.p,
                (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
         { int rc = search_phase<false>(h, g, xs, d_solvent, h->cur->d_worklist.p, sc + 0, h->nv_atoms, h->cur->d_list.p,
-                                       h->cur->d_def_real.p, sc + 2, 0); if (rc) return rc; }
+                                       h->cur->d_def_real.p, h->cur->d_def_real_info.p, sc + 2, 0); if (rc) return rc; }
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->cur->d_def_real.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr);
+               (const u64 *)h->cur->d_def_real.p, (const float2 *)h->cur->d_def_real_info.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr);
         if (c.keep_lists)
             CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->cur->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
                                cudaMemcpyDeviceToDevice, h->cur->stream));
@@ -363,10 +364,10 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
                (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
                h->cur->d_qpos.p, h->cur->d_xexact.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
         { int rc = search_phase<true>(h, g, xs, d_solvent, h->cur->d_rand_worklist.p, sc + 1, (size_t)nrand * h->nv_atoms,
-                                      c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, sc + 3, 1); if (rc) return rc; }
+                                      c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, h->cur->d_def_rand_info.p, sc + 3, 1); if (rc) return rc; }
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->cur->d_def_rand.p, (const int *)(sc + 3), (MdRec *)nullptr,
+               (const u64 *)h->cur->d_def_rand.p, (const float2 *)h->cur->d_def_rand_info.p, (const int *)(sc + 3), (MdRec *)nullptr,
                c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
         launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)(sc + 3), h->d_stats.p);
     }
@@ -590,6 +591,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         CK(h->cur->d_bulk_flags.ensure(nvm)); CK(h->cur->d_bulk_idx.ensure(nvm));
         CK(h->cur->d_worklist.ensure(nvm)); CK(h->cur->d_rand_worklist.ensure(std::max<size_t>(nrand * nvm, 1)));
         CK(h->cur->d_def_real.ensure(nvm)); CK(h->cur->d_def_rand.ensure(std::max<size_t>(nrand * nvm, 1)));
+    CK(h->cur->d_def_real_info.ensure(nvm)); CK(h->cur->d_def_rand_info.ensure(std::max<size_t>(nrand * nvm, 1)));
         if (c.keep_lists) {
             if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
             CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));

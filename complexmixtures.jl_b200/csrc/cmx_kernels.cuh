@@ -319,12 +319,15 @@ k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restri
         for (int chunk = 0; chunk < nrows; chunk += 32 * CMX_ROWS_PER_LANE) {
             // ---- probe: lane handles rows chunk + u*32 + lane
             float rd[CMX_ROWS_PER_LANE];
+            int rrow[CMX_ROWS_PER_LANE];          // (rz * ny + ry) of the probed row
 #pragma unroll
             for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
-                rd[u] = CUDART_INF_F;
+                rd[u] = CUDART_INF_F; rrow[u] = 0;
                 int r = chunk + u * 32 + lane;
                 if (r < nrows) {
-                    int ry = ry_lo + r % nry, rz = rz_lo + r / nry;
+                    int rzq = r / nry;
+                    int ry = ry_lo + (r - rzq * nry), rz = rz_lo + rzq;
+                    rrow[u] = rz * g.ny + ry;
                     float y0 = g.gmin[1] + ry * g.side, z0 = g.gmin[2] + rz * g.side;
                     float gy = fmaxf(fmaxf(y0 - ymax, ymin - (y0 + g.side)) - slack, 0.f);
                     float gz = fmaxf(fmaxf(z0 - zmax, zmin - (z0 + g.side)) - slack, 0.f);
@@ -347,24 +350,22 @@ k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restri
             }
             // ---- visit the occupied rows nearest-first
             while (true) {
-                float m = rd[0]; int um = 0;
+                float m = rd[0]; int um = 0, rowm = rrow[0];
 #pragma unroll
-                for (int u = 1; u < CMX_ROWS_PER_LANE; ++u) if (rd[u] < m) { m = rd[u]; um = u; }
+                for (int u = 1; u < CMX_ROWS_PER_LANE; ++u) if (rd[u] < m) { m = rd[u]; um = u; rowm = rrow[u]; }
                 float wm = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(m)));   // rd >= 0: bit order == value order
                 if (!(wm <= bound)) break;
                 int wl = __ffs(__ballot_sync(0xffffffffu, m == wm)) - 1;
-                int ru = __shfl_sync(0xffffffffu, um, wl);
+                const int row = __shfl_sync(0xffffffffu, rowm, wl);
                 if (lane == wl) {
 #pragma unroll
                     for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) if (u == um) rd[u] = CUDART_INF_F;
                 }
-                int r = chunk + ru * 32 + wl;
-                int ry = ry_lo + r % nry, rz = rz_lo + r / nry;
                 float hx = sqrtf(bound - wm) + slack;
                 int cxl = max((int)floorf((xmin - hx - g.gmin[0]) * g.inv_sidex), 0);
                 int cxh = min((int)floorf((xmax + hx - g.gmin[0]) * g.inv_sidex), g.nx - 1);
                 if (cxl > cxh) continue;
-                int rowbase = (rz * g.ny + ry) * g.nx;
+                int rowbase = row * g.nx;
                 int a = __ldg(&cell_start[rowbase + cxl]), b = __ldg(&cell_start[rowbase + cxh + 1]);
                 // the row's atoms are fetched 32 at a time with one coalesced load (next chunk prefetched into
                 // registers), staged in shared memory and then read by every lane as broadcasts
@@ -417,7 +418,8 @@ template <bool RANDOM>
 __global__ void __launch_bounds__(128)
 k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict__ xv, const float4 *__restrict__ res,
            const double *__restrict__ xexact, const int *__restrict__ worklist, const int *__restrict__ work_count,
-           MdRec *__restrict__ list, u64 *__restrict__ deferred, int *__restrict__ deferred_count) {
+           MdRec *__restrict__ list, u64 *__restrict__ deferred, float2 *__restrict__ deferred_info,
+           int *__restrict__ deferred_count) {
     const int count = *work_count;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
         const int item = worklist[w];
@@ -437,6 +439,7 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
         if (cls == 2 || rcls == 2) {
             int slot = atomicAdd(deferred_count, 1);
             deferred[slot] = ((u64)(RANDOM ? 1 + sample : 0) << 32) | (u64)(uint32_t)mol;
+            deferred_info[slot] = make_float2(best, rr.x);   // fp32 bounds: the exact kernel only looks at atoms that can matter
             continue;
         }
         auto pos = [&](int k, double &ex, double &ey, double &ez) {
@@ -515,39 +518,16 @@ __device__ __forceinline__ bool better(double d, int j, int i, const ExactBest &
     return d < b.d || (d == b.d && (j < b.j || (j == b.j && i < b.i)));
 }
 
-// fp32 bound first (block minimum over the cell-sorted solute incl. images), then the exact fp64
-// evaluation only of the solute atoms that can matter: those within (min + 4 tau) of the molecule's
-// nearest atom or of the reference atom's nearest atom.
+// Exact fp64 evaluation of one deferred molecule.  The fp32 search already bounded the answer: only
+// solute atoms (incl. images) whose fp32 distance is within 4 tau of the molecule's best, or of the
+// reference atom's best, can be the exact winner -- everything else is skipped after one fp32 test.
 template <class Mol>
 __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const float *__restrict__ xs,
                                             const float4 *__restrict__ sorted, int nsorted, const Mol &mol,
-                                            int molidx, bool random, MdRec *out, ExactBest *sh, float *shf) {
-    float mb = CUDART_INF_F, rb = CUDART_INF_F;
-    for (int k = 0; k < P.nv_apm; ++k) {
-        double ex, ey, ez; mol.get(g, k, ex, ey, ez);
-        double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
-        float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
-#pragma unroll 4
-        for (int p = threadIdx.x; p < nsorted; p += blockDim.x) {
-            float4 s = __ldg(&sorted[p]);
-            float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
-            float d2 = dx * dx + dy * dy + dz * dz;
-            mb = fminf(mb, d2);
-            if (k == P.iref) rb = fminf(rb, d2);
-        }
-    }
-    shf[threadIdx.x] = mb; shf[blockDim.x + threadIdx.x] = rb;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o; o >>= 1) {
-        if (threadIdx.x < o) {
-            shf[threadIdx.x] = fminf(shf[threadIdx.x], shf[threadIdx.x + o]);
-            shf[blockDim.x + threadIdx.x] = fminf(shf[blockDim.x + threadIdx.x], shf[blockDim.x + threadIdx.x + o]);
-        }
-        __syncthreads();
-    }
-    float lim_m = sqrtf(shf[0]) + 4.f * g.tau, lim_r = sqrtf(shf[blockDim.x]) + 4.f * g.tau;
+                                            int molidx, bool random, float2 info, MdRec *out, ExactBest *sh) {
+    const float capd = g.cut_hi + 4.f * g.tau;
+    float lim_m = fminf(sqrtf(info.x) + 4.f * g.tau, capd), lim_r = fminf(sqrtf(info.y) + 4.f * g.tau, capd);
     lim_m *= lim_m; lim_r *= lim_r;
-    __syncthreads();
     ExactBest b; b.d = CUDART_INF; b.dref = CUDART_INF; b.i = 0x7fffffff; b.j = 0x7fffffff;
     for (int k = 0; k < P.nv_apm; ++k) {
         double ex, ey, ez; mol.get(g, k, ex, ey, ez);
@@ -598,17 +578,18 @@ __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const 
 __global__ void __launch_bounds__(CMX_RESOLVE_THREADS)
 k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const float *__restrict__ xv,
           const float4 *__restrict__ sorted, const int *__restrict__ cell_start, int ncells, const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk_ptr, const u64 *__restrict__ deferred,
-          const int *__restrict__ deferred_count, MdRec *__restrict__ list, MdRec *__restrict__ rand_list) {
+          const float2 *__restrict__ deferred_info, const int *__restrict__ deferred_count, MdRec *__restrict__ list,
+          MdRec *__restrict__ rand_list) {
     __shared__ ExactBest sh[CMX_RESOLVE_THREADS];
-    __shared__ float shf[2 * CMX_RESOLVE_THREADS];
     int count = *deferred_count;
     const int nsorted = cell_start[ncells];
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         u64 item = deferred[w];
+        const float2 info = deferred_info[w];
         int phase = (int)(item >> 32), mol = (int)(item & 0xffffffffu);
         if (phase == 0) {
             RealMolG rl; rl.m.x = xv + (size_t)3 * P.nv_apm * mol;
-            resolve_one(g, P, xs, sorted, nsorted, rl, mol, false, list ? &list[mol] : nullptr, sh, shf);
+            resolve_one(g, P, xs, sorted, nsorted, rl, mol, false, info, list ? &list[mol] : nullptr, sh);
         } else {
             int sample = phase - 1;
             uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
@@ -616,7 +597,7 @@ k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const fl
             int nb = *n_bulk_ptr;
             int jmol = nb > 0 ? bulk_idx[pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
             RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
-            resolve_one(g, P, xs, sorted, nsorted, rm, mol, true, rand_list ? &rand_list[(size_t)sample * P.nv_mols + mol] : nullptr, sh, shf);
+            resolve_one(g, P, xs, sorted, nsorted, rm, mol, true, info, rand_list ? &rand_list[(size_t)sample * P.nv_mols + mol] : nullptr, sh);
         }
     }
 }
