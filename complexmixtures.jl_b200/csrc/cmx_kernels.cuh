@@ -523,28 +523,41 @@ __device__ __forceinline__ bool better(double d, int j, int i, const ExactBest &
 // reference atom's best, can be the exact winner -- everything else is skipped after one fp32 test.
 template <class Mol>
 __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const float *__restrict__ xs,
-                                            const float4 *__restrict__ sorted, int nsorted, const Mol &mol,
-                                            int molidx, bool random, float2 info, MdRec *out, ExactBest *sh) {
+                                            const float4 *__restrict__ sorted, const int *__restrict__ cell_start,
+                                            const Mol &mol, int molidx, bool random, float2 info, MdRec *out, ExactBest *sh) {
     const float capd = g.cut_hi + 4.f * g.tau;
     float lim_m = fminf(sqrtf(info.x) + 4.f * g.tau, capd), lim_r = fminf(sqrtf(info.y) + 4.f * g.tau, capd);
     lim_m *= lim_m; lim_r *= lim_r;
     ExactBest b; b.d = CUDART_INF; b.dref = CUDART_INF; b.i = 0x7fffffff; b.j = 0x7fffffff;
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
     for (int k = 0; k < P.nv_apm; ++k) {
         double ex, ey, ez; mol.get(g, k, ex, ey, ez);
         double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
         float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
         int j = molidx * P.nv_apm + k;
-#pragma unroll 4
-        for (int p = threadIdx.x; p < nsorted; p += blockDim.x) {
-            float4 s = __ldg(&sorted[p]);
-            float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
-            float d2 = dx * dx + dy * dy + dz * dz;
-            if (!(d2 <= lim_m || (k == P.iref && d2 <= lim_r))) continue;
-            int i = __float_as_int(s.w);
-            double d = dist_pbc64(g, (double)xs[3 * i], (double)xs[3 * i + 1], (double)xs[3 * i + 2], ex, ey, ez);
-            if (d <= g.cutd) {
-                if (better(d, j, i, b)) { b.d = d; b.i = i; b.j = j; }
-                if (k == P.iref && d < b.dref) b.dref = d;
+        // only the grid rows / x-span within reach of this atom (warps take rows, lanes stride the span)
+        const float lim = (k == P.iref) ? fmaxf(lim_m, lim_r) : lim_m;
+        const float reach = sqrtf(lim) + 4e-3f;
+        const int ry_lo = max((int)floorf((py - reach - g.gmin[1]) * g.inv_side), 0), ry_hi = min((int)floorf((py + reach - g.gmin[1]) * g.inv_side), g.ny - 1);
+        const int rz_lo = max((int)floorf((pz - reach - g.gmin[2]) * g.inv_side), 0), rz_hi = min((int)floorf((pz + reach - g.gmin[2]) * g.inv_side), g.nz - 1);
+        const int cxl = max((int)floorf((px - reach - g.gmin[0]) * g.inv_sidex), 0), cxh = min((int)floorf((px + reach - g.gmin[0]) * g.inv_sidex), g.nx - 1);
+        const int nry = ry_hi - ry_lo + 1, nrows = nry * (rz_hi - rz_lo + 1);
+        if (cxl > cxh) continue;
+        for (int r = wid; r < nrows; r += nw) {
+            int rzq = r / nry;
+            int rowbase = ((rz_lo + rzq) * g.ny + ry_lo + (r - rzq * nry)) * g.nx;
+            int pa = __ldg(&cell_start[rowbase + cxl]), pb = __ldg(&cell_start[rowbase + cxh + 1]);
+            for (int p = pa + lane; p < pb; p += 32) {
+                float4 s = __ldg(&sorted[p]);
+                float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
+                float d2 = dx * dx + dy * dy + dz * dz;
+                if (!(d2 <= lim_m || (k == P.iref && d2 <= lim_r))) continue;
+                int i = __float_as_int(s.w);
+                double d = dist_pbc64(g, (double)xs[3 * i], (double)xs[3 * i + 1], (double)xs[3 * i + 2], ex, ey, ez);
+                if (d <= g.cutd) {
+                    if (better(d, j, i, b)) { b.d = d; b.i = i; b.j = j; }
+                    if (k == P.iref && d < b.dref) b.dref = d;
+                }
             }
         }
     }
@@ -582,14 +595,14 @@ k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const fl
           MdRec *__restrict__ rand_list) {
     __shared__ ExactBest sh[CMX_RESOLVE_THREADS];
     int count = *deferred_count;
-    const int nsorted = cell_start[ncells];
+    (void)ncells;
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         u64 item = deferred[w];
         const float2 info = deferred_info[w];
         int phase = (int)(item >> 32), mol = (int)(item & 0xffffffffu);
         if (phase == 0) {
             RealMolG rl; rl.m.x = xv + (size_t)3 * P.nv_apm * mol;
-            resolve_one(g, P, xs, sorted, nsorted, rl, mol, false, info, list ? &list[mol] : nullptr, sh);
+            resolve_one(g, P, xs, sorted, cell_start, rl, mol, false, info, list ? &list[mol] : nullptr, sh);
         } else {
             int sample = phase - 1;
             uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
@@ -597,7 +610,7 @@ k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const fl
             int nb = *n_bulk_ptr;
             int jmol = nb > 0 ? bulk_idx[pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
             RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
-            resolve_one(g, P, xs, sorted, nsorted, rm, mol, true, info, rand_list ? &rand_list[(size_t)sample * P.nv_mols + mol] : nullptr, sh);
+            resolve_one(g, P, xs, sorted, cell_start, rm, mol, true, info, rand_list ? &rand_list[(size_t)sample * P.nv_mols + mol] : nullptr, sh);
         }
     }
 }

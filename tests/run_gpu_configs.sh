@@ -3,8 +3,8 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1; tail -1 gpurun_out/build.log
-for C in C2urea C3 C4; do
-  timeout 1500 python bench.py --config $C --steps 2 --warmup 3 --cpu-frames 4 --group-lanes 8 > gpurun_out/bench_$C.json 2> gpurun_out/bench_$C.err
+for C in C4 C5; do
+  timeout 1500 python bench.py --config $C --steps 2 --warmup 3 --cpu-frames 2 > gpurun_out/bench_$C.json 2> gpurun_out/bench_$C.err
   python - <<PY
 import json
 try:

@@ -277,3 +277,16 @@ def test_error_paths():
     eng.submit_arrays(p.xs[0], p.xv[0], p.cells[0], frame_index=1)   # the handle is still usable
     assert eng.finish()["md_count"].sum() == 24.0                    # 24 of 181 TMAO within 10 A
     eng.close()
+
+
+def test_slab_solute_spanning_the_cell():
+    """C5-like geometry at small scale: the solute slab spans the cell in x and y, so the search relies on
+    the periodic images of the solute atoms on every face."""
+    from cmx_b200 import synthetic as syn
+    s = syn.config_c5(0.004)       # ~4000 slab atoms, ~5300 waters, 63 x 63 x 50 A
+    sol, wat = s.selections["solute"], s.selections["water"]
+    fr = [s.frame(k + 1)[0] for k in range(2)]
+    p = Problem(sol, wat, opts(bulk_range=(10.0, 15.0), n_random_samples=4), [f[sol.indices - 1] for f in fr],
+                [f[wat.indices - 1] for f in fr], s.cell)
+    dev, o, stats = check(p)
+    assert dev["md_count"].sum() > 1000
