@@ -241,11 +241,15 @@ def main():
             t = torch.as_tensor(wobj, device=f"cuda:{local_rank}")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
+    submit_s = [0.0]
+
     def step_device(collective=True):
+        t_sub = time.perf_counter()
         for k in range(fps):
             rc = lib.cmx_submit_frame_device(h, C.c_void_p(ps + k * ss_stride), C.c_void_p(pv + k * sv_stride), w["frame_ids"][k], 1.0, cellp)
             if rc:
                 raise RuntimeError(lib.cmx_last_error(h).decode())
+        submit_s[0] += time.perf_counter() - t_sub
         eng.sync()
         if collective:
             allreduce_counts()
@@ -268,6 +272,7 @@ def main():
     eng.reset()
     barrier()
     st0 = eng.stats()
+    submit_s[0] = 0.0
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -275,6 +280,7 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
     st1 = eng.stats()
+    host_submit_ms = 1e3 * submit_s[0] / args.steps
     dev_ms = st1["gpu_ms_total"] - st0["gpu_ms_total"]
     t_dev = max(dev_ms * 1e-3, 1e-9)
     tt = torch.tensor([t_dev, wall], dtype=torch.float64, device="cuda")
@@ -364,6 +370,7 @@ def main():
                            "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps * world),
                            "deferred_to_exact_per_frame": deferred},
                 "device_ms_per_step": 1e3 * t_dev / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
+                "host_submit_ms_per_step": host_submit_ms,
                 "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
     eng.close()

@@ -177,6 +177,7 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
     for (int k = 0; k < 3; ++k) {
         g.inv[0 + 3 * k] = bxc[k] / det; g.inv[1 + 3 * k] = cxa[k] / det; g.inv[2 + 3 * k] = axb[k] / det;
     }
+    g.invl[0] = 1.0 / a[0]; g.invl[1] = 1.0 / b[1]; g.invl[2] = 1.0 / c[2];
     double w[3] = {std::fabs(det) / std::sqrt(bxc[0] * bxc[0] + bxc[1] * bxc[1] + bxc[2] * bxc[2]),
                    std::fabs(det) / std::sqrt(cxa[0] * cxa[0] + cxa[1] * cxa[1] + cxa[2] * cxa[2]),
                    std::fabs(det) / std::sqrt(axb[0] * axb[0] + axb[1] * axb[1] + axb[2] * axb[2])};
@@ -272,9 +273,9 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
     FrameCtx &x = *h->cur;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
     // (query positions, res and the per-cell counts were produced by k_gen_*)
-    launch(h, k_tile_count, dim3((unsigned)((nqc + 1 + 255) / 256)), dim3(256), (int)nqc, (const int *)x.d_qcell_count.p, x.d_tile_count.p);
     size_t tmp_bytes = x.d_cub_tmp.n;
-    CK(cub::DeviceScan::ExclusiveSum(x.d_cub_tmp.p, tmp_bytes, x.d_tile_count.p, x.d_qcell_start.p, (int)(nqc + 1), x.stream));
+    cub::TransformInputIterator<int, TileCountOp, const int *> tiles_of((const int *)x.d_qcell_count.p, TileCountOp());
+    CK(cub::DeviceScan::ExclusiveSum(x.d_cub_tmp.p, tmp_bytes, tiles_of, x.d_qcell_start.p, (int)(nqc + 1), x.stream));
     h->stats.kernel_launches += 2;
     // worst case: every atom in a tile of its own cell's last, partially filled tile
     size_t slots = std::min(max_atoms + 32 * nqc, x.d_qsorted.n);
@@ -285,9 +286,9 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
     cudaEvent_t pe = prof_begin(h, tag);
     u64 *pev = h->count_pairs ? h->d_stats.p : nullptr;
     if (pev) launch(h, k_tile_search<true>, dim3(h->num_sms * 8), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                    (const u64 *)x.d_rowmask.p, (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
+                    (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
     else launch(h, k_tile_search<false>, dim3(h->num_sms * 8), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                (const u64 *)x.d_rowmask.p, (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
+                (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
     prof_end(h, pe);
     launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
            (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count);
@@ -302,10 +303,11 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     size_t occ_words = (size_t)g.ncy * g.ncz * g.cw;
     CK(h->cur->d_cell_count.ensure(ncells + 1, true));
     CK(h->cur->d_cell_start.ensure(ncells + 1));
-    CK(h->cur->d_occ.ensure(occ_words));
+    // [8 per-frame scalars][cull-grid bitmap][row bitmap] share one buffer: one memset per solute molecule
+    CK(h->cur->d_occ.ensure(4 + occ_words + ((size_t)g.ny * g.nz * g.rw)));
     CK(h->cur->d_edt_x.ensure(ncc)); CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
     size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
-    CK(h->cur->d_rowmask.ensure(rowmask_words));
+    u64 *occ_p = h->cur->d_occ.p + 4, *rowmask_p = occ_p + occ_words;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
     CK(h->cur->d_qcell_count.ensure(nqc + 1, true)); CK(h->cur->d_qcell_start.ensure(nqc + 1)); CK(h->cur->d_tile_count.ensure(nqc + 1));
     {   // tile array: atoms + padding of each cell's last tile
@@ -313,49 +315,46 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         CK(h->cur->d_qsorted.ensure(maxq + 32 * nqc));
     }
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
-    int *sc = h->cur->d_scalars.p;
+    int *sc = (int *)h->cur->d_occ.p;
     for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
         const float *xs = d_solute + (size_t)3 * ns_apm * isolute;
         const int skip = c.autocorrelation ? isolute : -1;
         int nrand_k = 0;
         if (c.solute_nmols == 1) nrand_k = nrand;
         else for (int s = 0; s < nrand; ++s) nrand_k += (ref_solute_host(h, frame, (uint32_t)s) == isolute);
-        CK(cudaMemsetAsync(sc, 0, 8 * sizeof(int), h->cur->stream));
-        CK(cudaMemsetAsync(h->cur->d_occ.p, 0, occ_words * sizeof(u64), h->cur->stream));
-        CK(cudaMemsetAsync(h->cur->d_rowmask.p, 0, rowmask_words * sizeof(u64), h->cur->stream));
+        CK(cudaMemsetAsync(h->cur->d_occ.p, 0, (4 + occ_words + rowmask_words) * sizeof(u64), h->cur->stream));
         int tb = 128;
         launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
-               (const int *)nullptr, h->cur->d_occ.p, h->cur->d_rowmask.p, (float4 *)nullptr);
+               (const int *)nullptr, occ_p, rowmask_p, (float4 *)nullptr);
         size_t tmp_bytes = h->cur->d_cub_tmp.n;
         CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), h->cur->stream));
         h->stats.kernel_launches += 2;
         launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
-               (const int *)h->cur->d_cell_start.p, h->cur->d_occ.p, h->cur->d_rowmask.p, h->cur->d_sorted.p);
-        launch(h, k_edt_x, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)h->cur->d_occ.p, h->cur->d_edt_x.p);
+               (const int *)h->cur->d_cell_start.p, occ_p, rowmask_p, h->cur->d_sorted.p);
+        launch(h, k_edt_x, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)occ_p, h->cur->d_edt_x.p);
         launch(h, k_edt_y, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned char *)h->cur->d_edt_x.p, h->cur->d_edt_xy.p);
         launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->cur->d_edt_xy.p, h->cur->d_lbd2.p);
         launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
                (const float *)h->cur->d_lbd2.p, h->cur->d_list.p, h->cur->d_worklist.p, sc + 0, sc + 5);
-        CK(cudaMemcpyAsync(h->cur->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->cur->stream));
+        if (h->stats.frames < 64 || (h->stats.frames & 15) == 0)   // host-side bound for the NEXT frames' cull window (monotone)
+            CK(cudaMemcpyAsync(h->cur->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->cur->stream));
         launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->cur->d_lbd2.p,
                (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
         { int rc = search_phase<false>(h, g, xs, d_solvent, h->cur->d_worklist.p, sc + 0, h->nv_atoms, h->cur->d_list.p,
                                        h->cur->d_def_real.p, h->cur->d_def_real_info.p, sc + 2, 0); if (rc) return rc; }
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->cur->d_def_real.p, (const float2 *)h->cur->d_def_real_info.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr);
+               (const u64 *)h->cur->d_def_real.p, (const float2 *)h->cur->d_def_real_info.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr,
+               nrand_k == 0 ? h->d_stats.p : (u64 *)nullptr, (const int *)(sc + 2), (const int *)nullptr);
         if (c.keep_lists)
             CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->cur->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
                                cudaMemcpyDeviceToDevice, h->cur->stream));
-        if (nrand_k == 0) {
-            launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)nullptr, h->d_stats.p);
-            continue;
-        }
+        if (nrand_k == 0) continue;
         // bulk list of this solute molecule, ascending molecule index (src/mddf.jl:406-415)
-        launch(h, k_bulk_flags, dim3((nv_mols + 255) / 256), dim3(256), h->P, (const MdRec *)h->cur->d_list.p, skip, h->cur->d_bulk_flags.p);
-        tmp_bytes = h->cur->d_cub_tmp.n;
-        CK(cub::DeviceSelect::Flagged(h->cur->d_cub_tmp.p, tmp_bytes, cub::CountingInputIterator<int>(0), h->cur->d_bulk_flags.p,
-                                      h->cur->d_bulk_idx.p, sc + 4, nv_mols, h->cur->stream));
+        size_t tmp_bytes2 = h->cur->d_cub_tmp.n;
+        BulkPred pred{(const MdRec *)h->cur->d_list.p, skip, h->P.usecutoff, h->P.dbulk};
+        CK(cub::DeviceSelect::If(h->cur->d_cub_tmp.p, tmp_bytes2, cub::CountingInputIterator<int>(0), h->cur->d_bulk_idx.p, sc + 4,
+                                 nv_mols, pred, h->cur->stream));
         h->stats.kernel_launches += 2;
         long long total = (long long)nrand * nv_mols;
         launch(h, k_filter_rand, dim3((unsigned)((total + 255) / 256)), dim3(256), g, h->P, frame, isolute, skip,
@@ -368,8 +367,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
                (const u64 *)h->cur->d_def_rand.p, (const float2 *)h->cur->d_def_rand_info.p, (const int *)(sc + 3), (MdRec *)nullptr,
-               c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
-        launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)(sc + 2), (const int *)(sc + 3), h->d_stats.p);
+               c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_stats.p, (const int *)(sc + 2), (const int *)(sc + 3));
     }
     return CMX_OK;
 }
@@ -609,7 +607,8 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     // cub temp storage sized for the largest call we make
     size_t t1 = 0, t2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, t1, (int *)nullptr, (int *)nullptr, 1 << 28);
-    cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<int>(0), (unsigned char *)nullptr, (int *)nullptr, (int *)nullptr, (int)std::max<size_t>(nvm, 1));
+    cub::DeviceSelect::If(nullptr, t2, cub::CountingInputIterator<int>(0), (int *)nullptr, (int *)nullptr, (int)std::max<size_t>(nvm, 1),
+                          BulkPred{nullptr, -1, 0, 0.0});
     for (FrameCtx *x_ : h->ctx) CK(x_->d_cub_tmp.ensure(std::max(t1, t2) + 1024));
     CK(cudaDeviceSynchronize());
     return CMX_OK;

@@ -17,6 +17,7 @@ typedef unsigned long long u64;
 // ---- per-frame geometry (passed to kernels by value) --------------------------------------
 struct Geom {
     double m[9], inv[9];      // unit cell, column-major (columns = lattice vectors) and inverse
+    double invl[3];           // 1/L per axis (orthorhombic minimum image)
     double ctr[3];            // centre of the search grid; fp32 positions are stored relative to it
     double elo[3], ehi[3];    // extended AABB = AABB(primary cell) +- margin
     int ortho;
@@ -69,9 +70,11 @@ __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a,
 
 __device__ __forceinline__ void min_image64(const Geom &g, double &x, double &y, double &z) {
     if (g.ortho) {
-        x = dsub(x, dmul(g.m[0], rint(__ddiv_rn(x, g.m[0]))));
-        y = dsub(y, dmul(g.m[4], rint(__ddiv_rn(y, g.m[4]))));
-        z = dsub(z, dmul(g.m[8], rint(__ddiv_rn(z, g.m[8]))));
+        // image count = rint(x * (1/L)); differs from rint(x / L) only within one ulp of a half-integer,
+        // i.e. for |x| = L/2 >= cutoff where both images are equally far
+        x = dsub(x, dmul(g.m[0], rint(dmul(x, g.invl[0]))));
+        y = dsub(y, dmul(g.m[4], rint(dmul(y, g.invl[1]))));
+        z = dsub(z, dmul(g.m[8], rint(dmul(z, g.invl[2]))));
     } else {
         const double *v = g.inv, *m = g.m;
         double s0 = dadd(dadd(dmul(v[0], x), dmul(v[3], y)), dmul(v[6], z));

@@ -251,10 +251,18 @@ k_gen_rand(Geom g, Prob P, uint32_t frame, const float *__restrict__ xv, const f
 }
 
 // tiles never straddle query cells: a cell with n query atoms owns ceil(n/32) tiles
-__global__ void k_tile_count(int nqcells, const int *__restrict__ qcell_count, int *__restrict__ tile_count) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c <= nqcells) tile_count[c] = c < nqcells ? (qcell_count[c] + 31) >> 5 : 0;
-}
+struct TileCountOp { __host__ __device__ __forceinline__ int operator()(int n) const { return (n + 31) >> 5; } };
+
+// bulk molecules of the current solute molecule (inbulk, src/mddf.jl:55-57; the solute itself is skipped in
+// an autocorrelation, :409) -- predicate of the ordered stream compaction
+struct BulkPred {
+    const MdRec *list; int skip_mol, usecutoff; double dbulk;
+    __device__ __forceinline__ bool operator()(int m) const {
+        if (m == skip_mol) return false;
+        const MdRec e = list[m];
+        return usecutoff ? ((e.flags & 1) && e.d > dbulk) : !(e.flags & 1);
+    }
+};
 
 // scatter the counted query atoms into their cell's tiles: qsorted[tile*32 + rank] = {x, y, z, query id};
 // the unused slots of a cell's last tile keep the id -1 (the array is pre-filled with 0xff bytes)
@@ -592,9 +600,11 @@ __global__ void __launch_bounds__(CMX_RESOLVE_THREADS)
 k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const float *__restrict__ xv,
           const float4 *__restrict__ sorted, const int *__restrict__ cell_start, int ncells, const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk_ptr, const u64 *__restrict__ deferred,
           const float2 *__restrict__ deferred_info, const int *__restrict__ deferred_count, MdRec *__restrict__ list,
-          MdRec *__restrict__ rand_list) {
+          MdRec *__restrict__ rand_list, u64 *__restrict__ stats, const int *__restrict__ stat_a, const int *__restrict__ stat_b) {
     __shared__ ExactBest sh[CMX_RESOLVE_THREADS];
     int count = *deferred_count;
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0)   // run statistics: molecules that took the exact path
+        atomicAdd(&stats[1], (u64)(stat_a ? *stat_a : 0) + (u64)(stat_b ? *stat_b : 0));
     (void)ncells;
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         u64 item = deferred[w];

@@ -109,6 +109,7 @@ typedef struct {
     double inv[9];  /* column-major inverse */
     int ortho;
     double w[3];    /* perpendicular widths */
+    double invl[3]; /* 1/L per axis (orthorhombic minimum image) */
     double volume;
 } orc_cell;
 
@@ -132,6 +133,7 @@ void orc_cell_init(orc_cell *c, const double cell[9]) {
         c->inv[1 + 3 * k] = cxa[k] / det;
         c->inv[2 + 3 * k] = axb[k] / det;
     }
+    c->invl[0] = 1.0 / a[0]; c->invl[1] = 1.0 / b[1]; c->invl[2] = 1.0 / cc[2];
     c->w[0] = fabs(det) / sqrt(bxc[0] * bxc[0] + bxc[1] * bxc[1] + bxc[2] * bxc[2]);
     c->w[1] = fabs(det) / sqrt(cxa[0] * cxa[0] + cxa[1] * cxa[1] + cxa[2] * cxa[2]);
     c->w[2] = fabs(det) / sqrt(axb[0] * axb[0] + axb[1] * axb[1] + axb[2] * axb[2]);
@@ -143,9 +145,11 @@ void orc_cell_init(orc_cell *c, const double cell[9]) {
  * pair within the cutoff because CellListMap requires width > 2*cutoff. */
 static void min_image(const orc_cell *c, double dr[3]) {
     if (c->ortho) {
-        dr[0] = dr[0] - c->m[0] * rint(dr[0] / c->m[0]);
-        dr[1] = dr[1] - c->m[4] * rint(dr[1] / c->m[4]);
-        dr[2] = dr[2] - c->m[8] * rint(dr[2] / c->m[8]);
+        /* the image count is rint(dr * (1/L)): identical to rint(dr / L) except within one ulp of a
+         * half-integer, i.e. for |dr| = L/2 >= cutoff, where both images are equally far */
+        dr[0] = dr[0] - c->m[0] * rint(dr[0] * c->invl[0]);
+        dr[1] = dr[1] - c->m[4] * rint(dr[1] * c->invl[1]);
+        dr[2] = dr[2] - c->m[8] * rint(dr[2] * c->invl[2]);
     } else {
         const double *v = c->inv, *m = c->m;
         double s0 = (v[0] * dr[0] + v[3] * dr[1]) + v[6] * dr[2];
