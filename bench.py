@@ -62,6 +62,15 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(config, phase):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t[config][phase]
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -337,8 +346,8 @@ def main():
         step_device(collective=False)
         pe = eng.stats()["pair_evals"] / fps
         eng.set_option("count_pairs", 0); eng.set_option("active_streams", 0)
-        roof = {"bound": "hbm", "kernel": f"k_search ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+        roof = {"bound": "hbm", "kernel": f"k_tile_search ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": ncu_traffic(args.config, "random" if dom.startswith("random") else "real"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": dom_ms / ms_frame if ms_frame > 0 else None,
                 "frame_algorithmic_bytes": b_in + b_rand, "frame_achieved_GBps": (b_in + b_rand) * value / world / 1e9,
                 "pair_evals_per_frame": pe, "pair_evals_per_s": pe * value}

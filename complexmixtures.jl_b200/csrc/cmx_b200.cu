@@ -55,11 +55,11 @@ struct FrameCtx {
     cudaEvent_t ev_end = nullptr;
     DevBuf<int> d_cell_count, d_cell_start;
     DevBuf<float4> d_sorted;
-    DevBuf<u64> d_occ, d_rowmask;
+    DevBuf<u64> d_occ;                 // [8 scalars][cull bitmap][row bitmap]
     DevBuf<float4> d_qpos, d_qsorted, d_res;   // query atoms of the current phase: positions, tile order, results
-    DevBuf<int> d_qcell_count, d_qcell_start, d_tile_count;
+    DevBuf<int> d_qcell_count, d_qcell_start;
     DevBuf<double> d_xexact;
-    DevBuf<unsigned char> d_edt_x, d_bulk_flags;
+    DevBuf<unsigned char> d_edt_x;
     DevBuf<unsigned short> d_edt_xy;
     DevBuf<float> d_lbd2;
     DevBuf<MdRec> d_list;
@@ -71,8 +71,8 @@ struct FrameCtx {
     PairScratch pairs;
     int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
     void release() {
-        d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release(); d_rowmask.release();
-        d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_tile_count.release(); d_xexact.release(); d_edt_x.release(); d_bulk_flags.release();
+        d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release();
+        d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_xexact.release(); d_edt_x.release();
         d_edt_xy.release(); d_lbd2.release(); d_list.release(); d_worklist.release(); d_rand_worklist.release();
         d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_def_real_info.release(); d_def_rand_info.release(); d_scalars.release(); d_cub_tmp.release();
         if (h_scalars) cudaFreeHost(h_scalars);
@@ -86,7 +86,6 @@ struct cmx_handle {
     std::string err;
     int device = 0;
     int path = 1;            // 1 grid path, 2 molecule-pair path
-    int G = 8;               // lanes per solvent molecule in the search kernel
     int nbins = 0;
     size_t ns_atoms = 0, nv_atoms = 0, in_floats = 0;
     double cut_eff = 0;
@@ -309,7 +308,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
     u64 *occ_p = h->cur->d_occ.p + 4, *rowmask_p = occ_p + occ_words;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
-    CK(h->cur->d_qcell_count.ensure(nqc + 1, true)); CK(h->cur->d_qcell_start.ensure(nqc + 1)); CK(h->cur->d_tile_count.ensure(nqc + 1));
+    CK(h->cur->d_qcell_count.ensure(nqc + 1, true)); CK(h->cur->d_qcell_start.ensure(nqc + 1));
     {   // tile array: atoms + padding of each cell's last tile
         size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(c.coordination_number_only ? 0 : c.n_random_samples) * h->nv_atoms);
         CK(h->cur->d_qsorted.ensure(maxq + 32 * nqc));
@@ -509,9 +508,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     h->in_floats = 3 * (c.autocorrelation ? h->nv_atoms : h->ns_atoms + h->nv_atoms);
     h->path = c.path ? c.path : ((c.solute_nmols == 1 || c.solute_natomspermol > 64) ? 1 : 2);
     if (h->path != 1 && h->path != 2) return fail(h, CMX_ERR_ARG, "path must be 0 (auto), 1 (grid) or 2 (molecule pairs)");
-    int G = c.group_lanes ? c.group_lanes : 32;
-    if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");
-    h->G = G;
+    // (cmx_config.group_lanes is accepted for ABI stability and ignored: the search works on 32-query tiles)
     // search grid: a "row" is a (y,z) column of cells cut/4 wide; along x the cells are ~2.5 A so that
     // a row is scanned over a tight x-span.  Query atoms are tiled in cubic cells of ~6 A (about 20-30
     // solvent atoms, one warp).
@@ -586,7 +583,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         h->cur = x_;
         CK(h->cur->d_scalars.ensure(16, true)); 
         CK(h->cur->d_list.ensure(nvm));
-        CK(h->cur->d_bulk_flags.ensure(nvm)); CK(h->cur->d_bulk_idx.ensure(nvm));
+        CK(h->cur->d_bulk_idx.ensure(nvm));
         CK(h->cur->d_worklist.ensure(nvm)); CK(h->cur->d_rand_worklist.ensure(std::max<size_t>(nrand * nvm, 1)));
         CK(h->cur->d_def_real.ensure(nvm)); CK(h->cur->d_def_rand.ensure(std::max<size_t>(nrand * nvm, 1)));
     CK(h->cur->d_def_real_info.ensure(nvm)); CK(h->cur->d_def_rand_info.ensure(std::max<size_t>(nrand * nvm, 1)));
@@ -794,11 +791,7 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
         if (v < 0 || v > (int)h->ctx.size()) return fail(h, CMX_ERR_ARG, "active_streams out of range");
         h->active_ctx = v;
     }
-    else if (n == "group_lanes") {
-        int G = (int)value;
-        if (G != 1 && G != 2 && G != 4 && G != 8 && G != 16 && G != 32) return fail(h, CMX_ERR_ARG, "group_lanes must be a power of two <= 32");
-        h->G = G;
-    } else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
+    else if (n == "group_lanes") { /* ignored */    } else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
     return CMX_OK;
 }
 

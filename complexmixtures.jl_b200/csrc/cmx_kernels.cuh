@@ -472,15 +472,6 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7: bulk flags (inbulk, src/mddf.jl:55-57,406-415); the ordered compaction is a cub::DeviceSelect
-// ---------------------------------------------------------------------------------------------
-__global__ void k_bulk_flags(Prob P, const MdRec *__restrict__ list, int skip_mol, unsigned char *__restrict__ flags) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= P.nv_mols) return;
-    flags[m] = (m != skip_mol) && inbulk(P, list[m]);
-}
-
-// ---------------------------------------------------------------------------------------------
 // K8: cull the random placements by the position of their centre
 // ---------------------------------------------------------------------------------------------
 __global__ void k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol,

@@ -55,7 +55,7 @@ typedef struct cmx_config {
     int32_t path;                     /* 0 auto, 1 grid path (large solute molecule), 2 molecule-pair path */
     int32_t ring_slots;               /* pinned staging slots (0 -> 3)                           */
     int32_t keep_lists;               /* keep per-frame minimum-distance lists for cmx_read_*    */
-    int32_t group_lanes;              /* lanes cooperating on one solvent molecule (0 -> auto)   */
+    int32_t group_lanes;              /* reserved (ignored: the search works on 32-query tiles)  */
     int32_t n_streams;                /* frames in flight on separate compute streams (0 -> 4)   */
     int32_t reserved0;
     double cutoff;                    /* Options.cutoff                                          */

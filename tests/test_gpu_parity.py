@@ -100,11 +100,14 @@ def test_default_options_no_cutoff():
     check(p)
 
 
-@pytest.mark.parametrize("G", [1, 4, 32])
-def test_group_lanes(G):
+@pytest.mark.parametrize("n_streams", [1, 3, 8])
+def test_frames_in_flight_on_several_streams(n_streams):
+    """frames overlap on n_streams compute streams (private scratch, shared integer accumulators):
+    the counters do not depend on how many frames are in flight."""
     d = namd()
-    p = Problem(PROTEIN, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=2), d["protein"][:1], d["tmao"][:1], d["cells"][:1])
-    check(p, engine_kw=dict(group_lanes=G))
+    p = Problem(PROTEIN, TMAO, opts(bulk_range=(8.0, 10.0), n_random_samples=4), [d["protein"][k % 3] for k in range(9)],
+                [d["tmao"][k % 3] for k in range(9)], d["cells"][0])
+    check(p, lists=False, engine_kw=dict(n_streams=n_streams))
 
 
 def _synthetic(triclinic, seed=7, nprot=400, nwat=600, nco=60):
