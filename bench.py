@@ -47,7 +47,7 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=list(CONFIGS))
@@ -80,37 +80,44 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons DURING the timed region: one long-running `nvidia-smi -lms 50`
+    whose lines are time-stamped on arrival; only samples inside [start, stop] are summarised."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.index, self.samples, self._stop = index, [], threading.Event()
-        self.t = threading.Thread(target=self._run, daemon=True)
+        self.index, self.samples, self.t0, self.t1, self.proc = index, [], None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([t.strip() for t in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), [t.strip() for t in line.strip().split(",")]))
 
     def __enter__(self):
-        self.t.start(); return self
+        self.t0 = time.perf_counter(); return self
 
     def __exit__(self, *a):
-        self._stop.set(); self.t.join(timeout=5)
+        self.t1 = time.perf_counter()
+
+    def close(self):
+        if self.proc is not None:
+            self.proc.terminate()
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        inside = [s for t, s in self.samples if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) and len(s) >= 6]
+        if not inside:   # region shorter than the sampling period: fall back to the nearest samples
+            inside = [s for _, s in self.samples[-3:] if len(s) >= 6]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm = sorted(float(s[0]) for s in inside)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][1]), "reasons": reasons, "samples": len(inside)}
 
 
 def build_workload(args, rank, world):
@@ -282,12 +289,15 @@ def main():
     barrier()
     st0 = eng.stats()
     submit_s[0] = 0.0
-    with ClockSampler(local_rank) as clk:
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.15)
+    with sampler as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_device()
         barrier()
         wall = time.perf_counter() - t0
+    sampler.close()
     st1 = eng.stats()
     host_submit_ms = 1e3 * submit_s[0] / args.steps
     dev_ms = st1["gpu_ms_total"] - st0["gpu_ms_total"]
