@@ -293,3 +293,82 @@ def test_slab_solute_spanning_the_cell():
                 [f[wat.indices - 1] for f in fr], s.cell)
     dev, o, stats = check(p)
     assert dev["md_count"].sum() > 1000
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def _tiny(nsol_atoms, solvent_kind, nsolvent, cell, seed=3):
+    from cmx_b200 import synthetic as syn
+    return syn.make_system("tiny", cell=cell, solute_atoms=nsol_atoms, solvents=[("s", solvent_kind, nsolvent)], seed=seed)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_edge_single_atom_solute_and_single_solvent_molecule(path):
+    s = _tiny(1, "water", 1, [40.0, 41.0, 42.0])
+    sol, sv = s.selections["solute"], s.selections["s"]
+    x = s.frame(0)[0]
+    # put the water next to the solute atom so that there is exactly one hit
+    x[sv.indices - 1] += x[sol.indices - 1][0] - x[sv.indices - 1][0] + np.float32(3.0)
+    p = Problem(sol, sv, opts(bulk_range=(6.0, 9.0), n_random_samples=50), [x[sol.indices - 1]], [x[sv.indices - 1]], s.cell)
+    dev, o, _ = check(p, engine_kw=dict(path=path))
+    assert dev["md_count"].sum() == 1.0
+
+
+def test_edge_nothing_within_cutoff():
+    s = _tiny(50, "water", 40, [80.0, 80.0, 80.0])
+    sol, sv = s.selections["solute"], s.selections["s"]
+    x = s.frame(0)[0]
+    one = x[sv.indices - 1][:3].copy()
+    one = one - one[0] + x[sol.indices - 1].mean(axis=0) + np.float32(35.0)   # every molecule stacked 35 A away
+    far = np.tile(one, (40, 1)).astype(np.float32)
+    p = Problem(sol, sv, opts(bulk_range=(5.0, 8.0), n_random_samples=3), [x[sol.indices - 1]], [far], s.cell)
+    dev, o, _ = check(p)
+    assert dev["md_count"].sum() == 0.0 and dev["md_count_random"].sum() > 0   # no bulk molecule -> any molecule is drawn (src/mddf.jl:77-81)
+
+
+def test_edge_monoatomic_solvent_and_nondefault_irefatom():
+    from cmx_b200 import synthetic as syn
+    s = syn.make_system("m", cell=[36.0, 36.0, 36.0], solute_atoms=120, solvents=[("ion", "water", 90)], seed=9)
+    sol, wat = s.selections["solute"], s.selections["ion"]
+    x = s.frame(1)[0]
+    # monoatomic: every atom of the 3-site selection as its own molecule
+    ions = cm.AtomSelection(wat.indices, natomspermol=1)
+    p = Problem(sol, ions, opts(bulk_range=(6.0, 9.0), n_random_samples=5), [x[sol.indices - 1]], [x[ions.indices - 1]], s.cell)
+    check(p)
+    # reference atom = last atom of the molecule (Options(irefatom=3))
+    p = Problem(sol, wat, opts(bulk_range=(6.0, 9.0), n_random_samples=5, irefatom=3), [x[sol.indices - 1]], [x[wat.indices - 1]], s.cell)
+    assert p.irefatom == 3
+    check(p)
+    p = Problem(wat, wat, opts(bulk_range=(6.0, 9.0), n_random_samples=5, irefatom=2), [x[wat.indices - 1]], None, s.cell, autocorrelation=True)
+    check(p, nsolute_lists=2)
+
+
+def test_edge_large_solvent_molecules_and_unwrapped_split_molecules():
+    """solvent molecules of 14 atoms whose atoms sit in different periodic images (a molecule 'broken' by
+    wrapping, as in trajectories written with per-atom wrapping)."""
+    from cmx_b200 import synthetic as syn
+    s = syn.make_system("b", cell=[38.0, 40.0, 39.0], solute_atoms=150, solvents=[("co", "glycerol", 60)], seed=21)
+    sol, co = s.selections["solute"], s.selections["co"]
+    x = s.frame(2)[0].astype(np.float64)
+    rng = np.random.default_rng(5)
+    xv = x[co.indices - 1]
+    xv += rng.integers(-1, 2, size=xv.shape) * np.array([38.0, 40.0, 39.0])   # every ATOM shifted by its own lattice vector
+    p = Problem(sol, co, opts(bulk_range=(6.0, 9.0), n_random_samples=6), [x[sol.indices - 1].astype(np.float32)], [xv.astype(np.float32)], s.cell)
+    check(p)
+    p = Problem(co, co, opts(bulk_range=(6.0, 9.0), n_random_samples=6), [xv.astype(np.float32)], None, s.cell, autocorrelation=True)
+    check(p, nsolute_lists=2)
+
+
+def test_edge_exact_ties_lattice():
+    """atoms on an exact lattice: many exactly equal distances -> every tie must be resolved by (d, j, i)."""
+    g = np.arange(0, 24, 3.0)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    sol = cm.AtomSelection(np.arange(1, 65), nmols=1)
+    sv = cm.AtomSelection(np.arange(65, 65 + 448), natomspermol=2)
+    p = Problem(sol, sv, opts(bulk_range=(4.5, 6.0), n_random_samples=3), [pts[:64]], [pts[64:]], np.diag([24.0, 24.0, 24.0]))
+    dev, o, stats = check(p)
+    assert stats["deferred"] > 0    # the ties went through the exact kernel
+    sv1 = cm.AtomSelection(np.arange(1, 513), natomspermol=2)
+    p = Problem(sv1, sv1, opts(bulk_range=(4.5, 6.0), n_random_samples=3), [pts], None, np.diag([24.0, 24.0, 24.0]), autocorrelation=True)
+    check(p, nsolute_lists=3)
