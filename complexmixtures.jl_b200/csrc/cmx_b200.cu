@@ -355,8 +355,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         CK(cub::DeviceSelect::If(h->cur->d_cub_tmp.p, tmp_bytes2, cub::CountingInputIterator<int>(0), h->cur->d_bulk_idx.p, sc + 4,
                                  nv_mols, pred, h->cur->stream));
         h->stats.kernel_launches += 2;
-        long long total = (long long)nrand * nv_mols;
-        launch(h, k_filter_rand, dim3((unsigned)((total + 255) / 256)), dim3(256), g, h->P, frame, isolute, skip,
+        launch(h, k_filter_rand, dim3((unsigned)((nv_mols + 255) / 256), (unsigned)std::min(nrand, 65535)), dim3(256), g, h->P, frame, isolute, skip,
                (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
         launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, d_solvent, (const float *)h->cur->d_lbd2.p,
                (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),

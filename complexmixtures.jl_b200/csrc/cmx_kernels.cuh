@@ -474,34 +474,44 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
 // ---------------------------------------------------------------------------------------------
 // K8: cull the random placements by the position of their centre
 // ---------------------------------------------------------------------------------------------
-__global__ void k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol,
-                              const float *__restrict__ lbd2, const int *__restrict__ rmax_bits,
-                              int *__restrict__ worklist, int *__restrict__ work_count) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)P.nrand * P.nv_mols;
+// grid.y = sample, grid.x covers the slots; the centre is evaluated in fp32 (its error, ~1e-5 A, is far
+// below the 1e-3 A margin of the test); survivors are appended with one global atomic per block
+__global__ void __launch_bounds__(256)
+k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol, const float *__restrict__ lbd2,
+              const int *__restrict__ rmax_bits, int *__restrict__ worklist, int *__restrict__ work_count) {
+    __shared__ int s_count, s_base;
+    const int mol = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int sample = blockIdx.y; sample < P.nrand; sample += gridDim.y) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
     bool near = false;
-    if (t < total) {
-        int sample = (int)(t / P.nv_mols), mol = (int)(t - (long long)sample * P.nv_mols);
+    if (mol < P.nv_mols && mol != skip_mol) {
         bool mine = P.ns_mols == 1 || ref_solute_of_sample(P, frame, (uint32_t)sample) == isolute;
-        if (mine && mol != skip_mol) {
+        if (mine) {
             float rmax = __int_as_float(*rmax_bits);
             if (rmax > g.rmax_bound) near = true;   // transform window not valid for this radius: no culling
             else {
                 uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
-                double u0 = u01(r0.y), u1 = u01(r0.z), u2 = u01(r0.w);
-                const double *m = g.m;
-                double cx_ = m[0] * u0 + m[3] * u1 + m[6] * u2, cy_ = m[1] * u0 + m[4] * u1 + m[7] * u2,
-                       cz_ = m[2] * u0 + m[5] * u1 + m[8] * u2;
-                float lim = g.cut_hi + rmax + 1e-3f;
-                near = cull_lb2(g, lbd2, (float)(cx_ - g.ctr[0]), (float)(cy_ - g.ctr[1]), (float)(cz_ - g.ctr[2])) <= lim * lim;
+                const float sc = 1.0f / 4294967296.0f;
+                float u0 = ((float)r0.y + 0.5f) * sc, u1 = ((float)r0.z + 0.5f) * sc, u2 = ((float)r0.w + 0.5f) * sc;
+                float cx_ = (float)g.m[0] * u0 + (float)g.m[3] * u1 + (float)g.m[6] * u2 - (float)g.ctr[0];
+                float cy_ = (float)g.m[1] * u0 + (float)g.m[4] * u1 + (float)g.m[7] * u2 - (float)g.ctr[1];
+                float cz_ = (float)g.m[2] * u0 + (float)g.m[5] * u1 + (float)g.m[8] * u2 - (float)g.ctr[2];
+                float lim = g.cut_hi + rmax + 2e-3f;
+                near = cull_lb2(g, lbd2, cx_, cy_, cz_) <= lim * lim;
             }
         }
     }
     unsigned ball = __ballot_sync(0xffffffffu, near);
-    int lane = threadIdx.x & 31, base = 0;
-    if (lane == 0 && ball) base = atomicAdd(work_count, __popc(ball));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (near) worklist[base + __popc(ball & ((1u << lane) - 1))] = (int)t;
+    int lane = threadIdx.x & 31, wbase = 0;
+    if (lane == 0 && ball) wbase = atomicAdd(&s_count, __popc(ball));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(work_count, s_count);
+    __syncthreads();
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (near) worklist[s_base + wbase + __popc(ball & ((1u << lane) - 1))] = sample * P.nv_mols + mol;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
