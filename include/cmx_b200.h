@@ -119,7 +119,8 @@ int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solv
  * depend on which GPU processes the frame.  weight = 0 frames must not be submitted. */
 int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, const double cell[9]);
 
-/* Same, for coordinates already resident in device memory (device pointers to fp32 xyz). */
+/* Same, for coordinates already resident in device memory (device pointers to fp32 xyz).  The arrays
+ * must stay valid and unmodified until cmx_sync: up to n_streams frames are in flight. */
 int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const float *d_solvent_xyz,
                                 int64_t frame_index, double weight, const double cell[9]);
 

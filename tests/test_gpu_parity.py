@@ -372,3 +372,36 @@ def test_edge_exact_ties_lattice():
     sv1 = cm.AtomSelection(np.arange(1, 513), natomspermol=2)
     p = Problem(sv1, sv1, opts(bulk_range=(4.5, 6.0), n_random_samples=3), [pts], None, np.diag([24.0, 24.0, 24.0]), autocorrelation=True)
     check(p, nsolute_lists=3)
+
+
+def test_counters_device_block_is_the_allreduce_payload():
+    """cmx_counters_device exposes ONE contiguous uint64 block (the payload of the single all-reduce that
+    replaces sum!, src/results.jl:629-649); summing two engines' blocks on the device and reading the result
+    back through cmx_finish equals one engine that processed all frames."""
+    import torch
+    d = namd()
+    o = opts(bulk_range=(8.0, 10.0), n_random_samples=3)
+    p = Problem(PROTEIN, TMAO, o, d["protein"], d["tmao"], d["cells"])
+    full = p.engine(); ref = p.run_engine(full); full.close()
+
+    def wrap(eng):
+        ptr, n = eng.counters_device()
+
+        class W:
+            pass
+        w = W()
+        w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+        return torch.as_tensor(w, device="cuda:0"), n
+    a, b = p.engine(), p.engine()
+    for k, (xs, xv, cell, fid) in enumerate(zip(p.xs, p.xv, p.cells, p.frame_ids)):
+        (a if k % 2 == 0 else b).submit_arrays(xs, xv, cell, frame_index=fid)
+    a.sync(); b.sync()
+    ta, n = wrap(a); tb, _ = wrap(b)
+    nb = 500
+    assert n == nb * (4 + 2 * 1463 + 2 * 14)
+    ta += tb                              # what ncclAllReduce(sum) does across ranks
+    torch.cuda.synchronize()
+    got = a.finish()
+    a.close(); b.close()
+    for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count", "solvent_group_count_random"):
+        assert np.array_equal(got[k], ref[k]), k
