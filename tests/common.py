@@ -98,3 +98,29 @@ def assert_lists_equal(dev, ref, *, dtol=0.0, what="list"):
     mr = m & r_ref
     dr = np.abs(dev["d_ref_atom"][mr] - ref["d_ref_atom"][mr])
     assert dr.size == 0 or dr.max() <= dtol, f"{what}: max |d_ref - d_ref_ref| = {dr.max()}"
+
+
+def write_dcd(path, frames, cells):
+    """Minimal NAMD/CHARMM DCD writer with unit-cell records (layout read by src/trajectory_formats/NamdDCD.jl:
+    header, title, natoms; per frame [A, gamma, B, beta, alpha, C] + x, y, z Float32 records)."""
+    import struct
+    frames = np.asarray(frames, dtype=np.float32)
+    nf, n = frames.shape[0], frames.shape[1]
+
+    def rec(f, payload):
+        f.write(struct.pack("<i", len(payload))); f.write(payload); f.write(struct.pack("<i", len(payload)))
+    with open(path, "wb") as f:
+        icntrl = [0] * 20
+        icntrl[0], icntrl[1], icntrl[2], icntrl[3], icntrl[10], icntrl[19] = nf, 0, 1, nf, 1, 24
+        hdr = b"CORD" + struct.pack("<9i", *icntrl[:9]) + struct.pack("<f", 1.0) + struct.pack("<10i", *icntrl[10:])
+        rec(f, hdr)
+        rec(f, struct.pack("<i", 1) + b"written by the cmx-b200 test-suite".ljust(80))
+        rec(f, struct.pack("<i", n))
+        for k in range(nf):
+            c = np.asarray(cells[k] if np.ndim(cells) == 3 else cells, dtype=np.float64)
+            a, b, cc = c[:, 0], c[:, 1], c[:, 2]
+            A, B, C_ = np.linalg.norm(a), np.linalg.norm(b), np.linalg.norm(cc)
+            ang = lambda u, v: np.degrees(np.arccos(np.clip(u @ v / np.linalg.norm(u) / np.linalg.norm(v), -1, 1)))
+            rec(f, struct.pack("<6d", A, ang(a, b), B, ang(a, cc), ang(b, cc), C_))
+            for d in range(3):
+                rec(f, frames[k, :, d].astype("<f4").tobytes())

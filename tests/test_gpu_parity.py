@@ -405,3 +405,27 @@ def test_counters_device_block_is_the_allreduce_payload():
     a.close(); b.close()
     for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count", "solvent_group_count_random"):
         assert np.array_equal(got[k], ref[k]), k
+
+
+def test_public_mddf_from_dcd_file(tmp_path):
+    """mddf(trajectory_file, solute, solvent, options) through the DCD reader feeding the pinned ring, with
+    firstframe / stride / frame_weights handled like goto_nextframe! (src/mddf.jl:95-111)."""
+    from common import write_dcd
+    d = namd()
+    frames = np.concatenate([d["protein"], d["tmao"]], axis=1)
+    path = str(tmp_path / "t.dcd")
+    write_dcd(path, frames, d["cells"])
+    sol = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+    tm = cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14)
+    opt = opts(bulk_range=(8.0, 10.0), n_random_samples=4)
+    R = cm.mddf(path, sol, tm, opt, frame_weights=[1.0, 0.0, 2.0])
+    p = Problem(sol, tm, opt, d["protein"], d["tmao"], d["cells"], weights=[1.0, 0.0, 2.0])
+    o, _ = p.oracle()
+    ref = orc.finalresults(o.counters(), nmols_solute=1, nmols_solvent=181, autocorrelation=False, n_random_samples=4,
+                           binstep=0.02, dbulk=8.0, cutoff=10.0, usecutoff=True, Q=3.0)
+    assert np.allclose(R.md_count, ref.md_count, rtol=1e-13) and np.allclose(R.mddf, ref.mddf, rtol=1e-12)
+    assert np.isclose(R.volume.total, ref.volume_total) and R.files[0].irefatom == 1
+    Rs = cm.mddf(path, tm, opts(bulk_range=(8.0, 10.0), n_random_samples=2, firstframe=2))   # mddf(file, solute_and_solvent, options)
+    assert Rs.autocorrelation and Rs.md_count.sum() > 0
+    C = cm.coordination_number(path, sol, tm, opts(lastframe=1))
+    assert C.coordination_number[np.argmax(C.d > 3)] == 7.0 and np.all(C.md_count_random == 0)

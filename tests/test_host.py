@@ -201,3 +201,30 @@ def test_frame_sharding_allreduce_gloo_world2(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_dcd_reader_roundtrip(tmp_path):
+    """NamdDCD reader (src/trajectory_formats/NamdDCD.jl:141-188): records, selection gather, unit cell."""
+    from common import namd, write_dcd
+    d = namd()
+    frames = np.concatenate([d["protein"], d["tmao"]], axis=1)
+    path = str(tmp_path / "t.dcd")
+    tri = np.array([[40.0, 8.0, 5.0], [0.0, 38.0, 7.0], [0.0, 0.0, 36.0]])
+    write_dcd(path, frames, [d["cells"][0], tri, d["cells"][2]])
+    sol = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+    tm = cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14)
+    t = cm.make_trajectory(path, sol, tm)
+    assert isinstance(t, cm.NamdDCD) and t.nframes == 3 and t.natoms_file == 3997
+    t.open()
+    for k in range(3):
+        xs, xv = t.nextframe()
+        assert np.array_equal(xs, d["protein"][k]) and np.array_equal(xv, d["tmao"][k])
+        want = tri if k == 1 else d["cells"][k]
+        assert np.allclose(t.getunitcell(), want, rtol=1e-12, atol=1e-9)
+    t.close()
+    meta = cm.trajectory_metadata(t, cm.Options(silent=True, lastframe=2))
+    assert meta.irefatom == 1 and meta.lastframe_read == 2 and meta.n_groups_solute == 1463 and meta.n_groups_solvent == 14
+    with pytest.raises(ValueError):
+        cm.trajectory_metadata(t, cm.Options(silent=True, lastframe=7))
+    with pytest.raises(ValueError):
+        cm.trajectory_metadata(t, cm.Options(silent=True, irefatom=15))
