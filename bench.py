@@ -350,13 +350,16 @@ def main():
         ms_frame = (s1["gpu_ms_total"] - s0["gpu_ms_total"]) / fps
         b_in, b_rand = algorithmic_bytes(w)
         peak, peak_src = peaks()
+        pair_path = w["solute"].nmols > 1 and w["solute"].natomspermol <= 64     # the library's auto rule (cmx_config.path = 0)
+        kname = ("k_pair_random", "k_pairs") if pair_path else ("k_tile_search", "k_tile_search")
         dom_ms, dom_bytes, dom = (ms_rand, b_rand, "random-phase search") if ms_rand >= ms_real else (ms_real, b_in, "real-phase search")
+        kernel_name = kname[0] if ms_rand >= ms_real else kname[1]
         ach = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         eng.reset(); eng.set_option("count_pairs", 1)
         step_device(collective=False)
         pe = eng.stats()["pair_evals"] / fps
         eng.set_option("count_pairs", 0); eng.set_option("active_streams", 0)
-        roof = {"bound": "hbm", "kernel": f"k_tile_search ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        roof = {"bound": "hbm", "kernel": f"{kernel_name} ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu_traffic(args.config, "random" if dom.startswith("random") else "real"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": dom_ms / ms_frame if ms_frame > 0 else None,
                 "frame_algorithmic_bytes": b_in + b_rand, "frame_achieved_GBps": (b_in + b_rand) * value / world / 1e9,

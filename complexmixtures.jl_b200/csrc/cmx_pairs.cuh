@@ -130,19 +130,44 @@ struct PairFound {
 
 __device__ __forceinline__ void upd(float d2, float &b1, float &b2) { if (d2 < b1) { b2 = b1; b1 = d2; } else b2 = fminf(b2, d2); }
 
+// offa: float4 per atom of a (x, y, z, -) in shared memory; offb: xyz triplets of b in global memory.
+// The main loop only tracks best / second best; the reference-atom rows (atoms of a -> ref atom of b and, in
+// the symmetric pass, atoms of b -> ref atom of a) are re-evaluated afterwards (napm_a + napm_b extra pairs).
 template <bool SYM>
-__device__ __forceinline__ PairFound eval_pair(const float *__restrict__ offa /* smem or global */, int napm_a,
+__device__ __forceinline__ PairFound eval_pair(const float4 *__restrict__ offa, int napm_a,
                                                const float *__restrict__ offb, int napm_b, float Dx, float Dy,
                                                float Dz, int irefb, int irefa) {
     PairFound F; F.b1 = F.b2 = F.r1 = F.r2 = F.q1 = F.q2 = CUDART_INF_F; F.i = F.j = F.ri = F.qj = -1;
+    int best_pair = 0, pair = 0;          // running index j * napm_a + i of the current / best atom pair
     for (int j = 0; j < napm_b; ++j) {
         float vx = Dx + offb[3 * j], vy = Dy + offb[3 * j + 1], vz = Dz + offb[3 * j + 2];
-        for (int i = 0; i < napm_a; ++i) {
-            float dx = vx - offa[3 * i], dy = vy - offa[3 * i + 1], dz = vz - offa[3 * i + 2];
+#pragma unroll 2
+        for (int i = 0; i < napm_a; ++i, ++pair) {
+            float4 a = offa[i];
+            float dx = vx - a.x, dy = vy - a.y, dz = vz - a.z;
             float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            if (d2 < F.b1) { F.b2 = F.b1; F.b1 = d2; F.i = i; F.j = j; } else F.b2 = fminf(F.b2, d2);
-            if (j == irefb) { if (d2 < F.r1) { F.r2 = F.r1; F.r1 = d2; F.ri = i; } else F.r2 = fminf(F.r2, d2); }
-            if (SYM && i == irefa) { if (d2 < F.q1) { F.q2 = F.q1; F.q1 = d2; F.qj = j; } else F.q2 = fminf(F.q2, d2); }
+            F.b2 = fminf(F.b2, fmaxf(d2, F.b1));
+            if (d2 < F.b1) { F.b1 = d2; best_pair = pair; }
+        }
+    }
+    F.j = best_pair / napm_a; F.i = best_pair - F.j * napm_a;
+    {   // atoms of a -> reference atom of b
+        float vx = Dx + offb[3 * irefb], vy = Dy + offb[3 * irefb + 1], vz = Dz + offb[3 * irefb + 2];
+        for (int i = 0; i < napm_a; ++i) {
+            float4 a = offa[i];
+            float dx = vx - a.x, dy = vy - a.y, dz = vz - a.z;
+            float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            F.r2 = fminf(F.r2, fmaxf(d2, F.r1));
+            if (d2 < F.r1) { F.r1 = d2; F.ri = i; }
+        }
+    }
+    if (SYM) {   // atoms of b -> reference atom of a
+        float4 a = offa[irefa];
+        for (int j = 0; j < napm_b; ++j) {
+            float dx = Dx + offb[3 * j] - a.x, dy = Dy + offb[3 * j + 1] - a.y, dz = Dz + offb[3 * j + 2] - a.z;
+            float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            F.q2 = fminf(F.q2, fmaxf(d2, F.q1));
+            if (d2 < F.q1) { F.q1 = d2; F.qj = j; }
         }
     }
     return F;
@@ -192,20 +217,25 @@ __device__ __forceinline__ void finish_pair(const Geom &g, const PairGeom &pg, c
 // ---------------------------------------------------------------------------------------------
 #define CMX_PAIR_WARPS 4
 template <bool SYM>
-__global__ void __launch_bounds__(CMX_PAIR_WARPS * 32)
+__global__ void __launch_bounds__(CMX_PAIR_WARPS * 32, 6)
 k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *__restrict__ xv, MolData sol,
         MolData solv, const int *__restrict__ cell_start, const int *__restrict__ sorted_id,
         const double *__restrict__ s_anchor, const float *__restrict__ s_rad, const int *__restrict__ ra_solv_bits,
-        u64 *__restrict__ deferred, int *__restrict__ def_count, size_t def_cap, u64 *__restrict__ pair_evals) {
-    extern __shared__ float smem[];
+        u64 *__restrict__ deferred, int *__restrict__ def_count, size_t def_cap, u64 *__restrict__ pair_evals, int nsplit) {
+    extern __shared__ float4 smem4[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *offa = smem + (size_t)warp * (3 * P.ns_apm);
-    int *queue = (int *)(smem + (size_t)CMX_PAIR_WARPS * 3 * P.ns_apm) + warp * 64;
+    float4 *offa = smem4 + (size_t)warp * P.ns_apm;
+    int *queue = (int *)(smem4 + (size_t)CMX_PAIR_WARPS * P.ns_apm) + warp * 64;
     const float ra_solv_max = __int_as_float(*ra_solv_bits);
     unsigned long long npairs = 0;
-    for (int a = blockIdx.x * CMX_PAIR_WARPS + warp; a < P.ns_mols; a += gridDim.x * CMX_PAIR_WARPS) {
+    // a solute molecule's neighbour cells are dealt to `nsplit` warps (more warps in flight for few molecules)
+    for (int task = blockIdx.x * CMX_PAIR_WARPS + warp; task < P.ns_mols * nsplit; task += gridDim.x * CMX_PAIR_WARPS) {
+        const int a = task / nsplit, part = task - a * nsplit;
         __syncwarp();
-        for (int t = lane; t < 3 * P.ns_apm; t += 32) offa[t] = sol.off[(size_t)a * 3 * P.ns_apm + t];
+        for (int t = lane; t < P.ns_apm; t += 32) {
+            const float *o = sol.off + ((size_t)a * P.ns_apm + t) * 3;
+            offa[t] = make_float4(o[0], o[1], o[2], 0.f);
+        }
         __syncwarp();
         const double ax = sol.anchor[3 * (size_t)a], ay = sol.anchor[3 * (size_t)a + 1], az = sol.anchor[3 * (size_t)a + 2];
         const float ra = sol.rad[a];
@@ -232,11 +262,12 @@ k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *
             npairs += (unsigned long long)P.ns_apm * P.nv_apm;
             finish_pair<SYM>(g, pg, P, F, ok, xs, xv, a, b, deferred, def_count, def_cap);
         };
-        for (int cc = 0; cc < ncell; ++cc) {
-            int ix = cc % cnt[0], iy = (cc / cnt[0]) % cnt[1], iz = cc / (cnt[0] * cnt[1]);
-            int cx = (lo[0] + ix) % pg.n[0]; if (cx < 0) cx += pg.n[0];
-            int cy = (lo[1] + iy) % pg.n[1]; if (cy < 0) cy += pg.n[1];
-            int cz = (lo[2] + iz) % pg.n[2]; if (cz < 0) cz += pg.n[2];
+        for (int cc = part; cc < ncell; cc += nsplit) {
+            int iz = cc / (cnt[0] * cnt[1]); int rem = cc - iz * (cnt[0] * cnt[1]);
+            int iy = rem / cnt[0], ix = rem - iy * cnt[0];
+            int cx = lo[0] + ix; cx += cx < 0 ? pg.n[0] : 0; cx -= cx >= pg.n[0] ? pg.n[0] : 0;
+            int cy = lo[1] + iy; cy += cy < 0 ? pg.n[1] : 0; cy -= cy >= pg.n[1] ? pg.n[1] : 0;
+            int cz = lo[2] + iz; cz += cz < 0 ? pg.n[2] : 0; cz -= cz >= pg.n[2] ? pg.n[2] : 0;
             int c = (cz * pg.n[1] + cy) * pg.n[0] + cx;
             int beg = cell_start[c], end = cell_start[c + 1];
             for (int base = beg; base < end; base += 32) {

@@ -27,7 +27,7 @@ PairGeom make_pair_geom(cmx_handle *h, const Geom &g) {
 int pairs_create(cmx_handle *h) {
     const cmx_config &c = h->cfg;
     PairScratch &S = h->cur->pairs;
-    if (c.solute_natomspermol > 1024) return fail(h, CMX_ERR_ARG, "molecule-pair path: solute_natomspermol > 1024 (use path=1)");
+    if (c.solute_natomspermol > 512) return fail(h, CMX_ERR_ARG, "molecule-pair path: solute_natomspermol > 512 (use path=1)");
     if (c.solute_nmols >= (1 << 24) || c.solvent_nmols >= (1 << 24) || c.n_random_samples >= 65535)
         return fail(h, CMX_ERR_ARG, "molecule-pair path: too many molecules/samples for the deferred-item encoding");
     size_t nsm = c.solute_nmols, nvm = c.solvent_nmols, nrand = std::max(1, h->P.nrand);
@@ -113,16 +113,19 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     h->stats.kernel_launches += 2;
     launch(h, k_anchor_bin<true>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)S.cell_start,
            S.sorted_id, S.s_anchor, S.s_rad);
-    size_t smem = sizeof(float) * CMX_PAIR_WARPS * 3 * c.solute_natomspermol + sizeof(int) * CMX_PAIR_WARPS * 64;
-    int nblk = std::min((c.solute_nmols + CMX_PAIR_WARPS - 1) / CMX_PAIR_WARPS, h->num_sms * 16);
+    size_t smem = sizeof(float4) * CMX_PAIR_WARPS * c.solute_natomspermol + sizeof(int) * CMX_PAIR_WARPS * 64;
+    // (measured on C3: splitting a molecule's cells over several warps lowers the queue fill and is slower)
+    int nsplit = c.solute_nmols >= h->num_sms * 8 ? 1 : std::max(1, std::min(8, (h->num_sms * 8 + c.solute_nmols - 1) / c.solute_nmols));
+    long long ntask = (long long)c.solute_nmols * nsplit;
+    int nblk = (int)std::min<long long>((ntask + CMX_PAIR_WARPS - 1) / CMX_PAIR_WARPS, (long long)h->num_sms * 32);
     u64 *pe = h->count_pairs ? h->d_stats.p : nullptr;
     cudaEvent_t ev = prof_begin(h);
     if (c.autocorrelation) {
         k_pairs<true><<<nblk, CMX_PAIR_WARPS * 32, smem, h->cur->stream>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
-            S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe);
+            S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe, nsplit);
     } else {
         k_pairs<false><<<nblk, CMX_PAIR_WARPS * 32, smem, h->cur->stream>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
-            S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe);
+            S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe, nsplit);
     }
     h->stats.kernel_launches++;
     prof_end(h, ev);

@@ -2,6 +2,6 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1; tail -1 gpurun_out/build.log
-timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 120 --csv --log-file gpurun_out/launches_c5.csv \
-   python bench.py --config C5 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --frames-per-step 4 --streams 1 > gpurun_out/ncu_c5.log 2>&1
-tail -2 gpurun_out/ncu_c5.log | cut -c1-300
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pairs -s 3 -c 1 -f -o gpurun_out/prof_pairs \
+   python bench.py --config C3 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --frames-per-step 8 --streams 1 > gpurun_out/ncu_pairs.log 2>&1
+tail -1 gpurun_out/ncu_pairs.log | cut -c1-200
