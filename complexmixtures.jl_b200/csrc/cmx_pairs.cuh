@@ -42,6 +42,7 @@ struct PairScratch {
     int *cell_count = nullptr, *cell_start = nullptr;   // anchor cells
     int *sorted_id = nullptr;                            // solvent molecule ids sorted by cell
     double *s_anchor = nullptr; float *s_rad = nullptr;  // gathered in sorted order
+    float4 *s_anchor4 = nullptr;                         // fp32 {x, y, z (grid-relative), radius} for the candidate pre-test
     MdRec *ref_lists = nullptr;                          // [nrand][nv_mols]
     int *bulk_idx = nullptr, *n_bulk = nullptr;          // [nrand][nv_mols], [nrand]
     u64 *deferred = nullptr; int *def_count = nullptr;   // [cap], [2] (count, overflow)
@@ -87,6 +88,23 @@ __global__ void k_mol_prep(Geom g, const float *__restrict__ x, int nmols, int n
     }
 }
 
+// fp32 minimum image for conservative pre-tests (error ~1e-5 * L; callers add a 1e-2 A margin)
+__device__ __forceinline__ void min_image32(const Geom &g, float &x, float &y, float &z) {
+    if (g.ortho) {
+        x -= (float)g.m[0] * rintf(x * (float)g.invl[0]);
+        y -= (float)g.m[4] * rintf(y * (float)g.invl[1]);
+        z -= (float)g.m[8] * rintf(z * (float)g.invl[2]);
+    } else {
+        float s0 = (float)g.inv[0] * x + (float)g.inv[3] * y + (float)g.inv[6] * z;
+        float s1 = (float)g.inv[1] * x + (float)g.inv[4] * y + (float)g.inv[7] * z;
+        float s2 = (float)g.inv[2] * x + (float)g.inv[5] * y + (float)g.inv[8] * z;
+        s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
+        x = (float)g.m[0] * s0 + (float)g.m[3] * s1 + (float)g.m[6] * s2;
+        y = (float)g.m[1] * s0 + (float)g.m[4] * s1 + (float)g.m[7] * s2;
+        z = (float)g.m[2] * s0 + (float)g.m[5] * s1 + (float)g.m[8] * s2;
+    }
+}
+
 __device__ __forceinline__ void anchor_cell(const Geom &g, const PairGeom &pg, const double *a, int &cx, int &cy, int &cz) {
     double s0, s1, s2;
     if (g.ortho) { s0 = a[0] / g.m[0]; s1 = a[1] / g.m[4]; s2 = a[2] / g.m[8]; }
@@ -105,7 +123,7 @@ __device__ __forceinline__ void anchor_cell(const Geom &g, const PairGeom &pg, c
 template <bool SCATTER>
 __global__ void k_anchor_bin(Geom g, PairGeom pg, MolData md, int nmols, int *__restrict__ cell_count,
                              const int *__restrict__ cell_start, int *__restrict__ sorted_id,
-                             double *__restrict__ s_anchor, float *__restrict__ s_rad) {
+                             double *__restrict__ s_anchor, float *__restrict__ s_rad, float4 *__restrict__ s_anchor4) {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmols) return;
     int cx, cy, cz; anchor_cell(g, pg, md.anchor + 3 * (size_t)m, cx, cy, cz);
@@ -118,6 +136,8 @@ __global__ void k_anchor_bin(Geom g, PairGeom pg, MolData md, int nmols, int *__
         s_anchor[3 * (size_t)slot + 1] = md.anchor[3 * (size_t)m + 1];
         s_anchor[3 * (size_t)slot + 2] = md.anchor[3 * (size_t)m + 2];
         s_rad[slot] = md.rad[m];
+        s_anchor4[slot] = make_float4((float)(md.anchor[3 * (size_t)m] - g.ctr[0]), (float)(md.anchor[3 * (size_t)m + 1] - g.ctr[1]),
+                                      (float)(md.anchor[3 * (size_t)m + 2] - g.ctr[2]), md.rad[m]);
     }
 }
 
@@ -220,7 +240,8 @@ template <bool SYM>
 __global__ void __launch_bounds__(CMX_PAIR_WARPS * 32, 6)
 k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *__restrict__ xv, MolData sol,
         MolData solv, const int *__restrict__ cell_start, const int *__restrict__ sorted_id,
-        const double *__restrict__ s_anchor, const float *__restrict__ s_rad, const int *__restrict__ ra_solv_bits,
+        const double *__restrict__ s_anchor, const float *__restrict__ s_rad, const float4 *__restrict__ s_anchor4,
+        const int *__restrict__ ra_solv_bits,
         u64 *__restrict__ deferred, int *__restrict__ def_count, size_t def_cap, u64 *__restrict__ pair_evals, int nsplit) {
     extern __shared__ float4 smem4[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,10 +260,11 @@ k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *
         __syncwarp();
         const double ax = sol.anchor[3 * (size_t)a], ay = sol.anchor[3 * (size_t)a + 1], az = sol.anchor[3 * (size_t)a + 2];
         const float ra = sol.rad[a];
+        const float axf = (float)(ax - g.ctr[0]), ayf = (float)(ay - g.ctr[1]), azf = (float)(az - g.ctr[2]);
         const float reach = pg.cut_hi + ra + ra_solv_max + 1e-3f;
         // single-image regime: every candidate's atom-pair vectors built from ONE image of the anchor
         // difference are shorter than half the smallest cell width, hence true minimum images
-        const bool regime = pg.cut_hi + 2.f * (ra + ra_solv_max) + 2e-3f < pg.half_wmin;
+        const bool regime = pg.cut_hi + 2.f * (ra + ra_solv_max) + 3e-2f < pg.half_wmin;
         int c0[3]; { double aa[3] = {ax, ay, az}; anchor_cell(g, pg, aa, c0[0], c0[1], c0[2]); }
         int lo[3], cnt[3];
         for (int k = 0; k < 3; ++k) {
@@ -276,10 +298,10 @@ k_pairs(Geom g, PairGeom pg, Prob P, const float *__restrict__ xs, const float *
                 if (sidx < end) {
                     int b = sorted_id[sidx];
                     if (!(SYM && b <= a)) {   // autocorrelation: each unordered pair once; never the molecule itself
-                        double dx = s_anchor[3 * (size_t)sidx] - ax, dy = s_anchor[3 * (size_t)sidx + 1] - ay,
-                               dz = s_anchor[3 * (size_t)sidx + 2] - az;
-                        min_image64(g, dx, dy, dz);
-                        double lim = (double)pg.cut_hi + ra + s_rad[sidx] + 1e-3;
+                        float4 c4 = __ldg(&s_anchor4[sidx]);            // fp32 pre-test with a 1e-2 A margin; exact Delta later
+                        float dx = c4.x - axf, dy = c4.y - ayf, dz = c4.z - azf;
+                        min_image32(g, dx, dy, dz);
+                        float lim = pg.cut_hi + ra + c4.w + 1e-2f;
                         pass = dx * dx + dy * dy + dz * dz <= lim * lim;
                     }
                 }

@@ -47,6 +47,7 @@ int pairs_create(cmx_handle *h) {
     CK(cudaMalloc(&S.sorted_id, sizeof(int) * nvm));
     CK(cudaMalloc(&S.s_anchor, sizeof(double) * 3 * nvm));
     CK(cudaMalloc(&S.s_rad, sizeof(float) * nvm));
+    CK(cudaMalloc(&S.s_anchor4, sizeof(float4) * nvm));
     CK(cudaMalloc(&S.ref_lists, sizeof(MdRec) * nrand * nvm));
     CK(cudaMalloc(&S.bulk_idx, sizeof(int) * nrand * nvm));
     CK(cudaMalloc(&S.n_bulk, sizeof(int) * nrand));
@@ -69,7 +70,7 @@ void pairs_release(cmx_handle *h) {
     if (S.solv.off) cudaFree(S.solv.off);
     if (S.solv.rad) cudaFree(S.solv.rad);
     if (!shared) { if (S.sol.anchor) cudaFree(S.sol.anchor); if (S.sol.off) cudaFree(S.sol.off); if (S.sol.rad) cudaFree(S.sol.rad); }
-    void *ptrs[] = {S.cell_count, S.cell_start, S.sorted_id, S.s_anchor, S.s_rad, S.ref_lists, S.bulk_idx, S.n_bulk, S.deferred, S.def_count, S.d_radii};
+    void *ptrs[] = {S.s_anchor4, S.cell_count, S.cell_start, S.sorted_id, S.s_anchor, S.s_rad, S.ref_lists, S.bulk_idx, S.n_bulk, S.deferred, S.def_count, S.d_radii};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (S.h_radii) cudaFreeHost(S.h_radii);
     S = PairScratch{};
@@ -107,12 +108,12 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     CK(cudaMemsetAsync(S.def_count, 0, sizeof(int) * 1, h->cur->stream));
     int nvm = c.solvent_nmols;
     launch(h, k_anchor_bin<false>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)nullptr,
-           (int *)nullptr, (double *)nullptr, (float *)nullptr);
+           (int *)nullptr, (double *)nullptr, (float *)nullptr, (float4 *)nullptr);
     size_t tmp_bytes = h->cur->d_cub_tmp.n;
     CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, S.cell_count, S.cell_start, (int)(ncells + 1), h->cur->stream));
     h->stats.kernel_launches += 2;
     launch(h, k_anchor_bin<true>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)S.cell_start,
-           S.sorted_id, S.s_anchor, S.s_rad);
+           S.sorted_id, S.s_anchor, S.s_rad, S.s_anchor4);
     size_t smem = sizeof(float4) * CMX_PAIR_WARPS * c.solute_natomspermol + sizeof(int) * CMX_PAIR_WARPS * 64;
     // (measured on C3: splitting a molecule's cells over several warps lowers the queue fill and is slower)
     int nsplit = c.solute_nmols >= h->num_sms * 8 ? 1 : std::max(1, std::min(8, (h->num_sms * 8 + c.solute_nmols - 1) / c.solute_nmols));
@@ -122,10 +123,10 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     cudaEvent_t ev = prof_begin(h);
     if (c.autocorrelation) {
         k_pairs<true><<<nblk, CMX_PAIR_WARPS * 32, smem, h->cur->stream>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
-            S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe, nsplit);
+            S.sorted_id, S.s_anchor, S.s_rad, S.s_anchor4, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe, nsplit);
     } else {
         k_pairs<false><<<nblk, CMX_PAIR_WARPS * 32, smem, h->cur->stream>>>(g, pg, h->P, d_solute, d_solvent, S.sol, S.solv, S.cell_start,
-            S.sorted_id, S.s_anchor, S.s_rad, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe, nsplit);
+            S.sorted_id, S.s_anchor, S.s_rad, S.s_anchor4, S.d_radii + 1, S.deferred, S.def_count, S.def_cap, pe, nsplit);
     }
     h->stats.kernel_launches++;
     prof_end(h, ev);
