@@ -110,6 +110,7 @@ struct cmx_handle {
     FrameCtx *cur = nullptr;
     int active_ctx = 0;             // contexts actually used (option "active_streams"; 0 = all)
     float rmax_bound = 0.f;
+    int sample_chunk = 1;           // samples of the random phase per pass (grid path)
     // bookkeeping
     double cur_weight = 1.0; bool have_weight = false;
     double volume_total = 0, sum_weights = 0;
@@ -268,7 +269,7 @@ void prof_collect(cmx_handle *h) {
 // one search phase (real or random) over the molecules of a work list: tile the query atoms, search, combine
 template <bool RANDOM>
 int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv, const int *worklist, const int *work_count,
-                 size_t max_atoms, MdRec *list, u64 *deferred, float2 *def_info, int *def_count, int tag) {
+                 size_t max_atoms, MdRec *list, u64 *deferred, float2 *def_info, int *def_count, int tag, int s0) {
     FrameCtx &x = *h->cur;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
     // (query positions, res and the per-cell counts were produced by k_gen_*)
@@ -290,7 +291,7 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
                 (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
     prof_end(h, pe);
     launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
-           (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count);
+           (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count, s0);
     return CMX_OK;
 }
 
@@ -310,7 +311,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
     CK(h->cur->d_qcell_count.ensure(nqc + 1, true)); CK(h->cur->d_qcell_start.ensure(nqc + 1));
     {   // tile array: atoms + padding of each cell's last tile
-        size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(c.coordination_number_only ? 0 : c.n_random_samples) * h->nv_atoms);
+        size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(c.coordination_number_only ? 0 : h->sample_chunk) * h->nv_atoms);
         CK(h->cur->d_qsorted.ensure(maxq + 32 * nqc));
     }
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
@@ -340,7 +341,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->cur->d_lbd2.p,
                (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
         { int rc = search_phase<false>(h, g, xs, d_solvent, h->cur->d_worklist.p, sc + 0, h->nv_atoms, h->cur->d_list.p,
-                                       h->cur->d_def_real.p, h->cur->d_def_real_info.p, sc + 2, 0); if (rc) return rc; }
+                                       h->cur->d_def_real.p, h->cur->d_def_real_info.p, sc + 2, 0, 0); if (rc) return rc; }
         launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
                (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
                (const u64 *)h->cur->d_def_real.p, (const float2 *)h->cur->d_def_real_info.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr,
@@ -355,17 +356,24 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         CK(cub::DeviceSelect::If(h->cur->d_cub_tmp.p, tmp_bytes2, cub::CountingInputIterator<int>(0), h->cur->d_bulk_idx.p, sc + 4,
                                  nv_mols, pred, h->cur->stream));
         h->stats.kernel_launches += 2;
-        launch(h, k_filter_rand, dim3((unsigned)((nv_mols + 255) / 256), (unsigned)std::min(nrand, 65535)), dim3(256), g, h->P, frame, isolute, skip,
-               (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
-        launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, d_solvent, (const float *)h->cur->d_lbd2.p,
-               (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               h->cur->d_qpos.p, h->cur->d_xexact.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
-        { int rc = search_phase<true>(h, g, xs, d_solvent, h->cur->d_rand_worklist.p, sc + 1, (size_t)nrand * h->nv_atoms,
-                                      c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, h->cur->d_def_rand_info.p, sc + 3, 1); if (rc) return rc; }
-        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
-               (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->cur->d_def_rand.p, (const float2 *)h->cur->d_def_rand_info.p, (const int *)(sc + 3), (MdRec *)nullptr,
-               c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_stats.p, (const int *)(sc + 2), (const int *)(sc + 3));
+        // the random phase runs over chunks of samples so that the scratch (query atoms of the surviving
+        // random molecules) stays bounded for any n_random_samples; normally one chunk
+        for (int s0 = 0; s0 < nrand; s0 += h->sample_chunk) {
+            const int s1 = std::min(nrand, s0 + h->sample_chunk);
+            if (s0 > 0) { CK(cudaMemsetAsync(sc + 1, 0, sizeof(int), h->cur->stream)); CK(cudaMemsetAsync(sc + 3, 0, sizeof(int), h->cur->stream)); }
+            launch(h, k_filter_rand, dim3((unsigned)((nv_mols + 255) / 256), (unsigned)std::min(s1 - s0, 65535)), dim3(256), g, h->P, frame, isolute, skip,
+                   s0, s1, (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
+            launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, s0, d_solvent, (const float *)h->cur->d_lbd2.p,
+                   (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
+                   h->cur->d_qpos.p, h->cur->d_xexact.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
+            { int rc = search_phase<true>(h, g, xs, d_solvent, h->cur->d_rand_worklist.p, sc + 1, (size_t)(s1 - s0) * h->nv_atoms,
+                                          c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, h->cur->d_def_rand_info.p,
+                                          sc + 3, 1, s0); if (rc) return rc; }
+            launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
+                   (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
+                   (const u64 *)h->cur->d_def_rand.p, (const float2 *)h->cur->d_def_rand_info.p, (const int *)(sc + 3), (MdRec *)nullptr,
+                   c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_stats.p, (const int *)(s0 == 0 ? sc + 2 : nullptr), (const int *)(sc + 3));
+        }
     }
     return CMX_OK;
 }
@@ -494,7 +502,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     if (c.n_groups_solute < 1 || c.n_groups_solvent < 1) return fail(h, CMX_ERR_ARG, "n_groups_* must be positive");
     if (!c.solute_group_offsets && c.n_groups_solute != c.solute_natomspermol) return fail(h, CMX_ERR_ARG, "n_groups_solute must equal solute_natomspermol without custom groups");
     if (!c.solvent_group_offsets && c.n_groups_solvent != c.solvent_natomspermol) return fail(h, CMX_ERR_ARG, "n_groups_solvent must equal solvent_natomspermol without custom groups");
-    if ((double)c.n_random_samples * c.solvent_nmols > 2.0e9) return fail(h, CMX_ERR_ARG, "n_random_samples * solvent_nmols exceeds 2^31");
+    if (c.n_random_samples > 100000000) return fail(h, CMX_ERR_ARG, "n_random_samples is limited to 1e8");
     h->cfg = c;
     h->device = c.device;
     CK(cudaSetDevice(c.device));
@@ -577,24 +585,27 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     P.gsolv = q; q += nb * c.n_groups_solvent; P.gsolv_r = q;
     // scratch common to both paths
     size_t nvm = c.solvent_nmols, nrand = (size_t)P.nrand;
+    // random phase in chunks of samples: at most ~48 M query atoms of scratch per frame context
+    h->sample_chunk = (int)std::max<size_t>(1, std::min<size_t>(std::max<size_t>(nrand, 1), (size_t)(48.0e6 / (double)h->nv_atoms)));
+    const size_t nchunk = (size_t)h->sample_chunk;
     CK(h->d_stats.ensure(8, true));
     for (FrameCtx *x_ : h->ctx) {
         h->cur = x_;
         CK(h->cur->d_scalars.ensure(16, true)); 
         CK(h->cur->d_list.ensure(nvm));
         CK(h->cur->d_bulk_idx.ensure(nvm));
-        CK(h->cur->d_worklist.ensure(nvm)); CK(h->cur->d_rand_worklist.ensure(std::max<size_t>(nrand * nvm, 1)));
-        CK(h->cur->d_def_real.ensure(nvm)); CK(h->cur->d_def_rand.ensure(std::max<size_t>(nrand * nvm, 1)));
-    CK(h->cur->d_def_real_info.ensure(nvm)); CK(h->cur->d_def_rand_info.ensure(std::max<size_t>(nrand * nvm, 1)));
+        CK(h->cur->d_worklist.ensure(nvm)); CK(h->cur->d_rand_worklist.ensure(std::max<size_t>(nchunk * nvm, 1)));
+        CK(h->cur->d_def_real.ensure(nvm)); CK(h->cur->d_def_rand.ensure(std::max<size_t>(nchunk * nvm, 1)));
+    CK(h->cur->d_def_real_info.ensure(nvm)); CK(h->cur->d_def_rand_info.ensure(std::max<size_t>(nchunk * nvm, 1)));
         if (c.keep_lists) {
             if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
             CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));
         }
         if (h->path == 1) {
             CK(h->cur->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
-            size_t maxq = std::max<size_t>(h->nv_atoms, nrand * h->nv_atoms);
+            size_t maxq = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms);
             CK(h->cur->d_qpos.ensure(maxq)); CK(h->cur->d_qsorted.ensure(maxq)); CK(h->cur->d_res.ensure(maxq));
-            CK(h->cur->d_xexact.ensure(std::max<size_t>(3 * nrand * h->nv_atoms, 1)));
+            CK(h->cur->d_xexact.ensure(std::max<size_t>(3 * nchunk * h->nv_atoms, 1)));
         } else {
             int rc = pairs_create(h); if (rc) return rc;
         }
@@ -729,7 +740,7 @@ int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out) 
         // molecule from the last frame (still resident in its staging slot)
         if (!h->last_dsolv) return fail(h, CMX_ERR_STATE, "no frame submitted yet");
         PairGeom pg = make_pair_geom(h, h->last_g);
-        launch(h, k_ref_lists, dim3((unsigned)((nvm + 127) / 128), 1), dim3(128), h->last_g, pg, h->P, (uint32_t)h->last_frame, (int)isolute,
+        launch(h, k_ref_lists, dim3((unsigned)((nvm + 127) / 128), 1), dim3(128), h->last_g, pg, h->P, (uint32_t)h->last_frame, (int)isolute, 0,
                h->last_dsol, h->last_dsolv, h->cur->pairs.sol, h->cur->pairs.solv, h->cur->d_list.p);
         CK(cudaStreamSynchronize(h->cur->stream));
         CK(cudaMemcpy(tmp.data(), h->cur->d_list.p, sizeof(MdRec) * nvm, cudaMemcpyDeviceToHost));
@@ -784,6 +795,13 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
     std::string n(name);
     if (n == "count_pairs") h->count_pairs = value != 0;
     else if (n == "profile") h->profile = value != 0;
+    else if (n == "sample_chunk") {   // testing knob: smaller chunks of random samples per pass (never larger than allocated)
+        int rc = cmx_sync(h); if (rc) return rc;
+        int v = (int)value;
+        if (v < 1) return fail(h, CMX_ERR_ARG, "sample_chunk must be >= 1");
+        h->sample_chunk = std::min(h->sample_chunk, v);
+        for (FrameCtx *x : h->ctx) x->pairs.sample_chunk = std::max(1, std::min(x->pairs.sample_chunk, v));
+    }
     else if (n == "active_streams") {
         int rc = cmx_sync(h); if (rc) return rc;
         int v = (int)value;

@@ -228,14 +228,15 @@ __global__ void k_gen_real(Geom g, Prob P, const float *__restrict__ xv, const f
 }
 
 __global__ void __launch_bounds__(128)
-k_gen_rand(Geom g, Prob P, uint32_t frame, const float *__restrict__ xv, const float *__restrict__ lbd2,
+k_gen_rand(Geom g, Prob P, uint32_t frame, int s0, const float *__restrict__ xv, const float *__restrict__ lbd2,
            const int *__restrict__ worklist, const int *__restrict__ work_count, const int *__restrict__ bulk_idx,
            const int *__restrict__ n_bulk_ptr, float4 *__restrict__ qpos, double *__restrict__ xexact,
            float4 *__restrict__ res, int *__restrict__ qcell_count) {
     const int count = *work_count;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
         int item = worklist[w];
-        int sample = item / P.nv_mols, mol = item - sample * P.nv_mols;
+        int sl = item / P.nv_mols, mol = item - sl * P.nv_mols;
+        int sample = s0 + sl;
         uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
         uint4 r1 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 1u, P.seed_lo, P.seed_hi);
         int nb = *n_bulk_ptr;
@@ -427,12 +428,12 @@ __global__ void __launch_bounds__(128)
 k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict__ xv, const float4 *__restrict__ res,
            const double *__restrict__ xexact, const int *__restrict__ worklist, const int *__restrict__ work_count,
            MdRec *__restrict__ list, u64 *__restrict__ deferred, float2 *__restrict__ deferred_info,
-           int *__restrict__ deferred_count) {
+           int *__restrict__ deferred_count, int s0) {
     const int count = *work_count;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
         const int item = worklist[w];
         int sample = 0, mol = item;
-        if (RANDOM) { sample = item / P.nv_mols; mol = item - sample * P.nv_mols; }
+        if (RANDOM) { int sl = item / P.nv_mols; mol = item - sl * P.nv_mols; sample = s0 + sl; }
         const float4 *r = res + (size_t)w * P.nv_apm;
         float best = CUDART_INF_F, second = CUDART_INF_F; int bi = -1, bk = -1;
         for (int k = 0; k < P.nv_apm; ++k) {
@@ -477,11 +478,11 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
 // grid.y = sample, grid.x covers the slots; the centre is evaluated in fp32 (its error, ~1e-5 A, is far
 // below the 1e-3 A margin of the test); survivors are appended with one global atomic per block
 __global__ void __launch_bounds__(256)
-k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol, const float *__restrict__ lbd2,
+k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol, int s0, int s1, const float *__restrict__ lbd2,
               const int *__restrict__ rmax_bits, int *__restrict__ worklist, int *__restrict__ work_count) {
     __shared__ int s_count, s_base;
     const int mol = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int sample = blockIdx.y; sample < P.nrand; sample += gridDim.y) {
+    for (int sample = s0 + blockIdx.y; sample < s1; sample += gridDim.y) {
     __syncthreads();
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
@@ -510,7 +511,7 @@ k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol, const f
     if (threadIdx.x == 0 && s_count) s_base = atomicAdd(work_count, s_count);
     __syncthreads();
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (near) worklist[s_base + wbase + __popc(ball & ((1u << lane) - 1))] = sample * P.nv_mols + mol;
+    if (near) worklist[s_base + wbase + __popc(ball & ((1u << lane) - 1))] = (sample - s0) * P.nv_mols + mol;   // item within the chunk
     }
 }
 

@@ -47,6 +47,7 @@ struct PairScratch {
     int *bulk_idx = nullptr, *n_bulk = nullptr;          // [nrand][nv_mols], [nrand]
     u64 *deferred = nullptr; int *def_count = nullptr;   // [cap], [2] (count, overflow)
     size_t def_cap = 0, ncells_cap = 0;
+    int sample_chunk = 1;                                // samples of the random phase processed per pass
     float *h_radii = nullptr;                            // pinned: [0] ra_sol, [1] ra_solv, [2] rc_solv
     int *d_radii = nullptr;                              // device float bits, same layout
     float ra_sol_bound = 0, ra_solv_bound = 0;
@@ -349,13 +350,14 @@ __device__ __forceinline__ MdRec exact_list_entry(const Geom &g, const Prob &P, 
     return e;
 }
 
-// grid.y = list index; solute molecule = fixed_a (>= 0) or the reference solute of sample blockIdx.y
-__global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fixed_a, const float *__restrict__ xs,
+// grid.y = list index within the current chunk of samples; solute molecule = fixed_a (>= 0) or the reference
+// solute of sample s0 + blockIdx.y
+__global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fixed_a, int s0, const float *__restrict__ xs,
                             const float *__restrict__ xv, MolData sol, MolData solv, MdRec *__restrict__ lists) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.nv_mols) return;
     int s = blockIdx.y;
-    int a = fixed_a >= 0 ? fixed_a : ref_solute_of_sample(P, frame, (uint32_t)s);
+    int a = fixed_a >= 0 ? fixed_a : ref_solute_of_sample(P, frame, (uint32_t)(s0 + s));
     MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
     if (!(P.autocorr && b == a)) {
         double dx = solv.anchor[3 * (size_t)b] - sol.anchor[3 * (size_t)a], dy = solv.anchor[3 * (size_t)b + 1] - sol.anchor[3 * (size_t)a + 1],
@@ -373,12 +375,12 @@ __global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fix
 
 // ordered compaction of the bulk molecules of each sample's list (one block per sample)
 __global__ void __launch_bounds__(512)
-k_bulk_compact(Prob P, uint32_t frame, const MdRec *__restrict__ lists, int *__restrict__ bulk_idx, int *__restrict__ n_bulk) {
+k_bulk_compact(Prob P, uint32_t frame, int s0, const MdRec *__restrict__ lists, int *__restrict__ bulk_idx, int *__restrict__ n_bulk) {
     typedef cub::BlockScan<int, 512> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int base_sh;
-    int s = blockIdx.x;
-    int a = ref_solute_of_sample(P, frame, (uint32_t)s);
+    int s = blockIdx.x;                      // sample within the chunk
+    int a = ref_solute_of_sample(P, frame, (uint32_t)(s0 + s));
     if (threadIdx.x == 0) base_sh = 0;
     __syncthreads();
     for (int start = 0; start < P.nv_mols; start += 512) {
@@ -400,13 +402,14 @@ k_bulk_compact(Prob P, uint32_t frame, const MdRec *__restrict__ lists, int *__r
 // random phase: one thread per (sample, slot)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, const float *__restrict__ xs, const float *__restrict__ xv,
+k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, int s0, int ns, const float *__restrict__ xs, const float *__restrict__ xv,
               MolData sol, const int *__restrict__ rc_solv_bits, const int *__restrict__ bulk_idx,
               const int *__restrict__ n_bulk, MdRec *__restrict__ rand_list, u64 *__restrict__ deferred,
               int *__restrict__ def_count, size_t def_cap) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)P.nrand * P.nv_mols) return;
-    int s = (int)(t / P.nv_mols), slot = (int)(t - (long long)s * P.nv_mols);
+    if (t >= (long long)ns * P.nv_mols) return;
+    const int sl = (int)(t / P.nv_mols), slot = (int)(t - (long long)sl * P.nv_mols);   // sl: sample within the chunk
+    const int s = s0 + sl;
     int a = ref_solute_of_sample(P, frame, (uint32_t)s);
     if (P.autocorr && slot == a) return;   // src/minimum_distances.jl:90
     const float rc = __int_as_float(*rc_solv_bits);
@@ -424,8 +427,8 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, const float *__restri
         if (dn2 > lim * lim && lim < pg.half_wmin) return;   // true centre distance > lim as well
     }
     uint4 r1 = philox4x32((uint32_t)slot, (uint32_t)s, frame, 1u, P.seed_lo, P.seed_hi);
-    int nb = n_bulk[s];
-    int jmol = nb > 0 ? bulk_idx[(size_t)s * P.nv_mols + pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
+    int nb = n_bulk[sl];
+    int jmol = nb > 0 ? bulk_idx[(size_t)sl * P.nv_mols + pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
     RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
     const float *offa = sol.off + (size_t)a * 3 * P.ns_apm;
     float b1 = CUDART_INF_F, b2 = CUDART_INF_F, r1_ = CUDART_INF_F, r2_ = CUDART_INF_F;
@@ -449,7 +452,7 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, const float *__restri
     int cls = classify_p(pg, b1, b2);
     if (cls == 0 && ok) return;
     int rcls = classify_p(pg, r1_, r2_);
-    if (!ok || cls == 2 || rcls == 2) { defer_pair(deferred, def_count, def_cap, 1 + s, a, slot); return; }
+    if (!ok || cls == 2 || rcls == 2) { defer_pair(deferred, def_count, def_cap, 1 + sl, a, slot); return; }
     const float *xa = xs + (size_t)3 * P.ns_apm * a;
     double ex, ey, ez; rm.get(g, bk, ex, ey, ez);
     MdRec e; e.pad = 0; e.flags = 1; e.i = bi; e.j = slot * P.nv_apm + bk; e.dref = CUDART_INF;
@@ -467,7 +470,7 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, const float *__restri
 // ---------------------------------------------------------------------------------------------
 // exact resolve of deferred pairs (one thread per item: molecules on this path are small)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const float *__restrict__ xv,
+__global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, int s0, const float *__restrict__ xs, const float *__restrict__ xv,
                                const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk,
                                const u64 *__restrict__ deferred, const int *__restrict__ def_count, size_t def_cap,
                                MdRec *__restrict__ rand_list) {
@@ -485,11 +488,11 @@ __global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, const float *__re
                 if (f.flags & 1) { count_hit(P, false, f.d, f.i, f.j, 1ull); if (f.flags & 2) count_ref(P, false, f.dref); }
             }
         } else {
-            int s = phase - 1, slot = b;
+            int sl = phase - 1, s = s0 + sl, slot = b;    // sl: sample within the chunk
             uint4 r0 = philox4x32((uint32_t)slot, (uint32_t)s, frame, 0u, P.seed_lo, P.seed_hi);
             uint4 r1 = philox4x32((uint32_t)slot, (uint32_t)s, frame, 1u, P.seed_lo, P.seed_hi);
-            int nb = n_bulk[s];
-            int jmol = nb > 0 ? bulk_idx[(size_t)s * P.nv_mols + pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
+            int nb = n_bulk[sl];
+            int jmol = nb > 0 ? bulk_idx[(size_t)sl * P.nv_mols + pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
             RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
             MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
             for (int k = 0; k < P.nv_apm; ++k) {

@@ -28,9 +28,12 @@ int pairs_create(cmx_handle *h) {
     const cmx_config &c = h->cfg;
     PairScratch &S = h->cur->pairs;
     if (c.solute_natomspermol > 512) return fail(h, CMX_ERR_ARG, "molecule-pair path: solute_natomspermol > 512 (use path=1)");
-    if (c.solute_nmols >= (1 << 24) || c.solvent_nmols >= (1 << 24) || c.n_random_samples >= 65535)
-        return fail(h, CMX_ERR_ARG, "molecule-pair path: too many molecules/samples for the deferred-item encoding");
-    size_t nsm = c.solute_nmols, nvm = c.solvent_nmols, nrand = std::max(1, h->P.nrand);
+    if (c.solute_nmols >= (1 << 24) || c.solvent_nmols >= (1 << 24))
+        return fail(h, CMX_ERR_ARG, "molecule-pair path: too many molecules for the deferred-item encoding");
+    size_t nsm = c.solute_nmols, nvm = c.solvent_nmols;
+    // the random phase runs in chunks of samples: bounded scratch (256 MB of lists) and grid.y <= 32768
+    S.sample_chunk = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>((size_t)std::max(1, h->P.nrand), 32768), (size_t)(256.0e6 / (36.0 * nvm))));
+    size_t nrand = (size_t)S.sample_chunk;
     CK(cudaMalloc(&S.solv.anchor, sizeof(double) * 3 * nvm));
     CK(cudaMalloc(&S.solv.off, sizeof(float) * 3 * h->nv_atoms));
     CK(cudaMalloc(&S.solv.rad, sizeof(float) * nvm));
@@ -130,21 +133,27 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     }
     h->stats.kernel_launches++;
     prof_end(h, ev);
+    // real-phase ambiguous pairs first, so that the deferred list can be reused by every chunk of samples
+    launch(h, k_pair_resolve, dim3(h->num_sms * 2), dim3(128), g, h->P, frame, 0, d_solute, d_solvent, (const int *)S.bulk_idx,
+           (const int *)S.n_bulk, (const u64 *)S.deferred, (const int *)S.def_count, S.def_cap, (MdRec *)nullptr);
+    launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)S.def_count, (const int *)nullptr, h->d_stats.p);
     const int nrand = h->P.nrand;
-    if (nrand > 0) {
-        launch(h, k_ref_lists, dim3((nvm + 127) / 128, nrand), dim3(128), g, pg, h->P, frame, -1, d_solute, d_solvent, S.sol, S.solv, S.ref_lists);
-        launch(h, k_bulk_compact, dim3(nrand), dim3(512), h->P, frame, (const MdRec *)S.ref_lists, S.bulk_idx, S.n_bulk);
-        long long total = (long long)nrand * nvm;
+    for (int s0 = 0; s0 < nrand; s0 += S.sample_chunk) {
+        const int ns = std::min(S.sample_chunk, nrand - s0);
+        CK(cudaMemsetAsync(S.def_count, 0, sizeof(int), h->cur->stream));
+        launch(h, k_ref_lists, dim3((nvm + 127) / 128, ns), dim3(128), g, pg, h->P, frame, -1, s0, d_solute, d_solvent, S.sol, S.solv, S.ref_lists);
+        launch(h, k_bulk_compact, dim3(ns), dim3(512), h->P, frame, s0, (const MdRec *)S.ref_lists, S.bulk_idx, S.n_bulk);
+        long long total = (long long)ns * nvm;
         ev = prof_begin(h, 1);
-        launch(h, k_pair_random, dim3((unsigned)((total + 127) / 128)), dim3(128), g, pg, h->P, frame, d_solute, d_solvent, S.sol,
+        launch(h, k_pair_random, dim3((unsigned)((total + 127) / 128)), dim3(128), g, pg, h->P, frame, s0, ns, d_solute, d_solvent, S.sol,
                (const int *)(S.d_radii + 2), (const int *)S.bulk_idx, (const int *)S.n_bulk,
                c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, S.deferred, S.def_count, S.def_cap);
         prof_end(h, ev);
+        launch(h, k_pair_resolve, dim3(h->num_sms * 2), dim3(128), g, h->P, frame, s0, d_solute, d_solvent, (const int *)S.bulk_idx,
+               (const int *)S.n_bulk, (const u64 *)S.deferred, (const int *)S.def_count, S.def_cap,
+               c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
+        launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)S.def_count, (const int *)nullptr, h->d_stats.p);
     }
-    launch(h, k_pair_resolve, dim3(h->num_sms * 2), dim3(128), g, h->P, frame, d_solute, d_solvent, (const int *)S.bulk_idx,
-           (const int *)S.n_bulk, (const u64 *)S.deferred, (const int *)S.def_count, S.def_cap,
-           c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr);
-    launch(h, k_accumulate_stats, dim3(1), dim3(32), (const int *)S.def_count, (const int *)nullptr, h->d_stats.p);
     launch(h, k_check_overflow, dim3(1), dim3(32), (const int *)(S.def_count + 1), h->cur->d_scalars.p + 8);
     return CMX_OK;
 }

@@ -17,7 +17,7 @@ for r in rows:
     if r[0] == "Kernel Name": cur = {"name": r[1], "hdr": None, "rows": []}; blocks.append(cur)
     elif r[0] == "Address": cur["hdr"] = r
     elif cur is not None and cur["hdr"] is not None: cur["rows"].append(r)
-blk = [b for b in blocks if re.search(kre, b["name"])][0]
+blk = [b for b in blocks if re.search(kre, b["name"])][int(os.environ.get("NCU_INDEX", "0"))]
 h = blk["hdr"]; ia, ii, isamp, ithr = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples"), h.index("Thread Instructions Executed")
 base = int(blk["rows"][0][ia], 16)
 tmp = tempfile.mkdtemp()

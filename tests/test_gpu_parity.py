@@ -429,3 +429,38 @@ def test_public_mddf_from_dcd_file(tmp_path):
     assert Rs.autocorrelation and Rs.md_count.sum() > 0
     C = cm.coordination_number(path, sol, tm, opts(lastframe=1))
     assert C.coordination_number[np.argmax(C.d > 3)] == 7.0 and np.all(C.md_count_random == 0)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_random_phase_in_chunks_of_samples(path):
+    """the random phase runs over chunks of samples (bounded scratch for any n_random_samples): same counters
+    for any chunk size."""
+    d = namd()
+    o = opts(bulk_range=(8.0, 10.0), n_random_samples=7)
+    if path == 1:
+        p = Problem(PROTEIN, TMAO, o, d["protein"][:2], d["tmao"][:2], d["cells"][:2])
+    else:
+        p = Problem(TMAO, TMAO, o, d["tmao"][:2], None, d["cells"][:2], autocorrelation=True)
+    ref, _ = p.oracle()
+    for chunk in (1, 3):
+        eng = p.engine(path=path)
+        eng.set_option("sample_chunk", chunk)
+        dev = p.run_engine(eng); eng.close()
+        assert_counters_equal(dev, ref)
+
+
+def test_toy_with_the_reference_sample_count():
+    """n_random_samples = 10^5 as in the reference's toy tests (src/mddf.jl:601,641): more samples than a grid
+    dimension holds, on both device paths."""
+    t = toy()
+    protein = cm.AtomSelection([10], nmols=1)
+    water = cm.AtomSelection(np.arange(1, 10), natomspermol=3)
+    o = cm.Options(seed=321, silent=True, n_random_samples=10 ** 5, lastframe=1)
+    R = cm.mddf(cm.ArrayTrajectory(t["cross"], t["cross_cells"], protein, water), o)
+    assert R.volume.total == 27000.0 and np.isclose(R.md_count.sum(), 1.0) and np.isclose(R.coordination_number.sum(), 51.0)
+    assert np.isclose(R.volume.domain, 4 * np.pi / 3 * R.dbulk ** 3, rtol=0.01)      # the reference's tolerance (:607)
+    assert np.isclose(R.density.solvent_bulk, 2 / R.volume.bulk)
+    atom = cm.AtomSelection([1, 2], natomspermol=1)
+    R = cm.mddf(cm.ArrayTrajectory(t["self_monoatomic"], t["self_monoatomic_cells"], atom, atom), o)
+    assert R.volume.total == 27000.0 and np.isclose(R.md_count.sum(), 1.0)
+    assert np.isclose(R.volume.domain, 4 * np.pi / 3 * R.dbulk ** 3, rtol=0.1)       # (:639)
