@@ -214,7 +214,6 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
     g.side = (float)h->side; g.inv_side = (float)(1.0 / h->side);
     g.sidex = (float)h->sidex; g.inv_sidex = (float)(1.0 / h->sidex);
     g.cut_hi2 = g.cut_hi * g.cut_hi * (1.0f + 1e-6f);
-    g.K = h->Kdiv; g.nrows_tab = 0;
     g.nx = (int)std::ceil((g.ehi[0] - g.elo[0]) / h->sidex) + 1;
     g.ny = (int)std::ceil((g.ehi[1] - g.elo[1]) / h->side) + 1;
     g.nz = (int)std::ceil((g.ehi[2] - g.elo[2]) / h->side) + 1;
@@ -808,7 +807,8 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
         if (v < 0 || v > (int)h->ctx.size()) return fail(h, CMX_ERR_ARG, "active_streams out of range");
         h->active_ctx = v;
     }
-    else if (n == "group_lanes") { /* ignored */    } else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
+    else if (n == "group_lanes") { /* accepted, ignored */ }
+    else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
     return CMX_OK;
 }
 

@@ -25,7 +25,7 @@ struct Geom {
     float gmin[3];            // elo - ctr
     float side, inv_side;     // cell size along y and z (a "row" is one (y,z) column of cells)
     float sidex, inv_sidex;   // cell size along x (finer: rows are scanned over x-spans)
-    int nx, ny, nz, K, nrows_tab;
+    int nx, ny, nz;
     int rw;                   // 64-bit words per fine-grid row of the occupancy bitmask
     // query cells (cubic): tiles of 32 query atoms are consecutive runs in this order
     float qside, inv_qside;

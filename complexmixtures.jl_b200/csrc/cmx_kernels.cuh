@@ -27,7 +27,7 @@ namespace cmx {
 
 
 // ---------------------------------------------------------------------------------------------
-// K1/K3: bin the solute molecule (plus periodic images inside the extended box) into the grid
+// Solute grid: bin the solute molecule (plus periodic images inside the extended box) into the grid
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int fine_cell_of(const Geom &g, float px, float py, float pz) {
     int cx = (int)floorf((px - g.gmin[0]) * g.inv_sidex);
@@ -77,7 +77,7 @@ __global__ void k_solute_bin(Geom g, const float *__restrict__ xs, int natoms, i
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: Chebyshev distance (in coarse cells, capped) from every coarse cell to the nearest occupied one
+// Cull grid: lower bound of the distance from every cull cell to the solute
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t row_window(const u64 *row, int cw, int cx) {
     // 31-bit window of the row bitmap, bit 15 = column cx
@@ -144,7 +144,7 @@ __device__ __forceinline__ float cull_lb2(const Geom &g, const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5: cull the solvent molecules of the frame; survivors -> work list.  Also the largest
+// Real-phase cull: the solvent molecules of the frame; survivors -> work list.  Also the largest
 // centroid-to-atom distance of any molecule (bound used to cull random placements).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_filter_real(Geom g, Prob P, const float *__restrict__ xv, int skip_mol,
@@ -190,7 +190,7 @@ __global__ void k_filter_real(Geom g, Prob P, const float *__restrict__ xv, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6a: query atoms of the work-list molecules.  Real phase: wrapped fp32 positions of the frame's
+// Query atoms of the work-list molecules.  Real phase: wrapped fp32 positions of the frame's
 // atoms.  Random phase: the random molecules that survived the centre cull are generated (Philox +
 // rigid move, fp64) and stored as exact fp64 + wrapped fp32 positions; culled placements are never
 // materialised.  Every query atom that can be within the cutoff (distance-transform bound) is
@@ -282,7 +282,7 @@ __global__ void k_qscatter(Geom g, Prob P, const int *__restrict__ work_count, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6: the search.  One warp per tile of 32 query atoms that are neighbours in space (consecutive in
+// The search.  One warp per tile of 32 query atoms that are neighbours in space (consecutive in
 // query-cell order).  Every lane owns one query; all lanes walk the SAME solute atoms (broadcast
 // 16-byte loads of the cell-sorted solute), so there is no divergence and one row probe serves 32
 // queries.  Rows of the solute grid inside the tile's reach are probed in lane-parallel (occupancy
@@ -419,7 +419,7 @@ __device__ __forceinline__ int classify(const Geom &g, float b1, float b2) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6b: per molecule, combine its atoms' results (update_md, src/minimum_distances.jl:30-39), finalise
+// Finalisation: per molecule, combine its atoms' results (update_md, src/minimum_distances.jl:30-39), finalise
 // the winning pair and the reference-atom pair in fp64 with the reference's arithmetic, histogram
 // (update_counters!, src/update_counters.jl:43-88) -- or defer an ambiguous molecule to the exact kernel.
 // ---------------------------------------------------------------------------------------------
@@ -473,7 +473,7 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// K8: cull the random placements by the position of their centre
+// Random-phase cull: the random placements, by the position of their centre
 // ---------------------------------------------------------------------------------------------
 // grid.y = sample, grid.x covers the slots; the centre is evaluated in fp32 (its error, ~1e-5 A, is far
 // below the 1e-3 A margin of the test); survivors are appended with one global atomic per block
@@ -516,8 +516,8 @@ k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol, int s0,
 }
 
 // ---------------------------------------------------------------------------------------------
-// K9: exact resolve of the deferred molecules: fp64 brute force over the whole solute molecule
-// with the oracle's rule "smallest (d, j, i) wins".  One block per deferred item.
+// Exact resolve of the deferred (ambiguous in fp32) molecules: fp64 with the reference's arithmetic over the
+// solute atoms within reach of the fp32 result, rule "smallest (d, j, i) wins".  One block per deferred item.
 // ---------------------------------------------------------------------------------------------
 struct RealMolG {   // adapter: same interface as RandMol::get(g, k, ...)
     RealMol m;
