@@ -364,7 +364,11 @@ def main():
                 "traffic": ncu_traffic(args.config, "random" if dom.startswith("random") else "real"), "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": dom_ms / ms_frame if ms_frame > 0 else None,
                 "frame_algorithmic_bytes": b_in + b_rand, "frame_achieved_GBps": (b_in + b_rand) * value / world / 1e9,
-                "pair_evals_per_frame": pe, "pair_evals_per_s": pe * value}
+                "pair_evals_per_frame": pe, "pair_evals_per_s": pe * value,
+                # second view (the kernel is instruction-bound, not HBM-bound): pair evaluations per second inside the
+                # dominant kernel against lanes x clock / 12.5 instructions (the SASS inner loop of k_tile_search)
+                "alu_view": {"kernel_pair_evals_per_s": (pe * (ms_rand / max(ms_rand + ms_real, 1e-12)) / (dom_ms * 1e-3)) if dom_ms > 0 else None,
+                             "inner_loop_peak_pair_evals_per_s": 148 * 128 * 1.965e9 / 12.5}}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None

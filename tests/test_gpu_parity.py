@@ -464,3 +464,19 @@ def test_toy_with_the_reference_sample_count():
     R = cm.mddf(cm.ArrayTrajectory(t["self_monoatomic"], t["self_monoatomic_cells"], atom, atom), o)
     assert R.volume.total == 27000.0 and np.isclose(R.md_count.sum(), 1.0)
     assert np.isclose(R.volume.domain, 4 * np.pi / 3 * R.dbulk ** 3, rtol=0.1)       # (:639)
+
+
+@pytest.mark.parametrize("bulk_range", [(3.0, 5.0), (2.0, 3.5), (14.0, 20.0)])
+def test_small_and_large_cutoffs(bulk_range):
+    """cutoffs far from the usual 10-15 A: a small cutoff makes the search grid fine relative to a tile (several
+    row chunks per tile), a large one (with a triclinic cell) many cells per row."""
+    from cmx_b200 import synthetic as syn
+    big = bulk_range[1] > 10
+    cell = np.array([[52.0, 9.0, 6.0], [0.0, 50.0, 8.0], [0.0, 0.0, 49.0]]) if big else [30.0, 31.0, 32.0]
+    s = syn.make_system("c", cell=cell, solute_atoms=500 if big else 250, solvents=[("water", "water", 900 if big else 700)], seed=13)
+    sol, wat = s.selections["solute"], s.selections["water"]
+    fr = [s.frame(k)[0] for k in range(2)]
+    p = Problem(sol, wat, opts(bulk_range=bulk_range, n_random_samples=4, binstep=0.05 if not big else 0.02), [f[sol.indices - 1] for f in fr],
+                [f[wat.indices - 1] for f in fr], s.cell)
+    dev, o, _ = check(p)
+    assert dev["md_count"].sum() > 0
