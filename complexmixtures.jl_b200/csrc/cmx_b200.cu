@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -515,15 +516,21 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     h->path = c.path ? c.path : ((c.solute_nmols == 1 || c.solute_natomspermol > 64) ? 1 : 2);
     if (h->path != 1 && h->path != 2) return fail(h, CMX_ERR_ARG, "path must be 0 (auto), 1 (grid) or 2 (molecule pairs)");
     // (cmx_config.group_lanes is accepted for ABI stability and ignored: the search works on 32-query tiles)
-    // search grid: a "row" is a (y,z) column of cells cut/4 wide; along x the cells are ~2.5 A so that
-    // a row is scanned over a tight x-span.  Query atoms are tiled in cubic cells of ~6 A (about 20-30
-    // solvent atoms, one warp).
-    h->Kdiv = 4;
+    // search grid: a "row" is a (y,z) column of cells cut/3 wide; along x the cells are ~2.5 A so that
+    // a row is scanned over a tight x-span.  Query atoms are tiled in cubic cells of ~5 A (a dozen
+    // solvent atoms, one warp).  Values from a sweep on C2 (rows cut/2..cut/6, tiles 4.5..8 A): +10 % over
+    // cut/4 rows with 6 A tiles; fewer, fatter rows cost pair evaluations but save per-row bookkeeping.
+    h->Kdiv = 3;
     h->side = (h->cut_eff + 0.02) / h->Kdiv;
     h->sidex = (h->cut_eff + 0.02) / std::max(2, (int)std::lround(h->cut_eff / 2.5));
-    h->qside = std::min(8.0, std::max(5.0, h->cut_eff / 2.5));
+    h->qside = std::min(8.0, std::max(5.0, h->cut_eff / 3.0));
     // cull grid (distance transform): cut/5
     h->cside = (h->cut_eff + 0.02) / 5.0;
+    // tuning overrides (experiments only)
+    if (const char *e = std::getenv("CMX_ROWDIV")) { h->Kdiv = std::max(1, atoi(e)); h->side = (h->cut_eff + 0.02) / h->Kdiv; }
+    if (const char *e = std::getenv("CMX_XSIDE")) h->sidex = std::max(0.5, atof(e));
+    if (const char *e = std::getenv("CMX_QSIDE")) h->qside = std::max(1.0, atof(e));
+    if (const char *e = std::getenv("CMX_CULLDIV")) h->cside = (h->cut_eff + 0.02) / std::max(1.0, atof(e));
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     int nctx = c.n_streams > 0 ? c.n_streams : (h->nv_atoms + h->ns_atoms > 2000000 ? 4 : 8);
     if (c.keep_lists) nctx = 1;                  // the parity hooks read the scratch of the last frame
