@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""bench_extras.py -- measurements of the SURVEY 8(f) rows next to the hot path (not the headline bench.py):
+
+  feed    frames/s of a whole mddf run FROM A DCD FILE on disk: the library's native feed (cmx_run_dcd: reader
+          threads -> pinned ring -> raw-frame H2D -> device gather) with 1/2/4 reader threads, against the host
+          reader of this package writing into the staging slot (the structure of the reference's frame loop,
+          src/mddf.jl:296-334 + NamdDCD.jl:141-169); counters of both feeds must be identical.
+  reduce  the device-side group reduction (cmx_reduce_groups) over a per-atom contribution array of C5's shape
+          (1e6 rows x 750 bins x 8 B = 6 GB): kernel time (CUDA events) -> achieved GB/s against the measured
+          HBM peak (this kernel IS HBM-bound: algorithmic bytes = rows x nbins x 8).
+
+Prints one JSON line per measurement.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def feed(args):
+    import cmx_b200 as cm
+    from cmx_b200 import synthetic as syn
+    from cmx_b200.engine import DcdFile, Engine
+    from common import write_dcd
+    s = syn.config_c2(args.scale)
+    sol, wat = s.selections["solute"], s.selections["water"]
+    opt = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=10, seed=321, silent=True)
+    nf = args.frames
+    frames = np.stack([s.frame(k + 1)[0] for k in range(nf)]).astype(np.float32)
+    tmp = tempfile.mkdtemp(prefix="cmx_feed_", dir=args.tmpdir)
+    path = os.path.join(tmp, "c2.dcd")
+    write_dcd(path, frames, np.asarray(s.cell, dtype=np.float64))
+    size = os.path.getsize(path)
+    first = frames[0][wat.indices - 1][:3].astype(np.float64)
+    iref = int(np.argmin(np.linalg.norm(first - first.mean(axis=0), axis=1))) + 1
+    del frames
+    out = {"what": "feed", "workload": f"C2 (scale {args.scale}) mddf(protein, water) from a DCD file of {nf} frames, {size / 1e6:.0f} MB (page cache warm)",
+           "frames": nf, "file_bytes": size}
+    ref = None
+    for threads in (1, 2, 4):
+        eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=iref, autocorrelation=False)
+        f = DcdFile(path)
+        eng.run_dcd(f, sol.indices, wat.indices, list(range(min(nf, 16))), n_reader_threads=threads); eng.sync(); eng.reset()   # warm-up
+        t0 = time.perf_counter()
+        eng.run_dcd(f, sol.indices, wat.indices, list(range(nf)), n_reader_threads=threads)
+        c = eng.finish(copy=False)
+        dt = time.perf_counter() - t0
+        out[f"native_{threads}_threads_frames_per_s"] = nf / dt
+        out[f"native_{threads}_threads_file_GBps"] = size / dt / 1e9
+        if ref is None:
+            ref = {k: np.array(v) for k, v in c.items() if isinstance(v, np.ndarray)}
+        else:
+            assert all(np.array_equal(ref[k], c[k]) for k in ref), "native feed: counters depend on the reader thread count"
+        f.close(); eng.close()
+    # host reader of this package -> staging slot (first `host_frames` frames only: it is the slow side)
+    nh = min(nf, args.host_frames)
+    o2 = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=10, seed=321, silent=True, lastframe=nh, irefatom=iref)
+    t0 = time.perf_counter()
+    Rh = cm.mddf(path, sol, wat, o2, feed="host")
+    dth = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Rn = cm.mddf(path, sol, wat, o2, feed="native", reader_threads=2)
+    dtn = time.perf_counter() - t0
+    out["public_mddf_host_feed_frames_per_s"] = nh / dth
+    out["public_mddf_native_feed_frames_per_s"] = nh / dtn
+    out["public_mddf_frames"] = nh
+    out["feeds_identical"] = bool(np.array_equal(Rh.md_count, Rn.md_count) and np.array_equal(Rh.solute_group_count, Rn.solute_group_count)
+                                  and np.array_equal(Rh.md_count_random, Rn.md_count_random))
+    os.remove(path); os.rmdir(tmp)
+    print(json.dumps(out))
+
+
+def reduce(args):
+    import cmx_b200 as cm
+    from cmx_b200.engine import Engine
+    nrows, nsolv = args.rows, 100000
+    sol = cm.AtomSelection(np.arange(1, nrows + 1), nmols=1)
+    wat = cm.AtomSelection(np.arange(nrows + 1, nrows + 1 + 3 * nsolv), natomspermol=3)
+    opt = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=2, seed=321, silent=True)
+    rng = np.random.default_rng(1)
+    cell = np.diag([400.0, 400.0, 312.5])
+    xs = (rng.uniform(0, 1, size=(nrows, 3)) * np.array([400.0, 400.0, 50.0]) + np.array([0, 0, 130.0])).astype(np.float32)
+    ctr = rng.uniform(0, 1, size=(nsolv, 1, 3)) * np.array([400.0, 400.0, 312.5])
+    xv = (ctr + rng.normal(0, 0.5, size=(nsolv, 3, 3))).reshape(-1, 3).astype(np.float32)
+    eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=1, autocorrelation=False, n_streams=2)
+    eng.set_option("profile", 1)
+    for k in range(2):
+        eng.submit_arrays(xs, xv, cell, frame_index=k + 1)
+    eng.sync()
+    nb = eng.nbins
+    per = 16
+    groups = [np.arange(g * per, min((g + 1) * per, nrows)) for g in range((nrows + per - 1) // per)]
+    peak, src = hbm_peak()
+    res = {"what": "reduce", "rows": nrows, "nbins": nb, "algorithmic_bytes": nrows * nb * 8, "peak_GBps": peak, "peak_source": src}
+    for name, gs in (("residues_of_16_rows", groups), ("one_group_of_all_rows", [np.arange(nrows)])):
+        best = 1e30
+        for _ in range(args.repeat):
+            got = eng.reduce_groups("solute_group_count", gs)
+            best = min(best, eng.stats()["gpu_ms_reduce"])
+        res[name] = {"n_groups": len(gs), "kernel_ms": best, "achieved_GBps": nrows * nb * 8 / (best * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": nrows * nb * 8 / (best * 1e-3) / 1e9 / peak, "d2h_bytes": int(got.nbytes)}
+    full = eng.finish(copy=False)
+    want = full["solute_group_count"].reshape(len(groups), per, nb).sum(axis=1) if nrows % per == 0 else None
+    got = eng.reduce_groups("solute_group_count", groups)
+    res["equals_host_sum_of_rows"] = bool(want is None or np.array_equal(got, want))
+    res["hits"] = float(full["md_count"].sum())
+    eng.close()
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["feed", "reduce"])
+    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--host-frames", type=int, default=64)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--rows", type=int, default=1000000)
+    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--tmpdir", default=None)
+    a = ap.parse_args()
+    feed(a) if a.what == "feed" else reduce(a)

@@ -50,6 +50,8 @@ struct DevBuf {
 
 }  // namespace
 
+struct cmx_feed;   // native DCD feed ring + group-reduction scratch (cmx_feed.inl)
+
 // Everything one in-flight frame needs: its compute stream and scratch buffers.
 struct FrameCtx {
     cudaStream_t stream = nullptr;
@@ -125,6 +127,7 @@ struct cmx_handle {
     Geom last_g{};
     const float *last_dsol = nullptr, *last_dsolv = nullptr;
     int num_sms = 148;
+    cmx_feed *feed = nullptr;
 };
 
 namespace {
@@ -141,6 +144,7 @@ namespace {
 int fail(cmx_handle *h, int code, const std::string &msg) { h->err = msg; return code; }
 
 // molecule-pair path (cmx_pairs_host.inl)
+void feed_destroy(cmx_handle *h);
 int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent, uint32_t frame, const Geom &g);
 int pairs_create(cmx_handle *h);
 void pairs_release(cmx_handle *h);
@@ -477,6 +481,7 @@ int32_t cmx_destroy(cmx_handle *h) {
     }
     h->d_sol_off.release(); h->d_sol_ids.release(); h->d_solv_off.release(); h->d_solv_ids.release();
     h->d_cnt.release(); h->d_acc.release(); h->d_emit.release(); h->d_rand_list.release(); h->d_list_all.release(); h->d_stats.release();
+    feed_destroy(h);
     for (FrameCtx *x : h->ctx) { h->cur = x; pairs_release(h); x->release(); delete x; }
     h->ctx.clear(); h->cur = nullptr;
     for (auto &p : h->prof_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -820,3 +825,5 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
 }
 
 }  // extern "C"
+
+#include "cmx_feed.inl"

@@ -15,11 +15,11 @@ from typing import Optional
 
 import numpy as np
 
-from .engine import Engine
+from .engine import DcdFile, Engine
 from .options import Options
 from .results import Result, finalresults, new_result
 from .selection import AtomSelection
-from .trajectory import Trajectory, make_trajectory, trajectory_metadata
+from .trajectory import NamdDCD, Trajectory, make_trajectory, trajectory_metadata
 
 
 def frames_to_compute(options: Options, lastframe_read: int, frame_weights) -> list:
@@ -70,11 +70,17 @@ def allreduce_counters(eng: Engine, volume_total: float, sum_weights: float):
 def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[AtomSelection] = None,
          options: Optional[Options] = None, *, trajectory_format: str = "", frame_weights=(),
          coordination_number_only: bool = False, low_memory: bool = False, device: Optional[int] = None,
-         path: int = 0, _engine_kw: Optional[dict] = None) -> Result:
+         path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None) -> Result:
     """mddf(trajectory_file, solute, solvent, options; ...) or mddf(trajectory, options; ...).
 
     ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
     counters per GPU regardless of the thread count (src/parallel_setup.jl:21-54 does not apply).
+
+    ``feed``: "native" = the library's own DCD feed (``cmx_run_dcd``: reader threads -> pinned ring ->
+    raw frame H2D -> device gather of the selections; the frames of this rank are read by offset, the
+    others are never touched), "host" = this module's reader writing into the pinned staging slot
+    (``cmx_acquire_frame_buffer`` / ``cmx_submit_frame``), "auto" = native for DCD files.  Both give
+    the same counters.  The cooperative stop file (src/mddf.jl:301-304) is only polled by the host feed.
     """
     if isinstance(trajectory, str):
         if isinstance(solvent, Options) and options is None:      # mddf(file, solute_and_solvent, options)
@@ -95,23 +101,38 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
                  autocorrelation=R.autocorrelation, coordination_number_only=coordination_number_only, device=device,
                  path=path, **(_engine_kw or {}))
     todo = frames_to_compute(options, tmeta.lastframe_read, R.files[0].frame_weights)
-    mine = set(f for f, _ in shard(todo, rank, world))
-    weights = dict(todo)
-    trajectory.open()
-    trajectory.firstframe()
-    iframe = 0
-    try:
-        for iframe in range(1, tmeta.lastframe_read + 1):
-            if os.path.isfile("stop_complexmixtures"):   # src/mddf.jl:301-304
-                break
-            if iframe in mine:
-                xs, xv = eng.acquire()
-                trajectory.nextframe(xs, xv)             # reader writes fp32 straight into the pinned slot
-                eng.submit(iframe, weights[iframe], trajectory.getunitcell())
-            else:
-                trajectory.nextframe()
-    finally:
-        trajectory.close()
+    if feed not in ("auto", "native", "host"):
+        raise ValueError("feed must be 'auto', 'native' or 'host'")
+    native = feed == "native" or (feed == "auto" and isinstance(trajectory, NamdDCD))
+    if native and not isinstance(trajectory, NamdDCD):
+        raise ValueError("feed='native' needs a DCD trajectory")
+    if native:
+        my = shard(todo, rank, world)
+        dcd = DcdFile(trajectory.filename)
+        try:
+            w = [wt for _, wt in my]
+            eng.run_dcd(dcd, trajectory.solute.indices, trajectory.solvent.indices, [f - 1 for f, _ in my],
+                        None if all(v == 1.0 for v in w) else w, n_reader_threads=reader_threads)
+        finally:
+            eng.sync()
+            dcd.close()
+    else:
+        mine = set(f for f, _ in shard(todo, rank, world))
+        weights = dict(todo)
+        trajectory.open()
+        trajectory.firstframe()
+        try:
+            for iframe in range(1, tmeta.lastframe_read + 1):
+                if os.path.isfile("stop_complexmixtures"):   # src/mddf.jl:301-304
+                    break
+                if iframe in mine:
+                    xs, xv = eng.acquire()
+                    trajectory.nextframe(xs, xv)             # reader writes fp32 straight into the pinned slot
+                    eng.submit(iframe, weights[iframe], trajectory.getunitcell())
+                else:
+                    trajectory.nextframe()
+        finally:
+            trajectory.close()
     if world > 1:
         c0 = eng.finish()
         vol, sw = allreduce_counters(eng, c0["volume_total"], c0["sum_weights"])

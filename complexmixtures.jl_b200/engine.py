@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmx_b200.so")
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
-        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl")]
+        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl", "cmx_feed.inl")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "cmx_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "63"]
@@ -58,7 +58,11 @@ class CmxStats(C.Structure):
     _fields_ = [("frames", C.c_int64), ("kernel_launches", C.c_int64), ("deferred", C.c_int64), ("pair_evals", C.c_int64),
                 ("hits_real", C.c_int64), ("hits_random", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_main", C.c_double), ("gpu_ms_search_real", C.c_double),
-                ("gpu_ms_search_random", C.c_double)]
+                ("gpu_ms_search_random", C.c_double), ("gpu_ms_reduce", C.c_double)]
+
+
+class CmxDcdInfo(C.Structure):
+    _fields_ = [("natoms", C.c_int64), ("nframes", C.c_int64), ("first_frame_offset", C.c_int64), ("frame_bytes", C.c_int64)]
 
 
 MD_DTYPE = np.dtype([("within_cutoff", np.int32), ("i", np.int32), ("j", np.int32),
@@ -67,7 +71,8 @@ MD_DTYPE = np.dtype([("within_cutoff", np.int32), ("i", np.int32), ("j", np.int3
 EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_acquire_frame_buffer", "cmx_submit_frame",
            "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_finish", "cmx_read_minimum_distances",
            "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option", "cmx_alloc_pinned",
-           "cmx_free_pinned"]
+           "cmx_free_pinned", "cmx_dcd_last_error", "cmx_dcd_open", "cmx_dcd_close", "cmx_dcd_read_frame", "cmx_run_dcd",
+           "cmx_reduce_groups"]
 
 _lib = None
 
@@ -99,8 +104,14 @@ def load_library(path: str = LIB_PATH):
     lib.cmx_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     lib.cmx_alloc_pinned.argtypes = [C.POINTER(vp), C.c_int64]
     lib.cmx_free_pinned.argtypes = [vp]
+    lib.cmx_dcd_last_error.restype = C.c_char_p
+    lib.cmx_dcd_open.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(CmxDcdInfo)]
+    lib.cmx_dcd_close.argtypes = [vp]
+    lib.cmx_dcd_read_frame.argtypes = [vp, C.c_int64, vp, vp, vp, C.POINTER(C.c_double)]
+    lib.cmx_run_dcd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
+    lib.cmx_reduce_groups.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("cmx_version", "cmx_last_error"):
+        if name not in ("cmx_version", "cmx_last_error", "cmx_dcd_last_error"):
             getattr(lib, name).restype = C.c_int32
     _lib = lib
     return lib
@@ -118,6 +129,45 @@ def cell_to_c(cell) -> np.ndarray:
     if cell.shape == (3,):
         cell = np.diag(cell)
     return np.ascontiguousarray(cell.T).reshape(9).copy()
+
+
+class DcdFile:
+    """Native DCD reader of the library (cmx_dcd_*): pure host code, usable without a GPU.  Mirrors
+    NamdDCD (src/trajectory_formats/NamdDCD.jl): frame count from the file size, unit cell record
+    [A, gamma, B, beta, alpha, C] -> matrix with the lattice vectors as columns."""
+
+    def __init__(self, filename: str):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        info = CmxDcdInfo()
+        rc = self.lib.cmx_dcd_open(os.fsencode(filename), C.byref(self.h), C.byref(info))
+        if rc:
+            self.h = None
+            raise CmxError(rc, self.lib.cmx_dcd_last_error().decode())
+        self.filename = filename
+        self.natoms, self.nframes = int(info.natoms), int(info.nframes)
+        self.first_frame_offset, self.frame_bytes = int(info.first_frame_offset), int(info.frame_bytes)
+
+    def read_frame(self, iframe: int):
+        """(xyz fp32 [natoms,3], cell 3x3 with lattice vectors as columns) of 0-based frame ``iframe``."""
+        x = np.empty((3, self.natoms), dtype=np.float32)
+        cell = np.zeros(9)
+        rc = self.lib.cmx_dcd_read_frame(self.h, int(iframe), x[0].ctypes.data, x[1].ctypes.data, x[2].ctypes.data,
+                                         cell.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc:
+            raise CmxError(rc, self.lib.cmx_dcd_last_error().decode())
+        return np.ascontiguousarray(x.T), cell.reshape(3, 3).T.copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cmx_dcd_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:
@@ -203,6 +253,32 @@ class Engine:
         c = cell_to_c(cell)
         self._ck(self.lib.cmx_submit_frame_device(self.h, C.c_void_p(d_solute_ptr or 0), C.c_void_p(d_solvent_ptr), int(frame_index),
                                                   float(weight), c.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def run_dcd(self, dcd: "DcdFile", solute_indices, solvent_indices, frames, weights=None, n_reader_threads: int = 0):
+        """cmx_run_dcd: the whole frame loop for a DCD file inside the library (reader threads ->
+        pinned ring -> one H2D per raw frame -> device gather of the selections -> frame pipeline).
+        ``frames``: 0-based frame numbers in the file; the Philox frame key is frame + 1."""
+        fr = np.ascontiguousarray(frames, dtype=np.int64)
+        sv = np.ascontiguousarray(solvent_indices, dtype=np.int32)
+        ss = None if self.autocorrelation else np.ascontiguousarray(solute_indices, dtype=np.int32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self._ck(self.lib.cmx_run_dcd(self.h, dcd.h, None if ss is None else ss.ctypes.data, sv.ctypes.data, fr.ctypes.data,
+                                      None if w is None else w.ctypes.data, int(fr.size), int(n_reader_threads)))
+
+    def reduce_groups(self, which: str, groups) -> np.ndarray:
+        """cmx_reduce_groups: per-group sums of the rows of one group-count array, on the device.
+        ``which``: solute_group_count | solute_group_count_random | solvent_group_count |
+        solvent_group_count_random; ``groups``: sequence of sequences of 0-based row ids.
+        Returns f64 [n_groups, nbins] (what summing those rows of ``finish()`` would give)."""
+        code = ["solute_group_count", "solute_group_count_random", "solvent_group_count", "solvent_group_count_random"].index(which)
+        off = np.zeros(len(groups) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(g) for g in groups])
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.int32).reshape(-1) for g in groups])
+                                    if len(groups) and off[-1] else np.zeros(0, dtype=np.int32), dtype=np.int32)
+        out = np.zeros((len(groups), self.nbins))
+        self._ck(self.lib.cmx_reduce_groups(self.h, code, len(groups), off.ctypes.data, rows.ctypes.data if rows.size else None,
+                                            out.ctypes.data))
+        return out
 
     def sync(self):
         self._ck(self.lib.cmx_sync(self.h))

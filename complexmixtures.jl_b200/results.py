@@ -236,6 +236,50 @@ _VEC = ["d", "md_count", "md_count_random", "coordination_number", "coordination
 _MAT = ["solute_group_count", "solvent_group_count", "solute_group_count_random", "solvent_group_count_random"]
 
 
+def _same_selection(a: AtomSelection, b: AtomSelection) -> bool:
+    return (a.nmols == b.nmols and a.natomspermol == b.natomspermol and len(a.indices) == len(b.indices)
+            and bool(np.array_equal(a.indices, b.indices)) and a.n_groups == b.n_groups)
+
+
+def merge(results: List[Result]) -> Result:
+    """merge(r::Vector{Result}), src/tools/merge.jl:10-148: averages of the functions and counters of
+    the sets, weighted by the (weighted) number of frames of each set; ``weights`` of the merged
+    Result = fraction of the frames read from each file."""
+    results = list(results)
+    if not results:
+        raise ValueError("merge needs at least one Result")
+    r0 = results[0]
+    for i, ri in enumerate(results):
+        for rj in results[i + 1:]:
+            if ri.nbins != rj.nbins:
+                raise ValueError("To merge Results, the number of bins of the histograms of the sets must be the same.")
+            if not np.isclose(ri.cutoff, rj.cutoff):
+                raise ValueError("To merge Results, cutoff distance of the of the histograms of the sets must be the same.")
+            if not _same_selection(ri.solute, rj.solute) or not _same_selection(ri.solvent, rj.solvent):
+                raise ValueError("To merge Results, the solute and solvent selections of the sets must be the same.")
+    ntot_frames = sum(f.nframes_read for r in results for f in r.files)
+    tot_frame_weight = sum(sum_frame_weights(r) for r in results)
+    files = [f for r in results for f in r.files]
+    R = Result(nbins=r0.nbins, dbulk=r0.dbulk, cutoff=r0.cutoff, autocorrelation=r0.autocorrelation, solute=r0.solute,
+               solvent=r0.solvent, files=files, weights=[f.nframes_read / ntot_frames for f in files])
+    R.d = r0.d.copy()
+    arrays = ("mddf", "kb", "rdf", "kb_rdf", "md_count", "md_count_random", "coordination_number",
+              "coordination_number_random", "solute_group_count", "solute_group_count_random", "solvent_group_count",
+              "solvent_group_count_random", "rdf_count", "rdf_count_random", "sum_rdf_count", "sum_rdf_count_random")
+    for r in results:
+        w = sum_frame_weights(r) / tot_frame_weight
+        for k in arrays:
+            setattr(R, k, getattr(R, k) + w * np.asarray(getattr(r, k)))
+        R.density.solute += w * r.density.solute
+        R.density.solvent += w * r.density.solvent
+        R.density.solvent_bulk += w * r.density.solvent_bulk
+        R.volume.total += w * r.volume.total
+        R.volume.bulk += w * r.volume.bulk
+        R.volume.domain += w * r.volume.domain
+        R.volume.shell = R.volume.shell + w * np.asarray(r.volume.shell)
+    return R
+
+
 def save(R: Result, filename: str) -> str:
     out = {"Version": R.Version, "nbins": R.nbins, "dbulk": R.dbulk, "cutoff": R.cutoff,
            "autocorrelation": R.autocorrelation, "solute": R.solute.to_dict(), "solvent": R.solvent.to_dict()}

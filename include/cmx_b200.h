@@ -32,6 +32,7 @@ extern "C" {
 #define CMX_ERR_CUDA 2     /* CUDA runtime error (message has the CUDA error string)   */
 #define CMX_ERR_CELL 3     /* unit cell narrower than 2*cutoff in some direction       */
 #define CMX_ERR_STATE 4    /* call sequence error (e.g. submit without acquire)        */
+#define CMX_ERR_IO 5       /* trajectory file error (open / short read / bad header)   */
 
 typedef struct cmx_handle cmx_handle;
 
@@ -100,6 +101,7 @@ typedef struct cmx_stats {
     double gpu_ms_main;        /* device time spent in the search kernels (needs option "profile") */
     double gpu_ms_search_real;   /* ... of which: real-phase search / pair kernel                  */
     double gpu_ms_search_random; /* ... of which: random-phase search kernel                       */
+    double gpu_ms_reduce;        /* device time of the last cmx_reduce_groups row-sum kernel (option "profile") */
 } cmx_stats;
 
 const char *cmx_version(void);
@@ -143,6 +145,47 @@ int32_t cmx_read_random_minimum_distances(cmx_handle *h, int32_t sample, cmx_md 
 /* Page-locked host memory for the caller's result arrays (cmx_finish then copies at full PCIe speed). */
 int32_t cmx_alloc_pinned(void **ptr, int64_t bytes);
 int32_t cmx_free_pinned(void *ptr);
+
+/* ---- frame feed: native DCD reader ------------------------------------------------
+ * Replaces the host-side record read + per-atom gather of nextframe!(::NamdDCD)
+ * (src/trajectory_formats/NamdDCD.jl:141-169), getunitcell (:175-188) and the frame count from the
+ * file size (:211-230).  The cmx_dcd_* functions are pure host code (no GPU needed). */
+typedef struct cmx_dcd cmx_dcd;
+typedef struct cmx_dcd_info {
+    int64_t natoms;             /* atoms per frame in the file                                   */
+    int64_t nframes;            /* counted from the file size, not taken from the header         */
+    int64_t first_frame_offset; /* byte offset of the first frame                                */
+    int64_t frame_bytes;        /* 56 + 3*(8 + 4*natoms): cell record + X, Y, Z records          */
+} cmx_dcd_info;
+
+const char *cmx_dcd_last_error(void);
+int32_t cmx_dcd_open(const char *path, cmx_dcd **out, cmx_dcd_info *info);
+int32_t cmx_dcd_close(cmx_dcd *d);
+/* One frame (0-based) to host arrays: x, y, z [natoms] (any may be NULL) and the unit cell as the
+ * column-major 3x3 matrix cmx_submit_frame takes.  Thread-safe (pread). */
+int32_t cmx_dcd_read_frame(cmx_dcd *d, int64_t iframe, float *x, float *y, float *z, double cell[9]);
+
+/* The whole frame loop of the chunk task (src/mddf.jl:296-334) for a DCD file, in the library:
+ * reader threads pread the raw frame records straight into a pinned ring, the raw records go to the
+ * device in one async copy, a kernel gathers the selected atoms (indices are 1-based positions in
+ * the file, as AtomSelection.indices) and the frame is enqueued like cmx_submit_frame does.
+ * frames[k] = 0-based frame number in the file; the Philox frame key is frames[k] + 1 (the
+ * reference's 1-based iframe), so the result equals the acquire/submit path on the same frames.
+ * weights may be NULL (all 1); zero-weight frames must be left out by the caller.
+ * For an autocorrelation solute_indices is ignored.  Returns after the last frame is enqueued. */
+int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, const int32_t *solvent_indices,
+                    const int64_t *frames, const double *weights, int64_t nframes, int32_t n_reader_threads);
+
+/* ---- group reduction on the device ------------------------------------------------
+ * The count stage of contributions()/ResidueContributions (src/tools/contributions.jl:70-248,
+ * src/tools/residue_contributions.jl:157-215): out[g][b] = sum of the rows of one group-count array
+ * that belong to group g, with the frame weights applied as in cmx_finish -- without reading the
+ * (possibly multi-GB) per-atom array back to the host.
+ * which: 0 solute_group_count, 1 solute_group_count_random, 2 solvent_group_count,
+ * 3 solvent_group_count_random.  CSR group -> rows (0-based rows of that array).
+ * out: host array [n_groups][nbins] f64.  Integer counts are summed exactly (order independent). */
+int32_t cmx_reduce_groups(cmx_handle *h, int32_t which, int32_t n_groups, const int32_t *offsets,
+                          const int32_t *rows, double *out);
 
 int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out);
 int32_t cmx_reset(cmx_handle *h);                       /* zero all accumulators and statistics */

@@ -480,3 +480,151 @@ def test_small_and_large_cutoffs(bulk_range):
                 [f[wat.indices - 1] for f in fr], s.cell)
     dev, o, _ = check(p)
     assert dev["md_count"].sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# native DCD feed, device-side group reduction, merge
+# ---------------------------------------------------------------------------------------------
+def _dcd_with_padding(tmp_path, triclinic_second=False):
+    """a DCD whose selected atoms are a strict, shuffled-order subset of the file (so that the device gather matters)"""
+    from common import write_dcd
+    d = namd()
+    nf = d["protein"].shape[0]
+    rng = np.random.default_rng(11)
+    pad0 = rng.uniform(0, 80, size=(nf, 7, 3)).astype(np.float32)
+    pad1 = rng.uniform(0, 80, size=(nf, 13, 3)).astype(np.float32)
+    frames = np.concatenate([pad0, d["protein"], pad1, d["tmao"]], axis=1)       # protein at 8..1470, TMAO at 1484..4017
+    cells = [np.asarray(c, dtype=np.float64) for c in d["cells"]]
+    if triclinic_second:
+        cells[1] = np.array([[84.4, 6.0, 4.0], [0.0, 84.0, 5.0], [0.0, 0.0, 83.5]])
+    path = str(tmp_path / "padded.dcd")
+    write_dcd(path, frames, cells)
+    sol = cm.AtomSelection(np.arange(8, 8 + 1463), nmols=1)
+    tm = cm.AtomSelection(np.arange(1484, 1484 + 2534), natomspermol=14)
+    return path, sol, tm, d
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_native_dcd_feed_equals_the_staging_slot_path(tmp_path, threads):
+    """cmx_run_dcd (reader threads -> pinned ring -> raw H2D -> device gather) == acquire/submit with the host
+    reader == oracle, bit for bit; frames by number (any order/subset), weights, triclinic frame included."""
+    from cmx_b200.engine import DcdFile, Engine
+    path, sol, tm, d = _dcd_with_padding(tmp_path, triclinic_second=True)
+    opt = opts(bulk_range=(8.0, 10.0), n_random_samples=3)
+    f = DcdFile(path)
+    cells = [f.read_frame(k)[1] for k in range(3)]
+    # many passes over the 3 frames so that the ring (4+ slots) wraps several times
+    order = [0, 1, 2, 2, 1, 0, 1, 1, 2, 0, 0, 2, 1]
+    weights = [1.0, 2.0, 1.0, 1.0, 2.0, 1.0, 2.0, 2.0, 1.0, 1.0, 1.0, 1.0, 2.0]
+    eng = Engine(solute=sol, solvent=tm, options=opt, irefatom=1, autocorrelation=False)
+    eng.run_dcd(f, sol.indices, tm.indices, order, weights, n_reader_threads=threads)
+    dev = eng.finish()
+    st = eng.stats()
+    assert st["frames"] == len(order) and st["h2d_bytes"] == len(order) * f.frame_bytes
+    # same frames through the staging-slot path (frame key = frame number + 1)
+    eng2 = Engine(solute=sol, solvent=tm, options=opt, irefatom=1, autocorrelation=False)
+    for k, w in zip(order, weights):
+        eng2.submit_arrays(d["protein"][k], d["tmao"][k], cells[k], frame_index=k + 1, weight=w)
+    dev2 = eng2.finish(); eng2.close()
+    for key in dev:
+        assert np.array_equal(dev[key], dev2[key]), key
+    p = Problem(sol, tm, opt, [d["protein"][k] for k in order], [d["tmao"][k] for k in order], [cells[k] for k in order],
+                weights=weights, frame_ids=[k + 1 for k in order], irefatom=1)
+    o, _ = p.oracle()
+    assert_counters_equal(dev, o, exact=True)
+    # a second run on the same handle re-uses the ring; an autocorrelation ignores the solute indices
+    eng.reset()
+    eng.run_dcd(f, sol.indices, tm.indices, [2])
+    one = eng.finish(); eng.close()
+    p1 = Problem(sol, tm, opt, [d["protein"][2]], [d["tmao"][2]], [cells[2]], frame_ids=[3], irefatom=1)
+    assert_counters_equal(one, p1.oracle()[0])
+    enga = Engine(solute=tm, solvent=tm, options=opt, irefatom=1, autocorrelation=True)
+    enga.run_dcd(f, None, tm.indices, [0, 2])
+    da = enga.finish(); enga.close()
+    pa = Problem(tm, tm, opt, [d["tmao"][0], d["tmao"][2]], None, [cells[0], cells[2]], autocorrelation=True, frame_ids=[1, 3], irefatom=1)
+    assert_counters_equal(da, pa.oracle()[0])
+    f.close()
+
+
+def test_native_feed_errors_and_public_driver(tmp_path):
+    from cmx_b200.engine import CmxError, DcdFile, Engine
+    path, sol, tm, d = _dcd_with_padding(tmp_path)
+    opt = opts(bulk_range=(8.0, 10.0), n_random_samples=2)
+    f = DcdFile(path)
+    eng = Engine(solute=sol, solvent=tm, options=opt, irefatom=1, autocorrelation=False)
+    with pytest.raises(CmxError):
+        eng.run_dcd(f, sol.indices, tm.indices, [3])                       # frame outside the file
+    with pytest.raises(CmxError):
+        eng.run_dcd(f, sol.indices, tm.indices + 100000, [0])              # index outside the file
+    with pytest.raises(CmxError):
+        eng.run_dcd(f, sol.indices, tm.indices, [0], [0.0])                # zero weight
+    eng.run_dcd(f, sol.indices, tm.indices, [])                            # nothing to do
+    assert eng.stats()["frames"] == 0
+    eng.close(); f.close()
+    # public driver: native feed (default for DCD) == host feed, incl. firstframe/stride/weights
+    for kw in (dict(), dict(firstframe=2), dict(stride=2)):
+        o = opts(bulk_range=(8.0, 10.0), n_random_samples=2, **kw)
+        Rn = cm.mddf(path, sol, tm, o, frame_weights=[1.0, 3.0, 0.5], feed="native", reader_threads=2)
+        Rh = cm.mddf(path, sol, tm, o, frame_weights=[1.0, 3.0, 0.5], feed="host")
+        for key in ("md_count", "md_count_random", "rdf_count", "solute_group_count", "solvent_group_count_random", "mddf", "kb"):
+            assert np.array_equal(getattr(Rn, key), getattr(Rh, key)), (kw, key)
+        assert Rn.volume.total == Rh.volume.total
+    with pytest.raises(ValueError):
+        cm.mddf(cm.ArrayTrajectory(d["protein"], d["cells"], sol, sol), opts(), feed="native")
+
+
+@pytest.mark.parametrize("auto", [False, True])
+def test_reduce_groups_on_device(auto):
+    """cmx_reduce_groups == summing the rows of cmx_finish's arrays (contributions / ResidueContributions count stage)."""
+    d = namd()
+    opt = opts(bulk_range=(8.0, 10.0), n_random_samples=3)
+    if auto:
+        p = Problem(TMAO, TMAO, opt, d["tmao"][:2], None, d["cells"][:2], autocorrelation=True, irefatom=1)
+    else:
+        p = Problem(PROTEIN, TMAO, opt, d["protein"][:2], d["tmao"][:2], d["cells"][:2], irefatom=1)
+    eng = p.engine()
+    eng.set_option("profile", 1)
+    dev = p.run_engine(eng)
+    nrows = dev["solute_group_count"].shape[0]
+    rng = np.random.default_rng(5)
+    groups = [np.arange(0, nrows)[k::7] for k in range(7)]                     # disjoint cover
+    groups += [rng.choice(nrows, size=min(nrows, 300), replace=False), np.array([0]), np.zeros(0, dtype=int), np.arange(nrows)]
+    for which in ("solute_group_count", "solute_group_count_random", "solvent_group_count", "solvent_group_count_random"):
+        arr = dev[which]
+        gs = groups if arr.shape[0] == nrows else [np.arange(arr.shape[0]), np.array([1, 3]), np.zeros(0, dtype=int)]
+        got = eng.reduce_groups(which, gs)
+        want = np.stack([arr[np.asarray(g, dtype=int)].sum(axis=0) if len(g) else np.zeros(arr.shape[1]) for g in gs])
+        assert np.array_equal(got, want), which
+    assert eng.stats()["gpu_ms_reduce"] > 0
+    # the seven disjoint groups add up to md_count (tools/contributions.jl:320-348); half weights in an autocorrelation
+    tot = eng.reduce_groups("solute_group_count", groups[:7]).sum(axis=0)
+    assert np.array_equal(tot, dev["md_count"])
+    from cmx_b200.engine import CmxError
+    with pytest.raises(CmxError):
+        eng.reduce_groups("solute_group_count", [np.array([nrows])])
+    eng.close()
+    # varying frame weights: fp64 accumulators are part of the sum
+    pw = Problem(PROTEIN, TMAO, opt, d["protein"], d["tmao"], d["cells"], weights=[1.0, 0.3, 2.5], irefatom=1)
+    eng = pw.engine()
+    dev = pw.run_engine(eng)
+    gs = [np.arange(0, 1463)[k::3] for k in range(3)]
+    got = eng.reduce_groups("solute_group_count", gs); eng.close()
+    want = np.stack([dev["solute_group_count"][g].sum(axis=0) for g in gs])
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_merge_of_two_halves_equals_reference_semantics():
+    """merge (src/tools/merge.jl:150-222): toy two-atom system, halves of the trajectory, weighted frames."""
+    t = toy()
+    at1, at2 = cm.AtomSelection([1], nmols=1), cm.AtomSelection([2], nmols=1)
+    tr = lambda: cm.ArrayTrajectory(t["self_monoatomic"], t["self_monoatomic_cells"], at1, at2)
+    R1 = cm.mddf(tr(), opts(lastframe=1, n_random_samples=100))
+    R2 = cm.mddf(tr(), opts(firstframe=2, n_random_samples=100))
+    assert R1.md_count.sum() == 1 and R2.md_count.sum() == 0
+    R = cm.merge([R1, R2])
+    assert R.weights == [0.5, 0.5] and R.md_count.sum() == 0.5 and len(R.files) == 2
+    R1w = cm.mddf(tr(), opts(lastframe=1, n_random_samples=100), frame_weights=[2.0])
+    assert R1w.md_count.sum() == 1
+    R = cm.merge([R1w, R2])
+    assert np.isclose(R.md_count.sum(), 2 / 3) and np.isclose(R.solute_group_count.sum(), 2 / 3) and np.isclose(R.solvent_group_count.sum(), 2 / 3)
+    assert R.volume.total == 27000.0

@@ -132,12 +132,13 @@ def test_cabi_exports_every_declared_symbol():
     lib.cmx_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.cmx_version()
     # struct layouts agree with the header (compiled with the host compiler)
-    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats));}'
+    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats), sizeof(cmx_dcd_info));}'
     exe = os.path.join("/tmp", f"cmx_sz_{os.getpid()}")
     subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
     os.remove(exe)
-    assert sizes == [ctypes.sizeof(engine.CmxConfig), ctypes.sizeof(engine.CmxCounters), engine.MD_DTYPE.itemsize, ctypes.sizeof(engine.CmxStats)]
+    assert sizes == [ctypes.sizeof(engine.CmxConfig), ctypes.sizeof(engine.CmxCounters), engine.MD_DTYPE.itemsize, ctypes.sizeof(engine.CmxStats),
+                     ctypes.sizeof(engine.CmxDcdInfo)]
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_oracle():
@@ -228,3 +229,73 @@ def test_dcd_reader_roundtrip(tmp_path):
         cm.trajectory_metadata(t, cm.Options(silent=True, lastframe=7))
     with pytest.raises(ValueError):
         cm.trajectory_metadata(t, cm.Options(silent=True, irefatom=15))
+
+
+def test_native_dcd_reader_matches_host_reader(tmp_path):
+    """cmx_dcd_* (pure host code of the library, no GPU): header parsing, frame count from the file size,
+    X/Y/Z records and the unit cell agree with the NamdDCD mirror of src/trajectory_formats/NamdDCD.jl:141-230."""
+    from common import namd, write_dcd
+    from cmx_b200.engine import CmxError, DcdFile
+    d = namd()
+    frames = np.concatenate([d["protein"], d["tmao"]], axis=1)
+    path = str(tmp_path / "t.dcd")
+    tri = np.array([[40.0, 8.0, 5.0], [0.0, 38.0, 7.0], [0.0, 0.0, 36.0]])
+    cells = [d["cells"][0], tri, d["cells"][2]]
+    write_dcd(path, frames, cells)
+    f = DcdFile(path)
+    assert (f.natoms, f.nframes) == (3997, 3) and f.frame_bytes == 56 + 3 * (8 + 4 * 3997)
+    sel = cm.AtomSelection(np.arange(1, 3998), nmols=1)
+    t = cm.make_trajectory(path, sel, sel)
+    t.open()
+    for k in (0, 1, 2):
+        x, cell = f.read_frame(k)
+        xs, _ = t.nextframe()
+        assert np.array_equal(x, frames[k]) and np.array_equal(x, xs)
+        assert np.allclose(cell, t.getunitcell(), rtol=1e-15, atol=1e-12)
+        if k != 1:
+            assert np.array_equal(cell, np.asarray(cells[k]))          # orthorhombic: exact
+    t.close()
+    with pytest.raises(CmxError):
+        f.read_frame(3)
+    f.close()
+    # trailing partial frame is ignored (frame count from the size), garbage and missing files are errors
+    with open(path, "ab") as fh:
+        fh.write(b"\0" * 100)
+    g = DcdFile(path); assert g.nframes == 3; g.close()
+    bad = tmp_path / "bad.dcd"; bad.write_bytes(b"\x54\0\0\0XXXX" + b"\0" * 200)
+    with pytest.raises(CmxError):
+        DcdFile(str(bad))
+    with pytest.raises(CmxError):
+        DcdFile(str(tmp_path / "missing.dcd"))
+
+
+def test_merge_weights_and_errors():
+    """merge (src/tools/merge.jl:10-148) on hand-made Results: frame-weighted averages, file weights, error paths."""
+    from cmx_b200.results import Result, TrajectoryFileOptions, merge, sum_frame_weights
+    sol = cm.AtomSelection([1, 2, 3], nmols=1); solv = cm.AtomSelection(np.arange(4, 10), natomspermol=3)
+
+    def mk(nframes, fw, fill, **okw):
+        o = cm.Options(silent=True, **okw)
+        nb = cm.setbin(o.cutoff, o.binstep)
+        R = Result(nbins=nb, dbulk=o.dbulk, cutoff=o.cutoff, autocorrelation=False, solute=sol, solvent=solv,
+                   files=[TrajectoryFileOptions("f.dcd", o, 1, nframes, nframes, np.asarray(fw, dtype=float))])
+        R.md_count[:] = fill; R.mddf[:] = 2 * fill; R.solute_group_count[:] = fill; R.volume.total = 100.0 * fill
+        R.density.solvent_bulk = fill
+        return R
+    A, B = mk(2, [1.0, 1.0], 1.0), mk(6, [1.0] * 6, 3.0)
+    M = merge([A, B])
+    assert M.weights == [0.25, 0.75] and len(M.files) == 2
+    assert np.allclose(M.md_count, 0.25 * 1 + 0.75 * 3) and np.allclose(M.mddf, 2 * 2.5) and np.isclose(M.volume.total, 250.0)
+    assert np.allclose(M.solute_group_count, 2.5) and np.isclose(M.density.solvent_bulk, 2.5)
+    # custom frame weights change the data weights but not the file weights (merge.jl:112-121)
+    Aw = mk(2, [3.0, 3.0], 1.0)
+    Mw = merge([Aw, B])
+    assert Mw.weights == [0.25, 0.75] and np.allclose(Mw.md_count, 0.5 * 1 + 0.5 * 3)
+    assert sum_frame_weights(Mw) == 12.0
+    with pytest.raises(ValueError, match="number of bins"):
+        merge([A, mk(2, [1, 1], 1.0, binstep=0.05)])
+    with pytest.raises(ValueError, match="cutoff distance"):
+        merge([A, mk(2, [1, 1], 1.0, bulk_range=(4.0, 5.0), binstep=0.01)])
+    other = mk(2, [1, 1], 1.0); other.solute = cm.AtomSelection([1, 2, 4], nmols=1)
+    with pytest.raises(ValueError, match="selections"):
+        merge([A, other])
