@@ -127,6 +127,7 @@ struct cmx_handle {
     Geom last_g{};
     const float *last_dsol = nullptr, *last_dsolv = nullptr;
     int num_sms = 148;
+    int search_grid[2] = {148 * 5, 148 * 4};   // one resident wave of k_tile_search<false/true> (occupancy query at create)
     cmx_feed *feed = nullptr;
 };
 
@@ -277,10 +278,14 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
     FrameCtx &x = *h->cur;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
     // (query positions, res and the per-cell counts were produced by k_gen_*)
-    size_t tmp_bytes = x.d_cub_tmp.n;
-    cub::TransformInputIterator<int, TileCountOp, const int *> tiles_of((const int *)x.d_qcell_count.p, TileCountOp());
-    CK(cub::DeviceScan::ExclusiveSum(x.d_cub_tmp.p, tmp_bytes, tiles_of, x.d_qcell_start.p, (int)(nqc + 1), x.stream));
-    h->stats.kernel_launches += 2;
+    if (nqc + 1 <= CMX_SCAN_SMALL_MAX)
+        launch(h, k_scan_small<TileCountOp>, dim3(1), dim3(CMX_SCAN_THREADS), (const int *)x.d_qcell_count.p, x.d_qcell_start.p, (int)(nqc + 1), TileCountOp());
+    else {
+        size_t tmp_bytes = x.d_cub_tmp.n;
+        cub::TransformInputIterator<int, TileCountOp, const int *> tiles_of((const int *)x.d_qcell_count.p, TileCountOp());
+        CK(cub::DeviceScan::ExclusiveSum(x.d_cub_tmp.p, tmp_bytes, tiles_of, x.d_qcell_start.p, (int)(nqc + 1), x.stream));
+        h->stats.kernel_launches += 2;
+    }
     // worst case: every atom in a tile of its own cell's last, partially filled tile
     size_t slots = std::min(max_atoms + 32 * nqc, x.d_qsorted.n);
     CK(cudaMemsetAsync(x.d_qsorted.p, 0xff, sizeof(float4) * slots, x.stream));
@@ -289,10 +294,11 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
            (const int *)x.d_qcell_start.p, x.d_qsorted.p);
     cudaEvent_t pe = prof_begin(h, tag);
     u64 *pev = h->count_pairs ? h->d_stats.p : nullptr;
-    if (pev) launch(h, k_tile_search<true>, dim3(h->num_sms * 8), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                    (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
-    else launch(h, k_tile_search<false>, dim3(h->num_sms * 8), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev);
+    int *tile_queue = (int *)x.d_occ.p + (RANDOM ? 7 : 6);   // per-frame scalars, zeroed with the bitmaps
+    if (pev) launch(h, k_tile_search<true>, dim3(h->search_grid[1]), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
+                    (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue);
+    else launch(h, k_tile_search<false>, dim3(h->search_grid[0]), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
+                (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue);
     prof_end(h, pe);
     launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
            (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count, s0);
@@ -309,7 +315,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     CK(h->cur->d_cell_start.ensure(ncells + 1));
     // [8 per-frame scalars][cull-grid bitmap][row bitmap] share one buffer: one memset per solute molecule
     CK(h->cur->d_occ.ensure(4 + occ_words + ((size_t)g.ny * g.nz * g.rw)));
-    CK(h->cur->d_edt_x.ensure(ncc)); CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
+    CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
     size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
     u64 *occ_p = h->cur->d_occ.p + 4, *rowmask_p = occ_p + occ_words;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
@@ -330,13 +336,16 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         int tb = 128;
         launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
                (const int *)nullptr, occ_p, rowmask_p, (float4 *)nullptr);
-        size_t tmp_bytes = h->cur->d_cub_tmp.n;
-        CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), h->cur->stream));
-        h->stats.kernel_launches += 2;
+        if (ncells + 1 <= CMX_SCAN_SMALL_MAX)
+            launch(h, k_scan_small<IdentityOp>, dim3(1), dim3(CMX_SCAN_THREADS), (const int *)h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), IdentityOp());
+        else {
+            size_t tmp_bytes = h->cur->d_cub_tmp.n;
+            CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), h->cur->stream));
+            h->stats.kernel_launches += 2;
+        }
         launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
                (const int *)h->cur->d_cell_start.p, occ_p, rowmask_p, h->cur->d_sorted.p);
-        launch(h, k_edt_x, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)occ_p, h->cur->d_edt_x.p);
-        launch(h, k_edt_y, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned char *)h->cur->d_edt_x.p, h->cur->d_edt_xy.p);
+        launch(h, k_edt_xy, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)occ_p, h->cur->d_edt_xy.p);
         launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->cur->d_edt_xy.p, h->cur->d_lbd2.p);
         launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
                (const float *)h->cur->d_lbd2.p, h->cur->d_list.p, h->cur->d_worklist.p, sc + 0, sc + 5);
@@ -364,7 +373,8 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         // random molecules) stays bounded for any n_random_samples; normally one chunk
         for (int s0 = 0; s0 < nrand; s0 += h->sample_chunk) {
             const int s1 = std::min(nrand, s0 + h->sample_chunk);
-            if (s0 > 0) { CK(cudaMemsetAsync(sc + 1, 0, sizeof(int), h->cur->stream)); CK(cudaMemsetAsync(sc + 3, 0, sizeof(int), h->cur->stream)); }
+            if (s0 > 0) { CK(cudaMemsetAsync(sc + 1, 0, sizeof(int), h->cur->stream)); CK(cudaMemsetAsync(sc + 3, 0, sizeof(int), h->cur->stream));
+                          CK(cudaMemsetAsync(sc + 7, 0, sizeof(int), h->cur->stream)); }
             launch(h, k_filter_rand, dim3((unsigned)((nv_mols + 255) / 256), (unsigned)std::min(s1 - s0, 65535)), dim3(256), g, h->P, frame, isolute, skip,
                    s0, s1, (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
             launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, s0, d_solvent, (const float *)h->cur->d_lbd2.p,
@@ -513,6 +523,13 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     CK(cudaSetDevice(c.device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, c.device));
     h->num_sms = prop.multiProcessorCount;
+    {
+        int b0 = 0, b1 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_tile_search<false>, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_tile_search<true>, 256, 0));
+        h->search_grid[0] = h->num_sms * std::max(1, b0); h->search_grid[1] = h->num_sms * std::max(1, b1);
+        if (const char *e = std::getenv("CMX_SEARCH_BLOCKS_PER_SM")) h->search_grid[0] = h->search_grid[1] = h->num_sms * std::max(1, atoi(e));
+    }
     h->nbins = std::max(1, (int)std::ceil(c.cutoff / c.binstep));   // setbin(cutoff, binstep), src/results.jl:131
     h->cut_eff = c.usecutoff ? c.cutoff : c.dbulk;                   // src/minimum_distances.jl:168
     h->ns_atoms = (size_t)c.solute_nmols * c.solute_natomspermol;

@@ -136,6 +136,7 @@ int feed_prepare(cmx_handle *h, const cmx_dcd *d, const int32_t *sol_idx, const 
         }
         F.frame_bytes = fb;
     }
+    CK(cudaStreamSynchronize(h->s_copy));   // copies of an earlier run still reading the pinned slots
     for (auto &s : F.slots) { s.filled = -1; s.h2d_issued = -1; }
     // selection indices (1-based file positions -> 0-based), solute first then solvent
     const size_t ns = h->cfg.autocorrelation ? 0 : h->ns_atoms, nv = h->nv_atoms;
@@ -270,7 +271,11 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
     if (nframes == 0) return CMX_OK;
     CK(cudaSetDevice(h->device));
     const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_reader_threads > 0 ? n_reader_threads : 2, 16), nframes));
-    const int S = std::max(4, T + 2);
+    // ring slots: every compute stream needs a frame in flight and one being staged behind it (a slot is busy from the
+    // pread until its frame's kernels have finished), bounded to ~4 GB of pinned memory
+    const int nctx = h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size();
+    const int64_t cap = std::max<int64_t>(3, (int64_t)(4.0e9 / (double)d->info.frame_bytes));
+    const int S = (int)std::min<int64_t>(std::max(2 * nctx + 2, T + 2), cap);
     { int rc = feed_prepare(h, d, solute_indices, solvent_indices, S); if (rc) return rc; }
     cmx_feed &F = *h->feed;
     std::mutex mu;

@@ -97,19 +97,17 @@ __device__ __forceinline__ uint32_t row_window(const u64 *row, int cw, int cx) {
 // Pass X uses the row bitmaps (nearest set bit), passes Y and Z are min-plus scans over the window.
 __device__ __forceinline__ int edt_f(int a) { int t = max(a - 1, 0); return t * t; }
 
-__global__ void k_edt_x(Geom g, const u64 *__restrict__ occ_bits, unsigned char *__restrict__ ex) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int ncc = g.ncx * g.ncy * g.ncz;
-    if (c >= ncc) return;
-    int cx = c % g.ncx, row = c / g.ncx;
+__device__ __forceinline__ int edt_x_of(const Geom &g, const u64 *__restrict__ occ_bits, int row, int cx) {
     uint32_t w = row_window(occ_bits + (size_t)row * g.cw, g.cw, cx);
     uint32_t hi = w >> 15, lo = w & 0xffffu;
     int dr = hi ? (__ffs(hi) - 1) : 99;
     int dl = lo ? (__clz(lo) - 16) : 99;
-    ex[c] = (unsigned char)min(min(dl, dr), g.dwin + 1);
+    return min(min(dl, dr), g.dwin + 1);
 }
 
-__global__ void k_edt_y(Geom g, const unsigned char *__restrict__ ex, unsigned short *__restrict__ exy) {
+// passes X and Y in one kernel: the X distance of the 2*dwin+1 rows of the window is recomputed from the row
+// bitmaps (a handful of bit operations each) instead of being written and re-read by a separate launch
+__global__ void k_edt_xy(Geom g, const u64 *__restrict__ occ_bits, unsigned short *__restrict__ exy) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     int ncc = g.ncx * g.ncy * g.ncz;
     if (c >= ncc) return;
@@ -118,7 +116,7 @@ __global__ void k_edt_y(Geom g, const unsigned char *__restrict__ ex, unsigned s
     for (int dy = -D; dy <= D; ++dy) {
         int ry = cy + dy;
         if (ry < 0 || ry >= g.ncy) continue;
-        best = min(best, edt_f(ex[(cz * g.ncy + ry) * g.ncx + cx]) + edt_f(abs(dy)));
+        best = min(best, edt_f(edt_x_of(g, occ_bits, cz * g.ncy + ry, cx)) + edt_f(abs(dy)));
     }
     exy[c] = (unsigned short)best;
 }
@@ -254,6 +252,47 @@ k_gen_rand(Geom g, Prob P, uint32_t frame, int s0, const float *__restrict__ xv,
 // tiles never straddle query cells: a cell with n query atoms owns ceil(n/32) tiles
 struct TileCountOp { __host__ __device__ __forceinline__ int operator()(int n) const { return (n + 31) >> 5; } };
 
+// Exclusive scan of a SMALL array (cell / tile counts of one frame: tens of thousands of ints) by ONE block in ONE
+// launch -- the two-kernel decoupled look-back scan of cub only pays off for the large grids (C4, C5), where the
+// host keeps using it.  Four items per thread per pass (16-byte loads when aligned), carry kept in shared memory.
+#define CMX_SCAN_THREADS 1024
+#define CMX_SCAN_SMALL_MAX (1 << 17)
+template <class Op>
+__global__ void __launch_bounds__(CMX_SCAN_THREADS)
+k_scan_small(const int *__restrict__ in, int *__restrict__ out, int n, Op op) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 4 * CMX_SCAN_THREADS) {
+        const int i0 = base + 4 * threadIdx.x;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? op(in[i0 + k]) : 0;
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        const int carry = carry_s;
+        if (wid == 0) {
+            int ws = warp_sums[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            warp_sums[lane] = wi - ws;             // exclusive prefix of the warp totals
+            if (lane == 31) carry_s = carry + wi;  // read by everyone only after the next barrier
+        }
+        __syncthreads();
+        int run = carry + warp_sums[wid] + (incl - mine);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
+        __syncthreads();                            // warp_sums / carry_s are rewritten by the next pass
+    }
+}
+struct IdentityOp { __host__ __device__ __forceinline__ int operator()(int n) const { return n; } };
+
 // bulk molecules of the current solute molecule (inbulk, src/mddf.jl:55-57; the solute itself is skipped in
 // an autocorrelation, :409) -- predicate of the ordered stream compaction
 struct BulkPred {
@@ -300,15 +339,20 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
               const u64 *__restrict__ rowmask, const float4 *__restrict__ qsorted, const int *__restrict__ qcell_start,
-              int nqcells, float4 *__restrict__ res, u64 *__restrict__ pair_evals) {
+              int nqcells, float4 *__restrict__ res, u64 *__restrict__ pair_evals, int *__restrict__ tile_queue) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int ntiles = qcell_start[nqcells];     // exclusive scan of the per-cell tile counts
     const float slack = 2e-3f;
     unsigned long long npairs = 0;
     __shared__ float4 stage[8][32];               // per warp: one chunk of solute atoms
     float4 *st = stage[threadIdx.x >> 5];
-    for (int tile = warp; tile < ntiles; tile += nwarps) {
+    // tiles differ widely in cost (distance to the solute): the resident warps pull them from a queue (zeroed with
+    // the frame's scalars) instead of owning a fixed share, and the grid is exactly one resident wave
+    while (true) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_queue, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
         float4 q = __ldg(&qsorted[(size_t)tile * 32 + lane]);
         const bool valid = __float_as_int(q.w) >= 0;
         {   // unused slots shadow the tile's first query (always present)

@@ -92,6 +92,11 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
             options = solute
         options = options or Options()
     assert isinstance(trajectory, Trajectory)
+    if feed not in ("auto", "native", "host"):
+        raise ValueError("feed must be 'auto', 'native' or 'host'")
+    native = feed == "native" or (feed == "auto" and isinstance(trajectory, NamdDCD))
+    if native and not isinstance(trajectory, NamdDCD):
+        raise ValueError("feed='native' needs a DCD trajectory")
     tmeta = trajectory_metadata(trajectory, options)
     R = new_result(trajectory, options, tmeta, frame_weights)
     rank, world = _dist_info()
@@ -101,11 +106,6 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
                  autocorrelation=R.autocorrelation, coordination_number_only=coordination_number_only, device=device,
                  path=path, **(_engine_kw or {}))
     todo = frames_to_compute(options, tmeta.lastframe_read, R.files[0].frame_weights)
-    if feed not in ("auto", "native", "host"):
-        raise ValueError("feed must be 'auto', 'native' or 'host'")
-    native = feed == "native" or (feed == "auto" and isinstance(trajectory, NamdDCD))
-    if native and not isinstance(trajectory, NamdDCD):
-        raise ValueError("feed='native' needs a DCD trajectory")
     if native:
         my = shard(todo, rank, world)
         dcd = DcdFile(trajectory.filename)

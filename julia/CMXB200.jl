@@ -113,4 +113,49 @@ function mddf_b200(trajectory::Trajectory, options::Options=Options();
     return finalresults!(R, options; coordination_number_only)   # unmodified reference normalisation
 end
 
+# ---- SURVEY 8(f1): the library's own DCD feed ------------------------------------------------------
+struct CmxDcdInfo
+    natoms::Int64; nframes::Int64; first_frame_offset::Int64; frame_bytes::Int64
+end
+
+"""
+    run_dcd!(h, trajectory::ComplexMixtures.NamdDCD, frames, weights; reader_threads=2)
+
+Replaces the whole `for iframe ...` loop above for DCD files: `cmx_run_dcd` preads the raw frame records
+into a pinned ring on reader threads, copies each raw frame to the device once and gathers the selected
+atoms there (the host-side gather of `nextframe!`, src/trajectory_formats/NamdDCD.jl:141-169, disappears).
+`frames` are 1-based frame numbers as in the reference; the Philox key stays the 1-based frame number.
+"""
+function run_dcd!(h::Ptr{Cvoid}, trajectory, frames::Vector{Int}, weights::Vector{Float64}; reader_threads::Integer=2)
+    dref = Ref{Ptr{Cvoid}}(C_NULL); info = Ref(CmxDcdInfo(0, 0, 0, 0))
+    rc = ccall((:cmx_dcd_open, libcmx), Int32, (Cstring, Ref{Ptr{Cvoid}}, Ref{CmxDcdInfo}), trajectory.filename, dref, info)
+    rc == 0 || error(unsafe_string(ccall((:cmx_dcd_last_error, libcmx), Cstring, ())))
+    sol = Int32.(trajectory.solute.indices); solv = Int32.(trajectory.solvent.indices)
+    fr0 = Int64.(frames .- 1)
+    try
+        GC.@preserve sol solv fr0 weights check(h, ccall((:cmx_run_dcd, libcmx), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Int64, Int32),
+            h, dref[], sol, solv, fr0, weights, length(fr0), reader_threads))
+    finally
+        ccall((:cmx_dcd_close, libcmx), Int32, (Ptr{Cvoid},), dref[])
+    end
+end
+
+# ---- SURVEY 8(f2): contributions / ResidueContributions count stage on the device ----------------------
+"""
+    reduce_groups(h, which, groups, nbins) -> Matrix{Float64}(nbins, length(groups))
+
+`which`: 0 solute_group_count, 1 solute_group_count_random, 2 solvent_group_count, 3 solvent_group_count_random;
+`groups[g]` = 1-based rows (atoms of the selection, or custom groups) summed into output column g -- the loop over
+`group_count[igroup]` of `contributions` (src/tools/contributions.jl:206-236) without reading the per-atom array back.
+"""
+function reduce_groups(h::Ptr{Cvoid}, which::Integer, groups::Vector{Vector{Int}}, nbins::Integer)
+    off = Int32[0; cumsum(length.(groups))]
+    rows = Int32.(reduce(vcat, groups; init=Int[]) .- 1)
+    out = zeros(nbins, length(groups))
+    GC.@preserve off rows out check(h, ccall((:cmx_reduce_groups, libcmx), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}), h, which, length(groups), off, rows, out))
+    return out
+end
+
 end # module

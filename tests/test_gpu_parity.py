@@ -570,7 +570,7 @@ def test_native_feed_errors_and_public_driver(tmp_path):
             assert np.array_equal(getattr(Rn, key), getattr(Rh, key)), (kw, key)
         assert Rn.volume.total == Rh.volume.total
     with pytest.raises(ValueError):
-        cm.mddf(cm.ArrayTrajectory(d["protein"], d["cells"], sol, sol), opts(), feed="native")
+        cm.mddf(cm.ArrayTrajectory(d["protein"], d["cells"], PROTEIN, PROTEIN), opts(bulk_range=(8.0, 10.0)), feed="native")
 
 
 @pytest.mark.parametrize("auto", [False, True])
