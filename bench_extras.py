@@ -67,6 +67,11 @@ def feed(args):
         else:
             assert all(np.array_equal(ref[k], c[k]) for k in ref), "native feed: counters depend on the reader thread count"
         f.close(); eng.close()
+    # where the fixed cost of a short run goes: create / first run (ring allocation) / finish / destroy
+    t0 = time.perf_counter(); eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=iref, autocorrelation=False); t1 = time.perf_counter()
+    f = DcdFile(path); eng.run_dcd(f, sol.indices, wat.indices, list(range(min(nf, 64))), n_reader_threads=2); t2 = time.perf_counter()
+    eng.finish(copy=False); t3 = time.perf_counter(); f.close(); eng.close(); t4 = time.perf_counter()
+    out["fixed_costs_ms"] = {"create": 1e3 * (t1 - t0), "run_64_frames_incl_ring_alloc": 1e3 * (t2 - t1), "finish": 1e3 * (t3 - t2), "destroy": 1e3 * (t4 - t3)}
     # host reader of this package -> staging slot (first `host_frames` frames only: it is the slow side)
     nh = min(nf, args.host_frames)
     o2 = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=10, seed=321, silent=True, lastframe=nh, irefatom=iref)

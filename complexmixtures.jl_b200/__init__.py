@@ -23,8 +23,8 @@ __all__ = ["Options", "AtomSelection", "SoluteGroup", "SolventGroup", "Trajector
            "cell_from_lengths_angles"]
 
 
-from .driver import coordination_number, mddf  # noqa: E402  (the CUDA library itself is loaded lazily)
+from .driver import coordination_number, mddf, mddf_many  # noqa: E402  (the CUDA library itself is loaded lazily)
 from . import engine, synthetic  # noqa: E402
 from .engine import Engine  # noqa: E402
 
-__all__ += ["mddf", "coordination_number", "Engine", "engine", "synthetic"]
+__all__ += ["mddf", "mddf_many", "coordination_number", "Engine", "engine", "synthetic"]

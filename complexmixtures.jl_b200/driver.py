@@ -70,7 +70,8 @@ def allreduce_counters(eng: Engine, volume_total: float, sum_weights: float):
 def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[AtomSelection] = None,
          options: Optional[Options] = None, *, trajectory_format: str = "", frame_weights=(),
          coordination_number_only: bool = False, low_memory: bool = False, device: Optional[int] = None,
-         path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None) -> Result:
+         path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None,
+         _engine_cache: Optional[dict] = None) -> Result:
     """mddf(trajectory_file, solute, solvent, options; ...) or mddf(trajectory, options; ...).
 
     ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
@@ -102,9 +103,17 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     rank, world = _dist_info()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
-    eng = Engine(solute=trajectory.solute, solvent=trajectory.solvent, options=options, irefatom=tmeta.irefatom,
-                 autocorrelation=R.autocorrelation, coordination_number_only=coordination_number_only, device=device,
-                 path=path, **(_engine_kw or {}))
+    # mddf_many: one engine (device state, streams, staging ring) serves every trajectory of the batch
+    key = (tmeta.irefatom, R.autocorrelation, coordination_number_only, device, path)
+    eng = None if _engine_cache is None else _engine_cache.get(key)
+    if eng is None:
+        eng = Engine(solute=trajectory.solute, solvent=trajectory.solvent, options=options, irefatom=tmeta.irefatom,
+                     autocorrelation=R.autocorrelation, coordination_number_only=coordination_number_only, device=device,
+                     path=path, **(_engine_kw or {}))
+        if _engine_cache is not None:
+            _engine_cache[key] = eng
+    else:
+        eng.reset()
     todo = frames_to_compute(options, tmeta.lastframe_read, R.files[0].frame_weights)
     if native:
         my = shard(todo, rank, world)
@@ -141,7 +150,8 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     else:
         c = eng.finish()
     R.engine_stats = eng.stats()
-    eng.close()
+    if _engine_cache is None:
+        eng.close()
     for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count",
               "solute_group_count_random", "solvent_group_count", "solvent_group_count_random"):
         setattr(R, k, c[k])
@@ -155,3 +165,23 @@ def coordination_number(trajectory, solute=None, solvent=None, options=None, **k
         raise ValueError("The keyword argument `coordination_number_only` is not valid for this function. "
                          "It is, by definition, set to `true` in this function.")
     return mddf(trajectory, solute, solvent, options, coordination_number_only=True, **kw)
+
+
+def mddf_many(trajectory_files, solute: AtomSelection, solvent: Optional[AtomSelection] = None,
+              options: Optional[Options] = None, *, frame_weights=None, **kw):
+    """The same analysis on several trajectories (or parts of one), the use case of ``merge``
+    (src/tools/merge.jl:1-9): returns ``(results, merge(results))``.  Unlike calling ``mddf`` in a loop, ONE
+    engine -- device buffers, streams, pinned staging ring -- serves the whole batch (``cmx_reset`` between
+    files), so short trajectories do not pay the create/destroy cost again."""
+    from .results import merge
+    options = options or Options()
+    cache: dict = {}
+    results = []
+    try:
+        for k, f in enumerate(trajectory_files):
+            fw = () if frame_weights is None else frame_weights[k]
+            results.append(mddf(f, solute, solvent, options, frame_weights=fw, _engine_cache=cache, **kw))
+    finally:
+        for eng in cache.values():
+            eng.close()
+    return results, merge(results)

@@ -628,3 +628,24 @@ def test_merge_of_two_halves_equals_reference_semantics():
     R = cm.merge([R1w, R2])
     assert np.isclose(R.md_count.sum(), 2 / 3) and np.isclose(R.solute_group_count.sum(), 2 / 3) and np.isclose(R.solvent_group_count.sum(), 2 / 3)
     assert R.volume.total == 27000.0
+
+
+def test_mddf_many_reuses_one_engine(tmp_path):
+    """mddf_many: several DCD files through ONE engine (cmx_reset between them) == separate mddf calls, and the
+    merged Result equals merge() of the parts (frame-weighted, src/tools/merge.jl)."""
+    from common import write_dcd
+    d = namd()
+    frames = np.concatenate([d["protein"], d["tmao"]], axis=1)
+    pa, pb = str(tmp_path / "a.dcd"), str(tmp_path / "b.dcd")
+    write_dcd(pa, frames[:2], d["cells"][:2]); write_dcd(pb, frames[2:], d["cells"][2:])
+    sol = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+    tm = cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14)
+    o = opts(bulk_range=(8.0, 10.0), n_random_samples=2)
+    parts, merged = cm.mddf_many([pa, pb], sol, tm, o)
+    Ra, Rb = cm.mddf(pa, sol, tm, o), cm.mddf(pb, sol, tm, o)
+    for got, want in zip(parts, (Ra, Rb)):
+        for key in ("md_count", "md_count_random", "solute_group_count", "rdf_count", "mddf", "kb"):
+            assert np.array_equal(getattr(got, key), getattr(want, key)), key
+    M = cm.merge([Ra, Rb])
+    assert merged.weights == [2 / 3, 1 / 3] and np.allclose(merged.md_count, M.md_count, rtol=0, atol=0)
+    assert np.allclose(merged.md_count, (2 * Ra.md_count + Rb.md_count) / 3, rtol=1e-15)
