@@ -62,8 +62,9 @@ struct FrameCtx {
     DevBuf<float4> d_qpos, d_qsorted, d_res;   // query atoms of the current phase: positions, tile order, results
     DevBuf<int> d_qcell_count, d_qcell_start;
     DevBuf<double> d_xexact;
-    DevBuf<unsigned short> d_edt_xy, d_edt_uxy;
-    DevBuf<float> d_lbd2, d_ubd2;
+    DevBuf<unsigned char> d_edt_x;
+    DevBuf<unsigned short> d_edt_xy;
+    DevBuf<float> d_lbd2;
     DevBuf<MdRec> d_list;
     DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
     DevBuf<u64> d_def_real, d_def_rand;
@@ -74,7 +75,7 @@ struct FrameCtx {
     int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
     void release() {
         d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release();
-        d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_xexact.release(); d_edt_uxy.release(); d_ubd2.release();
+        d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_xexact.release(); d_edt_x.release();
         d_edt_xy.release(); d_lbd2.release(); d_list.release(); d_worklist.release(); d_rand_worklist.release();
         d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_def_real_info.release(); d_def_rand_info.release(); d_scalars.release(); d_cub_tmp.release();
         if (h_scalars) cudaFreeHost(h_scalars);
@@ -128,7 +129,6 @@ struct cmx_handle {
     int num_sms = 148;
     int search_grid[2] = {148 * 5, 148 * 4};   // one resident wave of k_tile_search<false/true> (occupancy query at create)
     int search_blocks_env = 0;
-    bool use_ub = true;                        // initial search bound from the distance transform's upper bound
     cmx_feed *feed = nullptr;
 };
 
@@ -306,9 +306,9 @@ int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv,
         return h->num_sms * std::max(1, (per_sm + nfly - 1) / nfly);
     };
     if (pev) launch(h, k_tile_search<true>, dim3(grid_of(1)), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                    (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue, (const float *)(h->use_ub ? x.d_ubd2.p : nullptr));
+                    (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue);
     else launch(h, k_tile_search<false>, dim3(grid_of(0)), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue, (const float *)(h->use_ub ? x.d_ubd2.p : nullptr));
+                (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue);
     prof_end(h, pe);
     launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
            (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count, s0);
@@ -325,7 +325,7 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     CK(h->cur->d_cell_start.ensure(ncells + 1));
     // [8 per-frame scalars][cull-grid bitmap][row bitmap] share one buffer: one memset per solute molecule
     CK(h->cur->d_occ.ensure(4 + occ_words + ((size_t)g.ny * g.nz * g.rw)));
-    CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_edt_uxy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc)); CK(h->cur->d_ubd2.ensure(ncc));
+    CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
     size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
     u64 *occ_p = h->cur->d_occ.p + 4, *rowmask_p = occ_p + occ_words;
     size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
@@ -355,9 +355,8 @@ int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent
         }
         launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
                (const int *)h->cur->d_cell_start.p, occ_p, rowmask_p, h->cur->d_sorted.p);
-        launch(h, k_edt_xy, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)occ_p, h->cur->d_edt_xy.p, h->cur->d_edt_uxy.p);
-        launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->cur->d_edt_xy.p,
-               (const unsigned short *)h->cur->d_edt_uxy.p, h->cur->d_lbd2.p, h->cur->d_ubd2.p);
+        launch(h, k_edt_xy, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)occ_p, h->cur->d_edt_xy.p);
+        launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->cur->d_edt_xy.p, h->cur->d_lbd2.p);
         launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
                (const float *)h->cur->d_lbd2.p, h->cur->d_list.p, h->cur->d_worklist.p, sc + 0, sc + 5);
         if (h->stats.frames < 64 || (h->stats.frames & 15) == 0)   // host-side bound for the NEXT frames' cull window (monotone)
@@ -539,7 +538,6 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_tile_search<false>, 256, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_tile_search<true>, 256, 0));
         h->search_grid[0] = h->num_sms * std::max(1, b0); h->search_grid[1] = h->num_sms * std::max(1, b1);
-        if (const char *e = std::getenv("CMX_NO_UB")) h->use_ub = atoi(e) == 0;   // experiments only
         if (const char *e = std::getenv("CMX_SEARCH_BLOCKS_PER_SM")) h->search_blocks_env = std::max(1, atoi(e));   // experiments only
     }
     h->nbins = std::max(1, (int)std::ceil(c.cutoff / c.binstep));   // setbin(cutoff, binstep), src/results.jl:131

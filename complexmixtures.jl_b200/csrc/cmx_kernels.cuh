@@ -106,49 +106,34 @@ __device__ __forceinline__ int edt_x_of(const Geom &g, const u64 *__restrict__ o
 }
 
 // passes X and Y in one kernel: the X distance of the 2*dwin+1 rows of the window is recomputed from the row
-// bitmaps (a handful of bit operations each) instead of being written and re-read by a separate launch.
-// Besides the lower bound the same passes carry an UPPER bound of the distance to the nearest solute atom: an
-// occupied cell (ax,ay,az) cells away holds at least one atom, and every component of the separation of two points
-// in those cells is at most (a+1) cells:  ub^2 = cside^2 * min over occupied cells of (ax+1)^2+(ay+1)^2+(az+1)^2.
-#define CMX_EDT_NONE 0xffffu
-__global__ void k_edt_xy(Geom g, const u64 *__restrict__ occ_bits, unsigned short *__restrict__ exy,
-                         unsigned short *__restrict__ uxy) {
+// bitmaps (a handful of bit operations each) instead of being written and re-read by a separate launch
+__global__ void k_edt_xy(Geom g, const u64 *__restrict__ occ_bits, unsigned short *__restrict__ exy) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     int ncc = g.ncx * g.ncy * g.ncz;
     if (c >= ncc) return;
     int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
-    int D = g.dwin, best = 3 * D * D, ubest = CMX_EDT_NONE;
+    int D = g.dwin, best = 3 * D * D;
     for (int dy = -D; dy <= D; ++dy) {
         int ry = cy + dy;
         if (ry < 0 || ry >= g.ncy) continue;
-        int ex = edt_x_of(g, occ_bits, cz * g.ncy + ry, cx);
-        best = min(best, edt_f(ex) + edt_f(abs(dy)));
-        if (ex <= D) ubest = min(ubest, (ex + 1) * (ex + 1) + (abs(dy) + 1) * (abs(dy) + 1));
+        best = min(best, edt_f(edt_x_of(g, occ_bits, cz * g.ncy + ry, cx)) + edt_f(abs(dy)));
     }
     exy[c] = (unsigned short)best;
-    uxy[c] = (unsigned short)ubest;
 }
 
-__global__ void k_edt_z(Geom g, const unsigned short *__restrict__ exy, const unsigned short *__restrict__ uxy,
-                        float *__restrict__ lbd2, float *__restrict__ ubd2) {
+__global__ void k_edt_z(Geom g, const unsigned short *__restrict__ exy, float *__restrict__ lbd2) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     int ncc = g.ncx * g.ncy * g.ncz;
     if (c >= ncc) return;
     int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
-    int D = g.dwin, best = 3 * D * D, ubest = 0x7fffffff;
+    int D = g.dwin, best = 3 * D * D;
     for (int dz = -D; dz <= D; ++dz) {
         int rz = cz + dz;
         if (rz < 0 || rz >= g.ncz) continue;
-        int o = (rz * g.ncy + cy) * g.ncx + cx;
-        best = min(best, (int)exy[o] + edt_f(abs(dz)));
-        int u = uxy[o];
-        if (u != (int)CMX_EDT_NONE) ubest = min(ubest, u + (abs(dz) + 1) * (abs(dz) + 1));
+        best = min(best, (int)exy[(rz * g.ncy + cy) * g.ncx + cx] + edt_f(abs(dz)));
     }
     // anything at or beyond the window is "far": the window is sized so that D*cside exceeds every threshold
     lbd2[c] = best >= D * D ? CUDART_INF_F : (float)best * g.cside * g.cside;
-    // 1e-3 A covers the fp32 rounding of the cell assignment of points next to a cell face
-    float ub = sqrtf((float)ubest) * g.cside * 1.000001f + 1e-3f;
-    ubd2[c] = ubest == 0x7fffffff ? CUDART_INF_F : ub * ub;
 }
 
 __device__ __forceinline__ float cull_lb2(const Geom &g, const float *__restrict__ lbd2, float px, float py, float pz) {
@@ -354,8 +339,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
               const u64 *__restrict__ rowmask, const float4 *__restrict__ qsorted, const int *__restrict__ qcell_start,
-              int nqcells, float4 *__restrict__ res, u64 *__restrict__ pair_evals, int *__restrict__ tile_queue,
-              const float *__restrict__ ubd2) {
+              int nqcells, float4 *__restrict__ res, u64 *__restrict__ pair_evals, int *__restrict__ tile_queue) {
     const int lane = threadIdx.x & 31;
     const int ntiles = qcell_start[nqcells];     // exclusive scan of the per-cell tile counts
     const float slack = 2e-3f;
@@ -378,15 +362,7 @@ k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restri
         const float xmin = warp_minf(q.x), xmax = warp_maxf(q.x), ymin = warp_minf(q.y), ymax = warp_maxf(q.y),
                     zmin = warp_minf(q.z), zmax = warp_maxf(q.z);
         float b1 = CUDART_INF_F, b2 = CUDART_INF_F; int bi = -1;
-        // initial bound: the distance transform's upper bound of every lane's nearest-atom distance (+ the near-tie
-        // window), instead of the cutoff -- tiles close to the solute probe few rows and short x-spans from the start
-        float bound;
-        {
-            int ccx, ccy, ccz; coarse_cell_of(g, q.x, q.y, q.z, ccx, ccy, ccz);
-            float ub = ubd2 ? __ldg(&ubd2[(ccz * g.ncy + ccy) * g.ncx + ccx]) : CUDART_INF_F;
-            float mine0 = valid ? fminf(ub + g.tol_d2, g.search2) : 0.f;
-            bound = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mine0)));
-        }
+        float bound = g.search2;
         const float reach = sqrtf(bound) + slack;
         const int ry_lo = max((int)floorf((ymin - reach - g.gmin[1]) * g.inv_side), 0);
         const int ry_hi = min((int)floorf((ymax + reach - g.gmin[1]) * g.inv_side), g.ny - 1);
