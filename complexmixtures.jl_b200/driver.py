@@ -71,7 +71,7 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
          options: Optional[Options] = None, *, trajectory_format: str = "", frame_weights=(),
          coordination_number_only: bool = False, low_memory: bool = False, device: Optional[int] = None,
          path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None,
-         _engine_cache: Optional[dict] = None) -> Result:
+         _engine_cache: Optional[dict] = None, distributed: Optional[bool] = None) -> Result:
     """mddf(trajectory_file, solute, solvent, options; ...) or mddf(trajectory, options; ...).
 
     ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
@@ -100,7 +100,7 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
         raise ValueError("feed='native' needs a DCD trajectory")
     tmeta = trajectory_metadata(trajectory, options)
     R = new_result(trajectory, options, tmeta, frame_weights)
-    rank, world = _dist_info()
+    rank, world = (0, 1) if distributed is False else _dist_info()   # distributed=False: ignore an initialised process group
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
     # mddf_many: one engine (device state, streams, staging ring) serves every trajectory of the batch
