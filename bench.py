@@ -394,7 +394,7 @@ def main():
                 "config": {"workload": w["desc"], "frames_per_step": fps, "frames_per_step_total": fps * world, "scale": args.scale,
                            "n_random_samples": opt.n_random_samples, "bulk_range": [opt.dbulk, opt.cutoff], "nbins": eng.nbins,
                            "l2": f"distinct inputs per step = {fps * (xv[0].nbytes + (0 if w['auto'] else xs[0].nbytes)) / 1e6:.0f} MB (larger than the 126 MB L2; no flush needed)",
-                           "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps * world),
+                           "frames_in_flight": args.streams or 8, "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps * world),
                            "deferred_to_exact_per_frame": deferred},
                 "device_ms_per_step": 1e3 * t_dev / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
                 "host_submit_ms_per_step": host_submit_ms,
