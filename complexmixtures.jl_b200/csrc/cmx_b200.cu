@@ -6,6 +6,10 @@
 // frame-weight handling and the final counters (sum!, src/results.jl:629-649).
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <cctype>
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +34,33 @@ struct Slot {
     float *d_in = nullptr;
     cudaEvent_t h2d_done = nullptr, consumed = nullptr;
     bool in_flight = false;
+};
+
+// Pinned staging memory is read by the GPU's DMA engine for every frame: allocate it on the NUMA node the GPU hangs
+// off (sysfs numa_node of its PCI function), unless the caller already runs under a memory policy (numactl etc.).
+int gpu_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    for (char *p = bus; *p; ++p) *p = (char)std::tolower((unsigned char)*p);
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+struct NumaPrefer {
+    bool active = false;
+    explicit NumaPrefer(int node) {
+        if (node < 0 || node >= 1024) return;
+        int mode = -1;
+        if (syscall(SYS_get_mempolicy, &mode, nullptr, 0ul, nullptr, 0ul) != 0 || mode != 0 /*MPOL_DEFAULT*/) return;
+        unsigned long mask[16] = {0};
+        mask[node / 64] |= 1ul << (node % 64);
+        active = syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, mask, 1025ul) == 0;
+    }
+    ~NumaPrefer() { if (active) syscall(SYS_set_mempolicy, 0 /*MPOL_DEFAULT*/, nullptr, 0ul); }
 };
 
 template <class T>
@@ -130,6 +161,7 @@ struct cmx_handle {
     int search_grid[2] = {148 * 5, 148 * 4};   // one resident wave of k_tile_search<false/true> (occupancy query at create)
     int search_blocks_env = 0;
     cmx_feed *feed = nullptr;
+    int numa_node = -1;                        // NUMA node of the GPU (-1 unknown): pinned staging memory is placed there
 };
 
 namespace {
@@ -579,6 +611,8 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_last));
     int slots = c.ring_slots > 0 ? c.ring_slots : 3;
     h->ring.resize(slots);
+    h->numa_node = gpu_numa_node(c.device);
+    NumaPrefer numa_guard(h->numa_node);
     for (auto &s : h->ring) {
         CK(cudaHostAlloc(&s.h_in, sizeof(float) * h->in_floats, cudaHostAllocDefault));
         CK(cudaMalloc(&s.d_in, sizeof(float) * h->in_floats));

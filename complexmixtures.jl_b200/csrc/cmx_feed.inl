@@ -126,6 +126,7 @@ int feed_prepare(cmx_handle *h, const cmx_dcd *d, const int32_t *sol_idx, const 
             if (s.consumed) cudaEventDestroy(s.consumed);
         }
         F.slots.assign((size_t)nslots, FeedSlot());
+        NumaPrefer numa_guard(h->numa_node);
         for (auto &s : F.slots) {
             CK(cudaHostAlloc(&s.h_raw, fb, cudaHostAllocDefault));
             CK(cudaMalloc(&s.d_raw, fb));
