@@ -292,6 +292,7 @@ typedef struct {
     int *start;    /* [ncells+1] */
     int *atoms;    /* [ny] atom indices sorted by cell */
     int *cellof;   /* scratch [ny] */
+    double *wpos;  /* [3*ny] positions wrapped into the primary cell, in cell-sorted order (pre-test only) */
     int ny;
 } orc_clist;
 
@@ -300,8 +301,16 @@ static void clist_alloc(orc_clist *cl, int ny) {
     cl->ny = ny;
     cl->atoms = (int *)malloc(sizeof(int) * (size_t)(ny > 0 ? ny : 1));
     cl->cellof = (int *)malloc(sizeof(int) * (size_t)(ny > 0 ? ny : 1));
+    cl->wpos = (double *)malloc(sizeof(double) * 3 * (size_t)(ny > 0 ? ny : 1));
 }
-static void clist_free(orc_clist *cl) { free(cl->start); free(cl->atoms); free(cl->cellof); }
+static void clist_free(orc_clist *cl) { free(cl->start); free(cl->atoms); free(cl->cellof); free(cl->wpos); }
+
+static void cart_of_frac(const orc_cell *c, const double s[3], double r[3]) {
+    const double *m = c->m;
+    r[0] = (m[0] * s[0] + m[3] * s[1]) + m[6] * s[2];
+    r[1] = (m[1] * s[0] + m[4] * s[1]) + m[7] * s[2];
+    r[2] = (m[2] * s[0] + m[5] * s[1]) + m[8] * s[2];
+}
 
 static void frac_of(const orc_cell *c, const double *r, double s[3]) {
     if (c->ortho) { s[0] = r[0] / c->m[0]; s[1] = r[1] / c->m[4]; s[2] = r[2] / c->m[8]; }
@@ -314,9 +323,12 @@ static void frac_of(const orc_cell *c, const double *r, double s[3]) {
     for (int k = 0; k < 3; ++k) { s[k] -= floor(s[k]); if (s[k] >= 1.0) s[k] = 0.0; }
 }
 
+/* cells are cut/ORC_LCELL wide (CellListMap's `lcell`, src/minimum_distances.jl:170): with 2 the 5x5x5 block of
+ * neighbour cells holds ~58 % of the candidates of the 3x3x3 block of cut-wide cells */
+#define ORC_LCELL 2
 static void clist_build(orc_clist *cl, const orc_cell *c, const double *y, double cut) {
     int n[3];
-    for (int k = 0; k < 3; ++k) { n[k] = (int)floor(c->w[k] / cut); if (n[k] < 1) n[k] = 1; if (n[k] > 256) n[k] = 256; }
+    for (int k = 0; k < 3; ++k) { n[k] = (int)floor(c->w[k] * ORC_LCELL / cut); if (n[k] < 1) n[k] = 1; if (n[k] > 256) n[k] = 256; }
     int ncells = n[0] * n[1] * n[2];
     if (ncells != cl->ncells) { free(cl->start); cl->start = (int *)malloc(sizeof(int) * (size_t)(ncells + 1)); }
     cl->n[0] = n[0]; cl->n[1] = n[1]; cl->n[2] = n[2]; cl->ncells = ncells;
@@ -330,35 +342,76 @@ static void clist_build(orc_clist *cl, const orc_cell *c, const double *y, doubl
     }
     for (int k = 0; k < ncells; ++k) cl->start[k + 1] += cl->start[k];
     int *fill = (int *)calloc((size_t)ncells, sizeof(int));
-    for (int j = 0; j < cl->ny; ++j) { int id = cl->cellof[j]; cl->atoms[cl->start[id] + fill[id]++] = j; }
+    for (int j = 0; j < cl->ny; ++j) {
+        int id = cl->cellof[j], slot = cl->start[id] + fill[id]++;
+        cl->atoms[slot] = j;
+        double sj[3]; frac_of(c, y + 3 * j, sj);
+        cart_of_frac(c, sj, cl->wpos + 3 * (size_t)slot);
+    }
     free(fill);
 }
 
-static int nb_range(int n, int *lo, int *hi) { /* distinct neighbour offsets along one axis */
-    if (n == 1) { *lo = 0; *hi = 0; } else if (n == 2) { *lo = 0; *hi = 1; } else { *lo = -1; *hi = 1; }
-    return *hi - *lo + 1;
+/* distinct cells within ORC_LCELL cells of cell `c0` along an axis with n cells (periodic) */
+static int nb_cells(int n, int c0, int out[2 * ORC_LCELL + 1]) {
+    if (n <= 2 * ORC_LCELL + 1) { for (int k = 0; k < n; ++k) out[k] = k; return n; }
+    for (int d = -ORC_LCELL; d <= ORC_LCELL; ++d) out[d + ORC_LCELL] = (c0 + d + n) % n;
+    return 2 * ORC_LCELL + 1;
 }
 
+/* Pair search of one solute molecule.  Candidates come from the (2*ORC_LCELL+1)^3 neighbour cells; each is first
+ * tested on wrapped coordinates with the periodic shift of its cell (three subtractions, no rounding calls), and
+ * only the pairs that pass (with a relative margin far above the rounding of that test) are evaluated with
+ * dist_pbc on the ORIGINAL coordinates -- the arithmetic every counted distance goes through.  A pair within
+ * the cutoff always lies, at its minimum image, in one of those cells (cell width >= cut/ORC_LCELL in every
+ * perpendicular direction), so the pre-test never loses one. */
 static int64_t md_clist(const orc_config *cfg, const orc_cell *c, const orc_clist *cl, const double *x,
                         const double *y, int isolute, orc_md *list) {
-    double cut = eff_cutoff(cfg);
+    const double cut = eff_cutoff(cfg);
+    const double cut2m = cut * cut * (1.0 + 1e-9);
     int64_t npairs = 0;
     for (int m = 0; m < cfg->nmols_solvent; ++m) list[m] = MD_ZERO;
     const int *n = cl->n;
-    int lo[3], hi[3];
-    for (int k = 0; k < 3; ++k) nb_range(n[k], &lo[k], &hi[k]);
+    const int L = ORC_LCELL;
+    const int shifted = n[0] > 2 * L + 1 && n[1] > 2 * L + 1 && n[2] > 2 * L + 1;
     for (int i = 0; i < cfg->napm_solute; ++i) {
-        double s[3]; frac_of(c, x + 3 * i, s);
+        const double *xi = x + 3 * i;
+        double s[3]; frac_of(c, xi, s);
         int cx = (int)(s[0] * n[0]), cy = (int)(s[1] * n[1]), cz = (int)(s[2] * n[2]);
         if (cx >= n[0]) cx = n[0] - 1; if (cy >= n[1]) cy = n[1] - 1; if (cz >= n[2]) cz = n[2] - 1;
-        for (int dz = lo[2]; dz <= hi[2]; ++dz)
-            for (int dy = lo[1]; dy <= hi[1]; ++dy)
-                for (int dx = lo[0]; dx <= hi[0]; ++dx) {
-                    int ex = (cx + dx + n[0]) % n[0], ey = (cy + dy + n[1]) % n[1], ez = (cz + dz + n[2]) % n[2];
-                    int id = (ez * n[1] + ey) * n[0] + ex;
-                    for (int p = cl->start[id]; p < cl->start[id + 1]; ++p) {
-                        int j = cl->atoms[p];
-                        double d = dist_pbc(c, x + 3 * i, y + 3 * j);
+        if (!shifted) {   /* small grids: every cell along a short axis, exact arithmetic for every candidate */
+            int ex[2 * ORC_LCELL + 1], ey[2 * ORC_LCELL + 1], ez[2 * ORC_LCELL + 1];
+            const int nx = nb_cells(n[0], cx, ex), ny = nb_cells(n[1], cy, ey), nz = nb_cells(n[2], cz, ez);
+            for (int kz = 0; kz < nz; ++kz)
+                for (int ky = 0; ky < ny; ++ky)
+                    for (int kx = 0; kx < nx; ++kx) {
+                        int id = (ez[kz] * n[1] + ey[ky]) * n[0] + ex[kx];
+                        for (int p = cl->start[id]; p < cl->start[id + 1]; ++p) {
+                            int j = cl->atoms[p];
+                            double d = dist_pbc(c, xi, y + 3 * j);
+                            if (d <= cut) { update_list(cfg, list, i, j, d, isolute); ++npairs; }
+                        }
+                    }
+            continue;
+        }
+        double xw[3]; cart_of_frac(c, s, xw);
+        for (int dz = -L; dz <= L; ++dz)
+            for (int dy = -L; dy <= L; ++dy)
+                for (int dx = -L; dx <= L; ++dx) {
+                    int rx = cx + dx, ry = cy + dy, rz = cz + dz;
+                    int kx = rx < 0 ? -1 : (rx >= n[0] ? 1 : 0), ky = ry < 0 ? -1 : (ry >= n[1] ? 1 : 0), kz = rz < 0 ? -1 : (rz >= n[2] ? 1 : 0);
+                    int id = ((rz - kz * n[2]) * n[1] + (ry - ky * n[1])) * n[0] + (rx - kx * n[0]);
+                    /* the neighbour cell's atoms sit at wpos + kx*a + ky*b + kz*c: move the solute atom the other way */
+                    const double *m = c->m;
+                    const double px = xw[0] - (kx * m[0] + ky * m[3] + kz * m[6]);
+                    const double py = xw[1] - (kx * m[1] + ky * m[4] + kz * m[7]);
+                    const double pz = xw[2] - (kx * m[2] + ky * m[5] + kz * m[8]);
+                    const double *w = cl->wpos + 3 * (size_t)cl->start[id];
+                    const int cnt = cl->start[id + 1] - cl->start[id];
+                    for (int q = 0; q < cnt; ++q) {
+                        double ax = w[3 * q] - px, ay = w[3 * q + 1] - py, az = w[3 * q + 2] - pz;
+                        if (ax * ax + ay * ay + az * az > cut2m) continue;
+                        int j = cl->atoms[cl->start[id] + q];
+                        double d = dist_pbc(c, xi, y + 3 * j);
                         if (d <= cut) { update_list(cfg, list, i, j, d, isolute); ++npairs; }
                     }
                 }

@@ -223,3 +223,28 @@ def test_multithreaded_run_frames_equals_serial():
         res.append(o.counters())
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k]) if k != "volume_total" else np.isclose(res[0][k], res[1][k])
+
+
+@pytest.mark.parametrize("triclinic", [False, True])
+@pytest.mark.parametrize("bulk_range", [(5.0, 7.0), (12.0, 16.0), (15.0, 20.0)])
+def test_cell_list_paths_equal_brute_force(triclinic, bulk_range):
+    """the CPU baseline's cell list (cells of cut/2, wrapped-coordinate pre-test with per-cell periodic shifts; plain
+    27..125-cell scan when an axis has <= 5 cells) visits exactly the pairs of the brute-force search: identical
+    lists and counters, unwrapped coordinates, several molecules of solute (random phase included)."""
+    from cmx_b200 import synthetic as syn
+    cell = np.array([[46.0, 9.0, 6.0], [0.0, 44.0, 8.0], [0.0, 0.0, 43.0]]) if triclinic else np.diag([44.0, 47.0, 42.0])
+    s = syn.make_system("t", cell=cell, solute_atoms=150, solvents=[("water", "water", 250), ("co", "urea", 30)], seed=9)
+    x, cell = s.frame(2)                              # frame(k) leaves the molecules unwrapped by up to +-2 cells
+    sol, co, wat = s.selections["solute"], s.selections["co"], s.selections["water"]
+    opt = cm.Options(bulk_range=bulk_range, n_random_samples=2, silent=True, seed=7)
+    for solute, solvent, auto in ((sol, wat, False), (co, wat, False), (co, co, True)):
+        p = Problem(solute, solvent, opt, [x[solute.indices - 1]], None if auto else [x[solvent.indices - 1]], cell, autocorrelation=auto)
+        a, la = p.oracle(use_clist=False, want_lists=True)
+        b, lb = p.oracle(use_clist=True, want_lists=True)
+        for k in range(len(la[0][0])):
+            assert np.array_equal(la[0][0][k], lb[0][0][k])
+        for k in range(len(la[0][1])):
+            assert np.array_equal(la[0][1][k], lb[0][1][k])
+        ca, cb = a.counters(), b.counters()
+        assert all(np.array_equal(ca[key], cb[key]) for key in ca if key != "volume_total")
+        assert ca["md_count"].sum() > 0
