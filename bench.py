@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--n-random-samples", type=int, default=10)
     ap.add_argument("--group-lanes", type=int, default=0)
     ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--no-hbm-kernel", action="store_true",
+                    help="skip the extra measurement of the HBM-bound kernel of the path's tail (cmx_reduce_groups, 6 GB)")
     return ap.parse_args()
 
 
@@ -386,21 +388,42 @@ def main():
                "sample": f"{nfc} frames of the same workload, oracle/cmx_oracle.c cell-list path, {ncores} OpenMP threads, frame-parallel",
                "counts_equal_device": bool(ok)}
 
+    # ---- the one HBM-bound kernel next to the path (rank 0, N=1): per-residue sums of a per-atom contribution array of
+    # C5's shape (1e6 rows x 750 bins x 8 B = 6 GB), cmx_reduce_groups; reported beside the dominant kernel's roofline
+    hbm_kernel = None
+    nbins = eng.nbins
+    if rank == 0 and world == 1 and not args.no_hbm_kernel and args.scale == 1.0:
+        eng.close()
+        eng = None
+        try:
+            import bench_extras
+            r = bench_extras.reduce_measure(1000000, repeat=2, check=False, device=local_rank)
+            k = r["residues_of_16_rows"]
+            hbm_kernel = {"kernel": r["kernel"], "bound": "hbm", "achieved": k["achieved_GBps"], "peak": r["peak_GBps"], "unit": "GB/s",
+                          "frac": k["frac_of_hbm_peak"], "kernel_ms_per_launch": k["kernel_ms"], "algorithmic_bytes_per_launch": r["algorithmic_bytes"],
+                          "workload": "62 500 groups of 16 rows of a 1e6 x 750 uint64 per-atom contribution array (C5 shape)",
+                          "d2h_bytes": k["d2h_bytes"], "traffic": (ncu_traffic("reduce_rows_500k", "traffic") or 0) * 2 or None,
+                          "traffic_note": "ncu --set full capture at 500 000 rows (profiles/r01b_reduce_rows_ncu_full.txt), scaled x2"}
+        except Exception as e:   # an extra: never fails the bench line
+            hbm_kernel = {"error": str(e)[:200]}
+
     if rank == 0:
         line = {"metric": "frames/sec of full mddf (real + random phases + counters)", "value": value, "unit": "frames/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_used / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search + f64 finalisation",
                 "data": "synthetic",
                 "config": {"workload": w["desc"], "frames_per_step": fps, "frames_per_step_total": fps * world, "scale": args.scale,
-                           "n_random_samples": opt.n_random_samples, "bulk_range": [opt.dbulk, opt.cutoff], "nbins": eng.nbins,
+                           "n_random_samples": opt.n_random_samples, "bulk_range": [opt.dbulk, opt.cutoff], "nbins": nbins,
                            "l2": f"distinct inputs per step = {fps * (xv[0].nbytes + (0 if w['auto'] else xs[0].nbytes)) / 1e6:.0f} MB (larger than the 126 MB L2; no flush needed)",
                            "frames_in_flight": args.streams or 8, "allreduce_per_step": world > 1, "hits_per_frame": hits / max(1, fps * args.steps * world),
                            "deferred_to_exact_per_frame": deferred},
                 "device_ms_per_step": 1e3 * t_dev / args.steps, "wall_ms_per_step": 1e3 * wall / args.steps,
                 "host_submit_ms_per_step": host_submit_ms,
-                "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clk.summary(), "e2e": e2e, "roofline": roof, "roofline_hbm_kernel": hbm_kernel,
+                "cpu_baseline": cpu}
         print(json.dumps(line))
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

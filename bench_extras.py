@@ -90,10 +90,12 @@ def feed(args):
     print(json.dumps(out))
 
 
-def reduce(args):
+def reduce_measure(nrows=1000000, repeat=3, check=True, device=0):
+    """cmx_reduce_groups over a per-atom solute_group_count array of `nrows` rows x 750 bins (C5's shape for 1e6 rows):
+    kernel time from CUDA events (option "profile") -> achieved GB/s against the measured HBM peak."""
     import cmx_b200 as cm
     from cmx_b200.engine import Engine
-    nrows, nsolv = args.rows, 100000
+    nsolv = 100000
     sol = cm.AtomSelection(np.arange(1, nrows + 1), nmols=1)
     wat = cm.AtomSelection(np.arange(nrows + 1, nrows + 1 + 3 * nsolv), natomspermol=3)
     opt = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=2, seed=321, silent=True)
@@ -102,30 +104,38 @@ def reduce(args):
     xs = (rng.uniform(0, 1, size=(nrows, 3)) * np.array([400.0, 400.0, 50.0]) + np.array([0, 0, 130.0])).astype(np.float32)
     ctr = rng.uniform(0, 1, size=(nsolv, 1, 3)) * np.array([400.0, 400.0, 312.5])
     xv = (ctr + rng.normal(0, 0.5, size=(nsolv, 3, 3))).reshape(-1, 3).astype(np.float32)
-    eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=1, autocorrelation=False, n_streams=2)
-    eng.set_option("profile", 1)
-    for k in range(2):
-        eng.submit_arrays(xs, xv, cell, frame_index=k + 1)
-    eng.sync()
-    nb = eng.nbins
-    per = 16
-    groups = [np.arange(g * per, min((g + 1) * per, nrows)) for g in range((nrows + per - 1) // per)]
-    peak, src = hbm_peak()
-    res = {"what": "reduce", "rows": nrows, "nbins": nb, "algorithmic_bytes": nrows * nb * 8, "peak_GBps": peak, "peak_source": src}
-    for name, gs in (("residues_of_16_rows", groups), ("one_group_of_all_rows", [np.arange(nrows)])):
-        best = 1e30
-        for _ in range(args.repeat):
-            got = eng.reduce_groups("solute_group_count", gs)
-            best = min(best, eng.stats()["gpu_ms_reduce"])
-        res[name] = {"n_groups": len(gs), "kernel_ms": best, "achieved_GBps": nrows * nb * 8 / (best * 1e-3) / 1e9,
-                     "frac_of_hbm_peak": nrows * nb * 8 / (best * 1e-3) / 1e9 / peak, "d2h_bytes": int(got.nbytes)}
-    full = eng.finish(copy=False)
-    want = full["solute_group_count"].reshape(len(groups), per, nb).sum(axis=1) if nrows % per == 0 else None
-    got = eng.reduce_groups("solute_group_count", groups)
-    res["equals_host_sum_of_rows"] = bool(want is None or np.array_equal(got, want))
-    res["hits"] = float(full["md_count"].sum())
-    eng.close()
-    print(json.dumps(res))
+    eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=1, autocorrelation=False, n_streams=2, device=device)
+    try:
+        eng.set_option("profile", 1)
+        for k in range(2):
+            eng.submit_arrays(xs, xv, cell, frame_index=k + 1)
+        eng.sync()
+        nb = eng.nbins
+        per = 16
+        groups = [np.arange(g * per, min((g + 1) * per, nrows)) for g in range((nrows + per - 1) // per)]
+        peak, src = hbm_peak()
+        res = {"what": "reduce", "kernel": "k_reduce_rows (cmx_reduce_groups)", "rows": nrows, "nbins": nb,
+               "algorithmic_bytes": nrows * nb * 8, "peak_GBps": peak, "peak_source": src}
+        for name, gs in (("residues_of_16_rows", groups), ("one_group_of_all_rows", [np.arange(nrows)])):
+            best = 1e30
+            for _ in range(repeat):
+                got = eng.reduce_groups("solute_group_count", gs)
+                best = min(best, eng.stats()["gpu_ms_reduce"])
+            res[name] = {"n_groups": len(gs), "kernel_ms": best, "achieved_GBps": nrows * nb * 8 / (best * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": nrows * nb * 8 / (best * 1e-3) / 1e9 / peak, "d2h_bytes": int(got.nbytes)}
+        if check:
+            full = eng.finish(copy=False)
+            want = full["solute_group_count"].reshape(len(groups), per, nb).sum(axis=1) if nrows % per == 0 else None
+            got = eng.reduce_groups("solute_group_count", groups)
+            res["equals_host_sum_of_rows"] = bool(want is None or np.array_equal(got, want))
+            res["hits"] = float(full["md_count"].sum())
+    finally:
+        eng.close()
+    return res
+
+
+def reduce(args):
+    print(json.dumps(reduce_measure(args.rows, args.repeat)))
 
 
 if __name__ == "__main__":
