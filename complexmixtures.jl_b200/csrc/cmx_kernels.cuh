@@ -267,6 +267,7 @@ k_scan_small(const int *__restrict__ in, int *__restrict__ out, int n, Op op) {
     __syncthreads();
     for (int base = 0; base < n; base += 4 * CMX_SCAN_THREADS) {
         const int i0 = base + 4 * threadIdx.x;
+        const int carry = carry_s;     // stable here: written between the two barriers below, read again only after the third
         int v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? op(in[i0 + k]) : 0;
@@ -276,13 +277,12 @@ k_scan_small(const int *__restrict__ in, int *__restrict__ out, int n, Op op) {
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         if (lane == 31) warp_sums[wid] = incl;
         __syncthreads();
-        const int carry = carry_s;
         if (wid == 0) {
             int ws = warp_sums[lane], wi = ws;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
             warp_sums[lane] = wi - ws;             // exclusive prefix of the warp totals
-            if (lane == 31) carry_s = carry + wi;  // read by everyone only after the next barrier
+            if (lane == 31) carry_s = carry + wi;  // every thread took its copy of the old value before the barrier above
         }
         __syncthreads();
         int run = carry + warp_sums[wid] + (incl - mine);
