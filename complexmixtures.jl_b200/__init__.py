@@ -12,12 +12,12 @@ module name ``cmx_b200``.  Layout:
 """
 from .options import Options
 from .selection import AtomSelection, SoluteGroup, SolventGroup
-from .trajectory import (ArrayTrajectory, NamdDCD, PDBTraj, Trajectory, make_trajectory,
+from .trajectory import (ArrayTrajectory, NamdDCD, PDBTraj, XTCTraj, Trajectory, make_trajectory,
                          trajectory_metadata, cell_from_lengths_angles)
 from .results import (Result, finalresults, load, merge, save, setbin, shellradius, sphericalshellvolume)
 from .contributions import contributions, coordination_number_of
 
-__all__ = ["Options", "AtomSelection", "SoluteGroup", "SolventGroup", "Trajectory", "NamdDCD", "PDBTraj",
+__all__ = ["Options", "AtomSelection", "SoluteGroup", "SolventGroup", "Trajectory", "NamdDCD", "PDBTraj", "XTCTraj",
            "ArrayTrajectory", "make_trajectory", "trajectory_metadata", "Result", "finalresults", "load", "merge", "save",
            "setbin", "shellradius", "sphericalshellvolume", "contributions", "coordination_number_of",
            "cell_from_lengths_angles"]

@@ -888,3 +888,4 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
 }  // extern "C"
 
 #include "cmx_feed.inl"
+#include "cmx_xtc.inl"

@@ -14,6 +14,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -72,13 +73,33 @@ __global__ void k_gather_dcd(const unsigned char *__restrict__ raw, long long na
     out[3 * (size_t)t] = __ldg(&X[a]); out[3 * (size_t)t + 1] = __ldg(&Y[a]); out[3 * (size_t)t + 2] = __ldg(&Z[a]);
 }
 
+// same gather for a raw frame that already is fp32 xyz triplets (decoded XTC)
+__global__ void k_gather_xyz(const float *__restrict__ raw, const int *__restrict__ idx, int n, float *__restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t a = (size_t)idx[t];
+    out[3 * (size_t)t] = __ldg(&raw[3 * a]); out[3 * (size_t)t + 1] = __ldg(&raw[3 * a + 1]); out[3 * (size_t)t + 2] = __ldg(&raw[3 * a + 2]);
+}
+
 }  // namespace
+
+// What the feed loop needs from a trajectory format: the size of one raw frame in the ring, its layout on the device
+// (0 = DCD records, 1 = fp32 xyz triplets in Angstrom) and a thread-safe "produce raw frame `frame` in `dst`" that also
+// yields the unit cell.
+struct FeedSource {
+    const char *what = "";
+    int64_t natoms = 0, nframes = 0;
+    size_t slot_bytes = 0;
+    int layout = 0;
+    std::function<bool(int64_t frame, unsigned char *dst, double cell[9], std::string &err)> fill;
+};
 
 struct FeedSlot {
     unsigned char *h_raw = nullptr, *d_raw = nullptr;
     float *d_xyz = nullptr;
     cudaEvent_t h2d_done = nullptr, gathered = nullptr, consumed = nullptr;
     int64_t filled = -1, h2d_issued = -1;
+    double cell[9] = {0};
     bool used = false;
 };
 
@@ -111,10 +132,10 @@ void feed_destroy(cmx_handle *h) {
     if (h->feed) { h->feed->release(); delete h->feed; h->feed = nullptr; }
 }
 
-int feed_prepare(cmx_handle *h, const cmx_dcd *d, const int32_t *sol_idx, const int32_t *solv_idx, int nslots) {
+int feed_prepare(cmx_handle *h, int64_t natoms_file, size_t slot_bytes, const int32_t *sol_idx, const int32_t *solv_idx, int nslots) {
     if (!h->feed) h->feed = new cmx_feed();
     cmx_feed &F = *h->feed;
-    const size_t fb = (size_t)d->info.frame_bytes;
+    const size_t fb = slot_bytes;
     if (F.frame_bytes != fb || (int)F.slots.size() != nslots) {
         { int rc = sync_all(h); if (rc) return rc; }
         for (auto &s : F.slots) {
@@ -145,7 +166,7 @@ int feed_prepare(cmx_handle *h, const cmx_dcd *d, const int32_t *sol_idx, const 
     for (size_t k = 0; k < ns; ++k) idx[k] = sol_idx[k] - 1;
     for (size_t k = 0; k < nv; ++k) idx[ns + k] = solv_idx[k] - 1;
     for (int32_t v : idx)
-        if (v < 0 || (int64_t)v >= d->info.natoms) return fail(h, CMX_ERR_ARG, "cmx_run_dcd: selection index outside the atoms of the file");
+        if (v < 0 || (int64_t)v >= natoms_file) return fail(h, CMX_ERR_ARG, "selection index outside the atoms of the file");
     if (idx != F.idx_host) {
         { int rc = sync_all(h); if (rc) return rc; }
         if (F.d_idx) { CK(cudaFree(F.d_idx)); F.d_idx = nullptr; }
@@ -259,33 +280,31 @@ int32_t cmx_dcd_read_frame(cmx_dcd *d, int64_t iframe, float *x, float *y, float
     return CMX_OK;
 }
 
-int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, const int32_t *solvent_indices,
+static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_indices, const int32_t *solvent_indices,
                     const int64_t *frames, const double *weights, int64_t nframes, int32_t n_reader_threads) {
-    if (!h) return CMX_ERR_ARG;
-    if (!d || !solvent_indices || (!frames && nframes > 0) || nframes < 0) return fail(h, CMX_ERR_ARG, "cmx_run_dcd: null argument");
-    if (!h->cfg.autocorrelation && !solute_indices) return fail(h, CMX_ERR_ARG, "cmx_run_dcd: null solute indices");
-    if (h->acquired >= 0) return fail(h, CMX_ERR_STATE, "cmx_run_dcd: a staging slot is acquired and not submitted");
+    if (!solvent_indices || (!frames && nframes > 0) || nframes < 0) return fail(h, CMX_ERR_ARG, std::string(src.what) + ": null argument");
+    if (!h->cfg.autocorrelation && !solute_indices) return fail(h, CMX_ERR_ARG, std::string(src.what) + ": null solute indices");
+    if (h->acquired >= 0) return fail(h, CMX_ERR_STATE, std::string(src.what) + ": a staging slot is acquired and not submitted");
     for (int64_t k = 0; k < nframes; ++k) {
-        if (frames[k] < 0 || frames[k] >= d->info.nframes) return fail(h, CMX_ERR_ARG, "cmx_run_dcd: frame number outside the file");
-        if (weights && !(weights[k] > 0)) return fail(h, CMX_ERR_ARG, "cmx_run_dcd: frame weights must be positive (skip zero-weight frames)");
+        if (frames[k] < 0 || frames[k] >= src.nframes) return fail(h, CMX_ERR_ARG, std::string(src.what) + ": frame number outside the file");
+        if (weights && !(weights[k] > 0)) return fail(h, CMX_ERR_ARG, std::string(src.what) + ": frame weights must be positive (skip zero-weight frames)");
     }
     if (nframes == 0) return CMX_OK;
     CK(cudaSetDevice(h->device));
     const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_reader_threads > 0 ? n_reader_threads : 2, 16), nframes));
     // ring slots: every compute stream needs a frame in flight and one being staged behind it (a slot is busy from the
-    // pread until its frame's kernels have finished), bounded to ~4 GB of pinned memory
+    // read until its frame's kernels have finished), bounded to ~4 GB of pinned memory
     const int nctx = h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size();
-    const int64_t cap = std::max<int64_t>(3, (int64_t)(4.0e9 / (double)d->info.frame_bytes));
+    const int64_t cap = std::max<int64_t>(3, (int64_t)(4.0e9 / (double)src.slot_bytes));
     const int S = (int)std::min<int64_t>(std::max(2 * nctx + 2, T + 2), cap);
-    { int rc = feed_prepare(h, d, solute_indices, solvent_indices, S); if (rc) return rc; }
+    { int rc = feed_prepare(h, src.natoms, src.slot_bytes, solute_indices, solvent_indices, S); if (rc) return rc; }
     cmx_feed &F = *h->feed;
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<bool> abort_flag{false};
     std::string io_error;
     const int device = h->device;
-    const int fd = d->fd;
-    const int64_t first = d->info.first_frame_offset, fb = d->info.frame_bytes;
+    const size_t fb = src.slot_bytes;
     auto reader = [&](int t) {
         cudaSetDevice(device);
         for (int64_t k = t; k < nframes; k += T) {
@@ -300,9 +319,10 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
                 io_error = "cudaEventSynchronize failed in the reader thread"; abort_flag = true; cv.notify_all();
                 return;
             }
-            bool ok = pread_all(fd, s.h_raw, (size_t)fb, (off_t)(first + frames[k] * fb));
+            std::string err;
+            bool ok = src.fill(frames[k], s.h_raw, s.cell, err);
             std::lock_guard<std::mutex> lk(mu);
-            if (!ok) { io_error = "short read in DCD frame " + std::to_string((long long)frames[k]); abort_flag = true; }
+            if (!ok) { if (!abort_flag.load()) io_error = err; abort_flag = true; }
             else s.filled = k;
             cv.notify_all();
             if (!ok) return;
@@ -319,14 +339,13 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
             cv.wait(lk, [&] { return abort_flag.load() || s.filled == k; });
             if (abort_flag.load()) { rc = fail(h, CMX_ERR_IO, io_error); break; }
         }
-        double u[6], cell[9];
-        std::memcpy(u, s.h_raw + 4, sizeof u);
-        dcd_cell(u, cell);
+        double cell[9];
+        std::memcpy(cell, s.cell, sizeof cell);
         FrameCtx *next = h->ctx[(size_t)(h->submitted % (int64_t)(h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size()))];
         cudaError_t e = cudaSuccess;
         auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
         if (s.used) step(cudaStreamWaitEvent(h->s_copy, s.gathered, 0));            // d_raw free again
-        step(cudaMemcpyAsync(s.d_raw, s.h_raw, (size_t)fb, cudaMemcpyHostToDevice, h->s_copy));
+        step(cudaMemcpyAsync(s.d_raw, s.h_raw, fb, cudaMemcpyHostToDevice, h->s_copy));
         step(cudaEventRecord(s.h2d_done, h->s_copy));
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -336,12 +355,14 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
         step(cudaStreamWaitEvent(next->stream, s.h2d_done, 0));
         if (s.used) step(cudaStreamWaitEvent(next->stream, s.consumed, 0));         // d_xyz free again
         if (e == cudaSuccess) {
-            k_gather_dcd<<<(unsigned)((F.n_idx + 255) / 256), 256, 0, next->stream>>>(s.d_raw, (long long)d->info.natoms, F.d_idx, (int)F.n_idx, s.d_xyz);
+            const unsigned nblk = (unsigned)((F.n_idx + 255) / 256);
+            if (src.layout == 0) k_gather_dcd<<<nblk, 256, 0, next->stream>>>(s.d_raw, (long long)src.natoms, F.d_idx, (int)F.n_idx, s.d_xyz);
+            else k_gather_xyz<<<nblk, 256, 0, next->stream>>>((const float *)s.d_raw, F.d_idx, (int)F.n_idx, s.d_xyz);
             h->stats.kernel_launches++;
             step(cudaEventRecord(s.gathered, next->stream));
         }
-        if (e != cudaSuccess) { h->err = std::string("cmx_run_dcd: ") + cudaGetErrorString(e); rc = CMX_ERR_CUDA; break; }
-        h->stats.h2d_bytes += fb;
+        if (e != cudaSuccess) { h->err = std::string(src.what) + ": " + cudaGetErrorString(e); rc = CMX_ERR_CUDA; break; }
+        h->stats.h2d_bytes += (int64_t)fb;
         const float *dsol = s.d_xyz, *dsolv = s.d_xyz + 3 * ns;
         rc = submit_common(h, dsol, dsolv, frames[k] + 1, weights ? weights[k] : 1.0, cell);
         cudaEventRecord(s.consumed, next->stream);
@@ -354,6 +375,25 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
     }
     for (auto &t : threads) t.join();
     return rc;
+}
+
+int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, const int32_t *solvent_indices,
+                    const int64_t *frames, const double *weights, int64_t nframes, int32_t n_reader_threads) {
+    if (!h) return CMX_ERR_ARG;
+    if (!d) return fail(h, CMX_ERR_ARG, "cmx_run_dcd: null argument");
+    FeedSource src;
+    src.what = "cmx_run_dcd"; src.natoms = d->info.natoms; src.nframes = d->info.nframes;
+    src.slot_bytes = (size_t)d->info.frame_bytes; src.layout = 0;
+    const int fd = d->fd;
+    const int64_t first = d->info.first_frame_offset, fb = d->info.frame_bytes;
+    src.fill = [fd, first, fb](int64_t frame, unsigned char *dst, double cell[9], std::string &err) {
+        if (!pread_all(fd, dst, (size_t)fb, (off_t)(first + frame * fb))) { err = "short read in DCD frame " + std::to_string((long long)frame); return false; }
+        double u[6];
+        std::memcpy(u, dst + 4, sizeof u);
+        dcd_cell(u, cell);
+        return true;
+    };
+    return run_feed(h, src, solute_indices, solvent_indices, frames, weights, nframes, n_reader_threads);
 }
 
 int32_t cmx_reduce_groups(cmx_handle *h, int32_t which, int32_t n_groups, const int32_t *offsets, const int32_t *rows, double *out) {

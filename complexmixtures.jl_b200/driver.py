@@ -15,11 +15,11 @@ from typing import Optional
 
 import numpy as np
 
-from .engine import DcdFile, Engine
+from .engine import DcdFile, Engine, XtcFile
 from .options import Options
 from .results import Result, finalresults, new_result
 from .selection import AtomSelection
-from .trajectory import NamdDCD, Trajectory, make_trajectory, trajectory_metadata
+from .trajectory import NamdDCD, Trajectory, XTCTraj, make_trajectory, trajectory_metadata
 
 
 def frames_to_compute(options: Options, lastframe_read: int, frame_weights) -> list:
@@ -77,10 +77,10 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
     counters per GPU regardless of the thread count (src/parallel_setup.jl:21-54 does not apply).
 
-    ``feed``: "native" = the library's own DCD feed (``cmx_run_dcd``: reader threads -> pinned ring ->
+    ``feed``: "native" = the library's own DCD / XTC feed (``cmx_run_dcd`` / ``cmx_run_xtc``: reader threads -> pinned ring ->
     raw frame H2D -> device gather of the selections; the frames of this rank are read by offset, the
     others are never touched), "host" = this module's reader writing into the pinned staging slot
-    (``cmx_acquire_frame_buffer`` / ``cmx_submit_frame``), "auto" = native for DCD files.  Both give
+    (``cmx_acquire_frame_buffer`` / ``cmx_submit_frame``), "auto" = native for DCD and XTC files.  Both give
     the same counters.  The cooperative stop file (src/mddf.jl:301-304) is only polled by the host feed.
     """
     if isinstance(trajectory, str):
@@ -95,9 +95,9 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     assert isinstance(trajectory, Trajectory)
     if feed not in ("auto", "native", "host"):
         raise ValueError("feed must be 'auto', 'native' or 'host'")
-    native = feed == "native" or (feed == "auto" and isinstance(trajectory, NamdDCD))
-    if native and not isinstance(trajectory, NamdDCD):
-        raise ValueError("feed='native' needs a DCD trajectory")
+    native = feed == "native" or (feed == "auto" and isinstance(trajectory, (NamdDCD, XTCTraj)))
+    if native and not isinstance(trajectory, (NamdDCD, XTCTraj)):
+        raise ValueError("feed='native' needs a DCD or XTC trajectory")
     tmeta = trajectory_metadata(trajectory, options)
     R = new_result(trajectory, options, tmeta, frame_weights)
     rank, world = (0, 1) if distributed is False else _dist_info()   # distributed=False: ignore an initialised process group
@@ -117,14 +117,15 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     todo = frames_to_compute(options, tmeta.lastframe_read, R.files[0].frame_weights)
     if native:
         my = shard(todo, rank, world)
-        dcd = DcdFile(trajectory.filename)
+        is_dcd = isinstance(trajectory, NamdDCD)
+        src = DcdFile(trajectory.filename) if is_dcd else XtcFile(trajectory.filename)
         try:
             w = [wt for _, wt in my]
-            eng.run_dcd(dcd, trajectory.solute.indices, trajectory.solvent.indices, [f - 1 for f, _ in my],
-                        None if all(v == 1.0 for v in w) else w, n_reader_threads=reader_threads)
+            (eng.run_dcd if is_dcd else eng.run_xtc)(src, trajectory.solute.indices, trajectory.solvent.indices, [f - 1 for f, _ in my],
+                                                     None if all(v == 1.0 for v in w) else w, n_reader_threads=reader_threads)
         finally:
             eng.sync()
-            dcd.close()
+            src.close()
     else:
         mine = set(f for f, _ in shard(todo, rank, world))
         weights = dict(todo)

@@ -8,13 +8,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+from typing import Optional
 
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmx_b200.so")
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
-        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl", "cmx_feed.inl")]
+        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl", "cmx_feed.inl", "cmx_xtc.inl")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "cmx_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "63"]
@@ -61,6 +62,10 @@ class CmxStats(C.Structure):
                 ("gpu_ms_search_random", C.c_double), ("gpu_ms_reduce", C.c_double)]
 
 
+class CmxXtcInfo(C.Structure):
+    _fields_ = [("natoms", C.c_int64), ("nframes", C.c_int64)]
+
+
 class CmxDcdInfo(C.Structure):
     _fields_ = [("natoms", C.c_int64), ("nframes", C.c_int64), ("first_frame_offset", C.c_int64), ("frame_bytes", C.c_int64)]
 
@@ -72,7 +77,7 @@ EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_ac
            "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_finish", "cmx_read_minimum_distances",
            "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option", "cmx_alloc_pinned",
            "cmx_free_pinned", "cmx_dcd_last_error", "cmx_dcd_open", "cmx_dcd_close", "cmx_dcd_read_frame", "cmx_run_dcd",
-           "cmx_reduce_groups"]
+           "cmx_reduce_groups", "cmx_xtc_open", "cmx_xtc_close", "cmx_xtc_read_frame", "cmx_run_xtc"]
 
 _lib = None
 
@@ -110,6 +115,10 @@ def load_library(path: str = LIB_PATH):
     lib.cmx_dcd_read_frame.argtypes = [vp, C.c_int64, vp, vp, vp, C.POINTER(C.c_double)]
     lib.cmx_run_dcd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
     lib.cmx_reduce_groups.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp]
+    lib.cmx_xtc_open.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(CmxXtcInfo)]
+    lib.cmx_xtc_close.argtypes = [vp]
+    lib.cmx_run_xtc.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
+    lib.cmx_xtc_read_frame.argtypes = [vp, C.c_int64, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name not in ("cmx_version", "cmx_last_error", "cmx_dcd_last_error"):
             getattr(lib, name).restype = C.c_int32
@@ -161,6 +170,42 @@ class DcdFile:
     def close(self):
         if getattr(self, "h", None):
             self.lib.cmx_dcd_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class XtcFile:
+    """Native GROMACS XTC reader of the library (cmx_xtc_*): pure host code, usable without a GPU.  Frames are
+    indexed at open time; ``read_frame`` decodes the compressed coordinate block to fp32 Angstrom."""
+
+    def __init__(self, filename: str):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        info = CmxXtcInfo()
+        rc = self.lib.cmx_xtc_open(os.fsencode(filename), C.byref(self.h), C.byref(info))
+        if rc:
+            self.h = None
+            raise CmxError(rc, self.lib.cmx_dcd_last_error().decode())
+        self.filename, self.natoms, self.nframes = filename, int(info.natoms), int(info.nframes)
+
+    def read_frame(self, iframe: int, out: Optional[np.ndarray] = None):
+        """(xyz fp32 [natoms,3] in Angstrom, cell 3x3 with the lattice vectors as columns, step, time)."""
+        xyz = np.empty((self.natoms, 3), dtype=np.float32) if out is None else out
+        cell, step, time = np.zeros(9), C.c_int32(), C.c_float()
+        rc = self.lib.cmx_xtc_read_frame(self.h, int(iframe), xyz.ctypes.data, cell.ctypes.data_as(C.POINTER(C.c_double)),
+                                         C.byref(step), C.byref(time))
+        if rc:
+            raise CmxError(rc, self.lib.cmx_dcd_last_error().decode())
+        return xyz, cell.reshape(3, 3).T.copy(), int(step.value), float(time.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cmx_xtc_close(self.h)
             self.h = None
 
     def __del__(self):
@@ -263,6 +308,15 @@ class Engine:
         ss = None if self.autocorrelation else np.ascontiguousarray(solute_indices, dtype=np.int32)
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         self._ck(self.lib.cmx_run_dcd(self.h, dcd.h, None if ss is None else ss.ctypes.data, sv.ctypes.data, fr.ctypes.data,
+                                      None if w is None else w.ctypes.data, int(fr.size), int(n_reader_threads)))
+
+    def run_xtc(self, xtc: "XtcFile", solute_indices, solvent_indices, frames, weights=None, n_reader_threads: int = 0):
+        """cmx_run_xtc: as ``run_dcd`` for a GROMACS XTC file (the reader threads also decode)."""
+        fr = np.ascontiguousarray(frames, dtype=np.int64)
+        sv = np.ascontiguousarray(solvent_indices, dtype=np.int32)
+        ss = None if self.autocorrelation else np.ascontiguousarray(solute_indices, dtype=np.int32)
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        self._ck(self.lib.cmx_run_xtc(self.h, xtc.h, None if ss is None else ss.ctypes.data, sv.ctypes.data, fr.ctypes.data,
                                       None if w is None else w.ctypes.data, int(fr.size), int(n_reader_threads)))
 
     def reduce_groups(self, which: str, groups) -> np.ndarray:

@@ -143,6 +143,38 @@ class NamdDCD(Trajectory):
         return cell_from_lengths_angles(A, B, C, a, b, g)
 
 
+class XTCTraj(Trajectory):
+    """GROMACS XTC through the library's native decoder (``cmx_xtc_*``); the reference reads this format with
+    Chemfiles (src/trajectory_formats/ChemFiles.jl): positions in Angstrom, unit cell with the lattice vectors as
+    matrix columns (convert_unitcell)."""
+
+    def __init__(self, filename: str, solute: AtomSelection, solvent: AtomSelection, lastframe: int = -1):
+        from .engine import XtcFile
+        self.filename, self.solute, self.solvent = filename, solute, solvent
+        self._x = XtcFile(filename)
+        self.natoms_file = self._x.natoms
+        self.nframes = self._x.nframes if lastframe <= 0 else min(self._x.nframes, lastframe)
+        if max(solute.indices.max(), solvent.indices.max()) > self.natoms_file:
+            raise ValueError("selection index outside the atoms of the XTC file")
+        self._alloc()
+        self._xyz = np.empty((self.natoms_file, 3), dtype=np.float32)
+        self._k, self._cell = 0, np.zeros((3, 3))
+
+    def open(self): self._k = 0
+    def close(self): pass
+    def firstframe(self): self._k = 0
+
+    def nextframe(self, dst_solute=None, dst_solvent=None):
+        if self._k >= self._x.nframes:
+            raise EOFError("end of XTC trajectory")
+        _, self._cell, self.step, self.time = self._x.read_frame(self._k, out=self._xyz)
+        self._k += 1
+        return self._gather(self._xyz, dst_solute, dst_solvent)
+
+    def getunitcell(self):
+        return self._cell
+
+
 class PDBTraj(Trajectory):
     """Multi-model PDB trajectory, one CRYST1 per frame (src/trajectory_formats/PDBTraj.jl)."""
 
@@ -220,12 +252,14 @@ def make_trajectory(filename: str, solute: AtomSelection, solvent: Optional[Atom
     fmt = format
     if not fmt:
         low = filename.lower()
-        fmt = "dcd" if low.endswith(".dcd") else "PDBTraj" if low.endswith(".pdb") else ""
+        fmt = "dcd" if low.endswith(".dcd") else "PDBTraj" if low.endswith(".pdb") else "xtc" if low.endswith(".xtc") else ""
     if fmt == "dcd":
         return NamdDCD(filename, solute, solvent, lastframe=lastframe)
+    if fmt == "xtc":
+        return XTCTraj(filename, solute, solvent, lastframe=lastframe)
     if fmt == "PDBTraj":
         return PDBTraj(filename, solute, solvent, lastframe=lastframe)
-    raise ValueError(f"Unsupported trajectory format for {filename!r}: the B200 host shim reads DCD "
+    raise ValueError(f"Unsupported trajectory format for {filename!r}: the B200 host shim reads DCD, XTC "
                      "and PDB natively; other formats stay with the Julia/Chemfiles reader.")
 
 

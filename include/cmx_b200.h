@@ -176,6 +176,25 @@ int32_t cmx_dcd_read_frame(cmx_dcd *d, int64_t iframe, float *x, float *y, float
 int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, const int32_t *solvent_indices,
                     const int64_t *frames, const double *weights, int64_t nframes, int32_t n_reader_threads);
 
+/* ---- frame feed: native XTC reader (host code; SURVEY 8 f1, second format) -------------------------
+ * Replaces the Chemfiles read of GROMACS XTC frames (src/trajectory_formats/ChemFiles.jl:112-138): frame index
+ * built at open time, compressed coordinate block decoded to fp32 xyz triplets in Angstrom (nm x 10), unit cell
+ * as the column-major 3x3 matrix cmx_submit_frame takes.  cmx_xtc_* are pure host code (errors through
+ * cmx_dcd_last_error()); cmx_run_xtc is the XTC twin of cmx_run_dcd. */
+typedef struct cmx_xtc cmx_xtc;
+typedef struct cmx_xtc_info {
+    int64_t natoms;
+    int64_t nframes;            /* complete frames found by walking the file */
+} cmx_xtc_info;
+int32_t cmx_xtc_open(const char *path, cmx_xtc **out, cmx_xtc_info *info);
+int32_t cmx_xtc_close(cmx_xtc *x);
+/* frame (0-based) -> xyz[3*natoms] fp32 Angstrom (may be NULL), cell[9] (may be NULL), MD step and time (may be NULL) */
+int32_t cmx_xtc_read_frame(cmx_xtc *x, int64_t iframe, float *xyz, double cell[9], int32_t *step, float *time);
+/* The frame loop for an XTC file (arguments as cmx_run_dcd): the reader threads read AND decode whole frames into the
+ * pinned ring (default 4 threads), one H2D per decoded frame, selection gather on the device. */
+int32_t cmx_run_xtc(cmx_handle *h, cmx_xtc *x, const int32_t *solute_indices, const int32_t *solvent_indices,
+                    const int64_t *frames, const double *weights, int64_t nframes, int32_t n_reader_threads);
+
 /* ---- group reduction on the device ------------------------------------------------
  * The count stage of contributions()/ResidueContributions (src/tools/contributions.jl:70-248,
  * src/tools/residue_contributions.jl:157-215): out[g][b] = sum of the rows of one group-count array

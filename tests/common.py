@@ -124,3 +124,19 @@ def write_dcd(path, frames, cells):
             rec(f, struct.pack("<6d", A, ang(a, b), B, ang(a, cc), ang(b, cc), C_))
             for d in range(3):
                 rec(f, frames[k, :, d].astype("<f4").tobytes())
+
+
+def write_xtc_small(path, frames_nm, boxes_nm, steps=None, dt=2.0):
+    """XTC writer for AT MOST 9 atoms per frame: such frames are stored by the format as plain big-endian floats
+    (no compression), which makes a writer a few lines.  frames_nm [nframes, natoms, 3] and boxes_nm [nframes, 3, 3]
+    (rows = box vectors) in nm."""
+    import struct
+    frames_nm = np.asarray(frames_nm, dtype=np.float32)
+    nf, n = frames_nm.shape[0], frames_nm.shape[1]
+    assert n <= 9
+    with open(path, "wb") as f:
+        for k in range(nf):
+            f.write(struct.pack(">iiif", 1995, n, k * 10 if steps is None else steps[k], k * dt))
+            f.write(struct.pack(">9f", *np.asarray(boxes_nm[k], dtype=np.float32).reshape(9)))
+            f.write(struct.pack(">i", n))
+            f.write(frames_nm[k].astype(">f4").tobytes())

@@ -516,7 +516,8 @@ def test_native_dcd_feed_equals_the_staging_slot_path(tmp_path, threads):
     # many passes over the 3 frames so that the ring (4+ slots) wraps several times
     order = [0, 1, 2, 2, 1, 0, 1, 1, 2, 0, 0, 2, 1]
     weights = [1.0, 2.0, 1.0, 1.0, 2.0, 1.0, 2.0, 2.0, 1.0, 1.0, 1.0, 1.0, 2.0]
-    eng = Engine(solute=sol, solvent=tm, options=opt, irefatom=1, autocorrelation=False)
+    # one stream -> a ring of 4 slots, so the 13 frames wrap it three times; three threads -> the default ring (18 slots)
+    eng = Engine(solute=sol, solvent=tm, options=opt, irefatom=1, autocorrelation=False, n_streams=1 if threads == 1 else 0)
     eng.run_dcd(f, sol.indices, tm.indices, order, weights, n_reader_threads=threads)
     dev = eng.finish()
     st = eng.stats()
@@ -649,3 +650,36 @@ def test_mddf_many_reuses_one_engine(tmp_path):
     M = cm.merge([Ra, Rb])
     assert merged.weights == [2 / 3, 1 / 3] and np.allclose(merged.md_count, M.md_count, rtol=0, atol=0)
     assert np.allclose(merged.md_count, (2 * Ra.md_count + Rb.md_count) / 3, rtol=1e-15)
+
+
+def test_xtc_native_and_host_feed_small(tmp_path):
+    """GROMACS XTC through cmx_run_xtc (reader threads decode into the pinned ring, device gather of xyz triplets) and
+    through the host reader XTCTraj: same Result as an in-memory trajectory of the decoded frames.  Frames of <= 9
+    atoms (plain floats in the format; the compressed block is covered on the CPU by tests/test_host.py)."""
+    from common import write_xtc_small
+    from cmx_b200.engine import XtcFile
+    t = toy()
+    fr, cells = t["self"], t["self_cells"]                                  # 6 atoms = 2 molecules x 3, 2 frames
+    nrep = 7                                                                # more frames than ring slots of a 1-stream run
+    frames_nm = np.concatenate([fr] * nrep).astype(np.float64) / 10.0
+    boxes_nm = np.concatenate([np.transpose(cells, (0, 2, 1))] * nrep) / 10.0   # XTC rows = box vectors
+    path = str(tmp_path / "toy.xtc")
+    write_xtc_small(path, frames_nm, boxes_nm)
+    x = XtcFile(path)
+    dec = [x.read_frame(k) for k in range(x.nframes)]
+    x.close()
+    sel = cm.AtomSelection(np.arange(1, 7), natomspermol=3)
+    o = opts(n_random_samples=50)
+    w = [1.0, 2.0] * nrep
+    Rn = cm.mddf(path, sel, o, frame_weights=w, feed="native", reader_threads=3, _engine_kw={"n_streams": 1})   # ring of 5 slots: wraps
+    Rh = cm.mddf(path, sel, o, frame_weights=w, feed="host")
+    Ra = cm.mddf(cm.ArrayTrajectory(np.stack([d[0] for d in dec]), np.stack([d[1] for d in dec]), sel, sel), o, frame_weights=w)
+    assert Rn.md_count.sum() > 0 and Rn.volume.total == Ra.volume.total
+    for key in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count", "solvent_group_count", "mddf", "kb"):
+        assert np.array_equal(getattr(Rn, key), getattr(Ra, key)), key
+        assert np.array_equal(getattr(Rh, key), getattr(Ra, key)), key
+    # a cross-correlation with a strict subset of the file's atoms (the gather matters), unit weights
+    a, b = cm.AtomSelection([1, 2, 3], nmols=1), cm.AtomSelection([4, 5, 6], natomspermol=3)
+    Rn = cm.mddf(path, a, b, o, feed="native")
+    Ra = cm.mddf(cm.ArrayTrajectory(np.stack([d[0] for d in dec]), np.stack([d[1] for d in dec]), a, b), o)
+    assert np.array_equal(Rn.md_count, Ra.md_count) and np.array_equal(Rn.md_count_random, Ra.md_count_random)

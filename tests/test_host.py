@@ -1,5 +1,6 @@
 """CPU tests of the host-side mirrors and of the C-ABI library (symbols only: no GPU calls)."""
 import ctypes
+import json
 import os
 import re
 import subprocess
@@ -132,13 +133,13 @@ def test_cabi_exports_every_declared_symbol():
     lib.cmx_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.cmx_version()
     # struct layouts agree with the header (compiled with the host compiler)
-    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats), sizeof(cmx_dcd_info));}'
+    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats), sizeof(cmx_dcd_info), sizeof(cmx_xtc_info));}'
     exe = os.path.join("/tmp", f"cmx_sz_{os.getpid()}")
     subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
     os.remove(exe)
     assert sizes == [ctypes.sizeof(engine.CmxConfig), ctypes.sizeof(engine.CmxCounters), engine.MD_DTYPE.itemsize, ctypes.sizeof(engine.CmxStats),
-                     ctypes.sizeof(engine.CmxDcdInfo)]
+                     ctypes.sizeof(engine.CmxDcdInfo), ctypes.sizeof(engine.CmxXtcInfo)]
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_oracle():
@@ -299,3 +300,67 @@ def test_merge_weights_and_errors():
     other = mk(2, [1, 1], 1.0); other.solute = cm.AtomSelection([1, 2, 4], nmols=1)
     with pytest.raises(ValueError, match="selections"):
         merge([A, other])
+
+
+def test_native_xtc_reader_small_uncompressed(tmp_path):
+    """cmx_xtc_* on frames of <= 9 atoms (stored as plain floats by the format): frame index, units (nm -> A), box
+    rows -> lattice vectors as matrix columns, selection gather of XTCTraj, truncated tail, garbage."""
+    from common import write_xtc_small
+    from cmx_b200.engine import CmxError, XtcFile
+    rng = np.random.default_rng(2)
+    fr = rng.uniform(0, 3, size=(4, 7, 3)).astype(np.float32)
+    boxes = np.array([np.diag([3.0, 3.1, 3.2]), [[3.0, 0, 0], [0.4, 2.9, 0], [0.3, 0.5, 2.8]], np.diag([3.0, 3.0, 3.0]), np.diag([2.5, 3.0, 3.5])])
+    path = str(tmp_path / "s.xtc")
+    write_xtc_small(path, fr, boxes)
+    x = XtcFile(path)
+    assert (x.natoms, x.nframes) == (7, 4)
+    for k in (2, 0, 3, 1):                                        # any order: frames are indexed
+        xyz, cell, step, time = x.read_frame(k)
+        assert np.array_equal(xyz, (fr[k].astype(np.float64) * 10.0).astype(np.float32)) and step == 10 * k and time == 2.0 * k
+        assert np.allclose(cell, 10.0 * boxes[k].T, rtol=1e-7)    # columns = lattice vectors
+    with pytest.raises(CmxError):
+        x.read_frame(4)
+    x.close()
+    sel_a, sel_b = cm.AtomSelection([2, 5], nmols=1), cm.AtomSelection([1, 3, 4, 7], natomspermol=2)
+    t = cm.make_trajectory(path, sel_a, sel_b)
+    assert isinstance(t, cm.XTCTraj) and t.nframes == 4
+    t.open()
+    xs, xv = t.nextframe()
+    assert np.allclose(xs, 10 * fr[0][[1, 4]], rtol=1e-6) and np.allclose(xv, 10 * fr[0][[0, 2, 3, 6]], rtol=1e-6)
+    assert np.allclose(t.getunitcell(), 10.0 * boxes[0].T, rtol=1e-7)
+    t.close()
+    with open(path, "ab") as fh:
+        fh.write(b"\x00\x00\x07\xcb" + b"\x00" * 20)              # a truncated extra frame is ignored
+    y = XtcFile(path); assert y.nframes == 4; y.close()
+    bad = tmp_path / "bad.xtc"; bad.write_bytes(b"\x00" * 300)
+    with pytest.raises(CmxError):
+        XtcFile(str(bad))
+    with pytest.raises(ValueError):
+        cm.make_trajectory(path, cm.AtomSelection([8], nmols=1), sel_b)
+
+
+def test_native_xtc_reader_reference_fixture():
+    """the compressed coordinate block, on the reference's own fixture test/data/nucleic/trajectory.xtc (present in
+    the build container only): the decoder is pinned by physics -- the last 1000 molecules are TIP3P water and must
+    come out rigid (O-H 0.9572 A, H-H 1.5139 A within the 0.01 A grid of the format) in every frame -- and against
+    the committed summary tests/golden/xtc_nucleic.json."""
+    from cmx_b200.engine import XtcFile
+    src = "/root/reference/test/data/nucleic/trajectory.xtc"
+    if not os.path.exists(src):
+        pytest.skip("reference fixture not present on this machine")
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "xtc_nucleic.json")))
+    x = XtcFile(src)
+    assert (x.natoms, x.nframes) == (g["natoms"], g["nframes"]) == (95988, 6)
+    for k, fr in enumerate(g["frames"]):
+        xyz, cell, step, time = x.read_frame(k)
+        w = xyz[-3000:].astype(np.float64).reshape(-1, 3, 3)
+        oh1, oh2 = np.linalg.norm(w[:, 1] - w[:, 0], axis=1), np.linalg.norm(w[:, 2] - w[:, 0], axis=1)
+        hh = np.linalg.norm(w[:, 2] - w[:, 1], axis=1)
+        assert abs(oh1.mean() - 0.9572) < 2e-3 and abs(oh2.mean() - 0.9572) < 2e-3 and abs(hh.mean() - 1.5139) < 2e-3
+        assert max(np.abs(oh1 - 0.9572).max(), np.abs(oh2 - 0.9572).max(), np.abs(hh - 1.5139).max()) < 0.03
+        L = np.diag(cell)
+        assert np.all(xyz.min(axis=0) > -0.05 * L) and np.all(xyz.max(axis=0) < 1.05 * L)
+        assert step == fr["step"] and time == fr["time"] and np.array_equal(cell, np.array(fr["cell"]))
+        assert np.array_equal(xyz[:4].astype(float), np.array(fr["first_atoms"])) and np.array_equal(xyz[-3:].astype(float), np.array(fr["last_atoms"]))
+        assert np.allclose(np.sum(xyz.astype(np.float64), axis=0), fr["sum"], rtol=1e-12)
+    x.close()
