@@ -141,6 +141,23 @@ function run_dcd!(h::Ptr{Cvoid}, trajectory, frames::Vector{Int}, weights::Vecto
     end
 end
 
+# XTC twin: `cmx_xtc_open` / `cmx_run_xtc` / `cmx_xtc_close` take the same arguments (a Chemfiles trajectory's
+# `trajectory.filename` ending in .xtc); errors of cmx_xtc_open come through `cmx_dcd_last_error` as well.
+function run_xtc!(h::Ptr{Cvoid}, trajectory, frames::Vector{Int}, weights::Vector{Float64}; reader_threads::Integer=4)
+    xref = Ref{Ptr{Cvoid}}(C_NULL); info = Ref((Int64(0), Int64(0)))
+    rc = ccall((:cmx_xtc_open, libcmx), Int32, (Cstring, Ref{Ptr{Cvoid}}, Ptr{Cvoid}), trajectory.filename, xref, info)
+    rc == 0 || error(unsafe_string(ccall((:cmx_dcd_last_error, libcmx), Cstring, ())))
+    sol = Int32.(trajectory.solute.indices); solv = Int32.(trajectory.solvent.indices)
+    fr0 = Int64.(frames .- 1)
+    try
+        GC.@preserve sol solv fr0 weights check(h, ccall((:cmx_run_xtc, libcmx), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Int64, Int32),
+            h, xref[], sol, solv, fr0, weights, length(fr0), reader_threads))
+    finally
+        ccall((:cmx_xtc_close, libcmx), Int32, (Ptr{Cvoid},), xref[])
+    end
+end
+
 # ---- SURVEY 8(f2): contributions / ResidueContributions count stage on the device ----------------------
 """
     reduce_groups(h, which, groups, nbins) -> Matrix{Float64}(nbins, length(groups))
