@@ -140,3 +140,142 @@ def write_xtc_small(path, frames_nm, boxes_nm, steps=None, dt=2.0):
             f.write(struct.pack(">9f", *np.asarray(boxes_nm[k], dtype=np.float32).reshape(9)))
             f.write(struct.pack(">i", n))
             f.write(frames_nm[k].astype(">f4").tobytes())
+
+
+# ---- XTC writer with the compressed coordinate block (test infrastructure; pure Python, serial) -----------------------
+_XTC_MAGICINTS = [0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512,
+                  645, 812, 1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007,
+                  32768, 41285, 52015, 65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561,
+                  832255, 1048576, 1321122, 1664510, 2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607,
+                  10568983, 13316085, 16777216]
+_XTC_FIRSTIDX, _XTC_LASTIDX = 9, len(_XTC_MAGICINTS) - 1
+
+
+class _BitWriter:
+    def __init__(self):
+        self.out, self.acc, self.nacc = bytearray(), 0, 0
+
+    def bits(self, nbits, value):
+        self.acc = (self.acc << nbits) | (value & ((1 << nbits) - 1))
+        self.nacc += nbits
+        while self.nacc >= 8:
+            self.nacc -= 8
+            self.out.append((self.acc >> self.nacc) & 0xff)
+        self.acc &= (1 << self.nacc) - 1
+
+    def ints3(self, nbits, sizes, nums):
+        """three integers as one mixed-radix number (radices `sizes`), sent least-significant byte first"""
+        v = (nums[0] * sizes[1] + nums[1]) * sizes[2] + nums[2]
+        nbytes = []
+        while v:
+            nbytes.append(v & 0xff); v >>= 8
+        # the reader takes whole bytes while more than 8 bits remain, then the rest in one piece
+        k, left = 0, nbits
+        while left > 8:
+            self.bits(8, nbytes[k] if k < len(nbytes) else 0); k += 1; left -= 8
+        if left > 0:
+            self.bits(left, nbytes[k] if k < len(nbytes) else 0)
+
+    def bytes(self):
+        if self.nacc:
+            return bytes(self.out) + bytes([(self.acc << (8 - self.nacc)) & 0xff])
+        return bytes(self.out)
+
+
+def _xtc_sizeofint(size):
+    num, nbits = 1, 0
+    while size >= num and nbits < 32:
+        nbits += 1; num <<= 1
+    return nbits
+
+
+def _xtc_sizeofints(sizes):
+    return max(1, (sizes[0] * sizes[1] * sizes[2]).bit_length())
+
+
+def xtc_compress(ints, precision=1000.0):
+    """the compressed coordinate block of one frame from quantised coordinates ints[natoms,3] (more than 9 atoms)."""
+    import struct
+    M = _XTC_MAGICINTS
+    c = [list(map(int, r)) for r in np.asarray(ints)]
+    n = len(c)
+    mn = [min(r[k] for r in c) for k in range(3)]; mx = [max(r[k] for r in c) for k in range(3)]
+    sizeint = [mx[k] - mn[k] + 1 for k in range(3)]
+    if max(sizeint) > 0xffffff:
+        bitsizeint, bitsize = [_xtc_sizeofint(s) for s in sizeint], 0
+    else:
+        bitsizeint, bitsize = None, _xtc_sizeofints(sizeint)
+    mindiff = min((sum(abs(c[i][k] - c[i - 1][k]) for k in range(3)) for i in range(1, n)), default=0x7fffffff)
+    smallidx = _XTC_FIRSTIDX
+    while smallidx < _XTC_LASTIDX and M[smallidx] < mindiff:
+        smallidx += 1
+    smallidx0 = smallidx
+    maxidx = min(_XTC_LASTIDX, smallidx + 8); minidx = maxidx - 8
+    smaller, smallnum, larger = M[max(_XTC_FIRSTIDX, smallidx - 1)] // 2, M[smallidx] // 2, M[maxidx] // 2
+    w = _BitWriter()
+    i, prevrun, prev = 0, -1, [0, 0, 0]
+    close = lambda a, b, lim: all(abs(a[k] - b[k]) < lim for k in range(3))
+    while i < n:
+        is_small = 0
+        if smallidx < maxidx and i >= 1 and close(c[i], prev, larger):
+            is_smaller = 1
+        elif smallidx > minidx:
+            is_smaller = -1
+        else:
+            is_smaller = 0
+        if i + 1 < n and close(c[i], c[i + 1], smallnum):
+            c[i], c[i + 1] = c[i + 1], c[i]          # first and second atom of a run are stored swapped
+            is_small = 1
+        tmp = [c[i][k] - mn[k] for k in range(3)]
+        if bitsize == 0:
+            for k in range(3):
+                w.bits(bitsizeint[k], tmp[k])
+        else:
+            w.ints3(bitsize, sizeint, tmp)
+        prev = c[i]; i += 1
+        run, small = 0, []
+        if is_small == 0 and is_smaller == -1:
+            is_smaller = 0
+        while is_small and run < 8 * 3:
+            if is_smaller == -1 and sum((c[i][k] - prev[k]) ** 2 for k in range(3)) >= smaller * smaller:
+                is_smaller = 0
+            small.append([c[i][k] - prev[k] + smallnum for k in range(3)]); run += 3
+            prev = c[i]; i += 1
+            is_small = 1 if (i < n and close(c[i], prev, smallnum)) else 0
+        if run != prevrun or is_smaller != 0:
+            prevrun = run
+            w.bits(1, 1); w.bits(5, run + is_smaller + 1)
+        else:
+            w.bits(1, 0)
+        sz = [M[smallidx]] * 3
+        for t in small:
+            w.ints3(smallidx, sz, t)
+        if is_smaller != 0:
+            smallidx += is_smaller
+            if is_smaller < 0:
+                smallnum = smaller; smaller = M[smallidx - 1] // 2
+            else:
+                smaller = smallnum; smallnum = M[smallidx] // 2
+    body = w.bytes()
+    pad = (-len(body)) % 4
+    return (struct.pack(">f3i3ii", precision, *mn, *mx, smallidx0) + struct.pack(">i", len(body)) + body + b"\0" * pad)
+
+
+def write_xtc(path, frames_nm, boxes_nm, precision=1000.0, steps=None, dt=2.0):
+    """XTC writer (any number of atoms): coordinates are quantised to round(x * precision) as the format does."""
+    import struct
+    frames_nm = np.asarray(frames_nm, dtype=np.float32)
+    nf, n = frames_nm.shape[0], frames_nm.shape[1]
+    if n <= 9:
+        return write_xtc_small(path, frames_nm, boxes_nm, steps=steps, dt=dt)
+    quant = []
+    with open(path, "wb") as f:
+        for k in range(nf):
+            f.write(struct.pack(">iiif", 1995, n, k * 10 if steps is None else steps[k], k * dt))
+            f.write(struct.pack(">9f", *np.asarray(boxes_nm[k], dtype=np.float32).reshape(9)))
+            f.write(struct.pack(">i", n))
+            x = frames_nm[k].astype(np.float64) * precision
+            ints = np.where(x >= 0, np.floor(x + 0.5), np.ceil(x - 0.5)).astype(np.int64)
+            quant.append(ints)
+            f.write(xtc_compress(ints, precision))
+    return quant

@@ -683,3 +683,35 @@ def test_xtc_native_and_host_feed_small(tmp_path):
     Rn = cm.mddf(path, a, b, o, feed="native")
     Ra = cm.mddf(cm.ArrayTrajectory(np.stack([d[0] for d in dec]), np.stack([d[1] for d in dec]), a, b), o)
     assert np.array_equal(Rn.md_count, Ra.md_count) and np.array_equal(Rn.md_count_random, Ra.md_count_random)
+
+
+def test_xtc_compressed_feed(tmp_path):
+    """a compressed XTC (protein + TMAO of the NAMD fixture, written by the test-suite's own XTC writer, which
+    reproduces GROMACS' bytes on the reference's fixture) through cmx_run_xtc with decoding reader threads: same
+    counters as the decoded frames through the staging-slot path, and as the oracle on those frames."""
+    from common import write_xtc
+    from cmx_b200.engine import Engine, XtcFile
+    d = namd()
+    frames = np.concatenate([d["protein"], d["tmao"]], axis=1)                 # 3997 atoms, Angstrom
+    boxes = np.stack([np.asarray(c, dtype=np.float64).T / 10.0 for c in d["cells"]])
+    path = str(tmp_path / "c.xtc")
+    write_xtc(path, frames.astype(np.float64) / 10.0, boxes)
+    x = XtcFile(path)
+    assert (x.natoms, x.nframes) == (3997, 3)
+    dec = [x.read_frame(k) for k in range(3)]
+    assert max(np.abs(dec[k][0] - frames[k]).max() for k in range(3)) < 0.0051   # the format's 0.01 A grid
+    sol = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+    tm = cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14)
+    opt = opts(bulk_range=(8.0, 10.0), n_random_samples=3)
+    order = [0, 1, 2, 1, 0, 2, 2]
+    eng = Engine(solute=sol, solvent=tm, options=opt, irefatom=1, autocorrelation=False, n_streams=2)
+    eng.run_xtc(x, sol.indices, tm.indices, order, n_reader_threads=3)
+    dev = eng.finish(); eng.close(); x.close()
+    p = Problem(sol, tm, opt, [dec[k][0][:1463] for k in order], [dec[k][0][1463:] for k in order], [dec[k][1] for k in order],
+                frame_ids=[k + 1 for k in order], irefatom=1)
+    o, _ = p.oracle()
+    assert_counters_equal(dev, o)
+    eng2 = p.engine()
+    dev2 = p.run_engine(eng2); eng2.close()
+    for key in dev:
+        assert np.array_equal(dev[key], dev2[key]), key
