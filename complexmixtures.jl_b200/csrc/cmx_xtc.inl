@@ -33,26 +33,36 @@ inline uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | (
 inline int32_t be32i(const unsigned char *p) { return (int32_t)be32(p); }
 inline float be32f(const unsigned char *p) { uint32_t u = be32(p); float f; std::memcpy(&f, &u, 4); return f; }
 
-struct XtcBits {   // big-endian bit reader over the compressed block
-    const unsigned char *buf; size_t n, cnt = 0; unsigned lastbits = 0; uint32_t lastbyte = 0; bool overrun = false;
-    inline uint32_t next() { if (cnt < n) return buf[cnt++]; overrun = true; return 0; }
-    uint32_t bits(int nbits) {
-        const uint32_t mask = nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
-        uint32_t num = 0;
-        while (nbits >= 8) {
-            lastbyte = (lastbyte << 8) | next();
-            num |= (lastbyte >> lastbits) << (nbits - 8);
-            nbits -= 8;
+struct XtcBits {   // big-endian bit reader over the compressed block: 64-bit window refilled bytewise
+    const unsigned char *buf; size_t n, cnt = 0; uint64_t acc = 0; int nacc = 0; bool overrun = false;
+    inline void refill(int need) {
+        while (nacc < need) {
+            uint64_t b = 0;
+            if (cnt < n) b = buf[cnt++]; else overrun = true;
+            acc = (acc << 8) | b; nacc += 8;
         }
-        if (nbits > 0) {
-            if ((int)lastbits < nbits) { lastbits += 8; lastbyte = (lastbyte << 8) | next(); }
-            lastbits -= (unsigned)nbits;
-            num |= (lastbyte >> lastbits) & ((1u << nbits) - 1u);
-        }
-        return num & mask;
     }
-    // three integers packed as one mixed-radix number of `nbits` bits with radices sizes[0..2]
+    // nbits <= 32: the next nbits of the stream, most significant bit first
+    inline uint32_t bits(int nbits) {
+        if (nbits == 0) return 0;
+        refill(nbits);
+        nacc -= nbits;
+        return (uint32_t)((acc >> nacc) & ((nbits >= 32) ? 0xffffffffull : ((1ull << nbits) - 1ull)));
+    }
+    // Three integers packed as one mixed-radix number of `nbits` bits with radices sizes[0..2].  The number is stored
+    // least-significant BYTE first (whole bytes, then the remaining high bits in one piece).
     void ints3(int nbits, const unsigned sizes[3], int out[3]) {
+        if (nbits <= 64) {   // the usual case: assemble the number in a machine word, two divisions
+            uint64_t v = 0; int shift = 0, left = nbits;
+            while (left > 8) { v |= (uint64_t)bits(8) << shift; shift += 8; left -= 8; }
+            if (left > 0) v |= (uint64_t)bits(left) << shift;
+            const uint64_t q2 = v / sizes[2];
+            out[2] = (int)(v - q2 * sizes[2]);
+            const uint64_t q1 = q2 / sizes[1];
+            out[1] = (int)(q2 - q1 * sizes[1]);
+            out[0] = (int)q1;
+            return;
+        }
         unsigned bytes[32] = {0};
         int nb = 0;
         while (nbits > 8) { bytes[nb++] = bits(8); nbits -= 8; }
