@@ -32,32 +32,57 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def write_xtc_replicated(path, system, nf, distinct=4):
+    """an XTC of `nf` frames for feed measurements: `distinct` frames are compressed by the test-suite's (pure Python,
+    ~0.7 s per 100k-atom frame) writer and their bytes repeated with increasing step numbers."""
+    import struct
+    from common import xtc_compress
+    box = (np.asarray(system.cell, dtype=np.float64).T / 10.0).astype(np.float32)
+    blocks = []
+    for k in range(distinct):
+        x = system.frame(k + 1)[0].astype(np.float64) / 10.0 * 1000.0
+        ints = np.where(x >= 0, np.floor(x + 0.5), np.ceil(x - 0.5)).astype(np.int64)
+        blocks.append(xtc_compress(ints, 1000.0))
+    n = system.natoms
+    with open(path, "wb") as f:
+        for k in range(nf):
+            f.write(struct.pack(">iiif", 1995, n, 10 * k, 2.0 * k) + struct.pack(">9f", *box.reshape(9)) + struct.pack(">i", n))
+            f.write(blocks[k % distinct])
+
+
 def feed(args):
     import cmx_b200 as cm
     from cmx_b200 import synthetic as syn
-    from cmx_b200.engine import DcdFile, Engine
+    from cmx_b200.engine import DcdFile, Engine, XtcFile
     from common import write_dcd
     s = syn.config_c2(args.scale)
     sol, wat = s.selections["solute"], s.selections["water"]
     opt = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=10, seed=321, silent=True)
     nf = args.frames
-    frames = np.stack([s.frame(k + 1)[0] for k in range(nf)]).astype(np.float32)
     tmp = tempfile.mkdtemp(prefix="cmx_feed_", dir=args.tmpdir)
-    path = os.path.join(tmp, "c2.dcd")
-    write_dcd(path, frames, np.asarray(s.cell, dtype=np.float64))
+    xtc = args.format == "xtc"
+    path = os.path.join(tmp, "c2.xtc" if xtc else "c2.dcd")
+    if xtc:
+        write_xtc_replicated(path, s, nf)
+    else:
+        frames = np.stack([s.frame(k + 1)[0] for k in range(nf)]).astype(np.float32)
+        write_dcd(path, frames, np.asarray(s.cell, dtype=np.float64))
+        del frames
     size = os.path.getsize(path)
-    first = frames[0][wat.indices - 1][:3].astype(np.float64)
+    first = s.frame(1)[0][wat.indices - 1][:3].astype(np.float64)
     iref = int(np.argmin(np.linalg.norm(first - first.mean(axis=0), axis=1))) + 1
-    del frames
-    out = {"what": "feed", "workload": f"C2 (scale {args.scale}) mddf(protein, water) from a DCD file of {nf} frames, {size / 1e6:.0f} MB (page cache warm)",
+    out = {"what": "feed", "format": args.format,
+           "workload": f"C2 (scale {args.scale}) mddf(protein, water) from a {args.format.upper()} file of {nf} frames, {size / 1e6:.0f} MB (page cache warm)",
            "frames": nf, "file_bytes": size}
     ref = None
-    for threads in (1, 2, 4):
+    Reader = XtcFile if xtc else DcdFile
+    for threads in ((2, 4, 8, 16) if xtc else (1, 2, 4)):
         eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=iref, autocorrelation=False)
-        f = DcdFile(path)
-        eng.run_dcd(f, sol.indices, wat.indices, list(range(min(nf, 16))), n_reader_threads=threads); eng.sync(); eng.reset()   # warm-up
+        f = Reader(path)
+        run = eng.run_xtc if xtc else eng.run_dcd
+        run(f, sol.indices, wat.indices, list(range(min(nf, 16))), n_reader_threads=threads); eng.sync(); eng.reset()   # warm-up
         t0 = time.perf_counter()
-        eng.run_dcd(f, sol.indices, wat.indices, list(range(nf)), n_reader_threads=threads)
+        run(f, sol.indices, wat.indices, list(range(nf)), n_reader_threads=threads)
         c = eng.finish(copy=False)
         dt = time.perf_counter() - t0
         out[f"native_{threads}_threads_frames_per_s"] = nf / dt
@@ -69,7 +94,7 @@ def feed(args):
         f.close(); eng.close()
     # where the fixed cost of a short run goes: create / first run (ring allocation) / finish / destroy
     t0 = time.perf_counter(); eng = Engine(solute=sol, solvent=wat, options=opt, irefatom=iref, autocorrelation=False); t1 = time.perf_counter()
-    f = DcdFile(path); eng.run_dcd(f, sol.indices, wat.indices, list(range(min(nf, 64))), n_reader_threads=2); t2 = time.perf_counter()
+    f = Reader(path); (eng.run_xtc if xtc else eng.run_dcd)(f, sol.indices, wat.indices, list(range(min(nf, 64))), n_reader_threads=2); t2 = time.perf_counter()
     eng.finish(copy=False); t3 = time.perf_counter(); f.close(); eng.close(); t4 = time.perf_counter()
     out["fixed_costs_ms"] = {"create": 1e3 * (t1 - t0), "run_64_frames_incl_ring_alloc": 1e3 * (t2 - t1), "finish": 1e3 * (t3 - t2), "destroy": 1e3 * (t4 - t3)}
     # host reader of this package -> staging slot (first `host_frames` frames only: it is the slow side)
@@ -147,5 +172,6 @@ if __name__ == "__main__":
     ap.add_argument("--rows", type=int, default=1000000)
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--tmpdir", default=None)
+    ap.add_argument("--format", default="dcd", choices=["dcd", "xtc"], help="trajectory format of the feed measurement")
     a = ap.parse_args()
     feed(a) if a.what == "feed" else reduce(a)
