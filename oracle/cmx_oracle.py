@@ -22,7 +22,8 @@ _LIB = None
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libcmx_oracle.so")
     src = os.path.join(_HERE, "cmx_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    src2 = os.path.join(_HERE, "xtc_two_phase.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(src2)):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return so
 
@@ -281,3 +282,22 @@ def finalresults(c: dict, *, nmols_solute, nmols_solvent, autocorrelation, n_ran
         r.sum_rdf_count_random = np.cumsum(r.rdf_count_random)
         r.kb_rdf = ANGS3_TO_CM3_PER_MOL * (1 / r.density_solvent_bulk) * (r.sum_rdf_count - r.sum_rdf_count_random)
     return r
+
+
+# ---- prototype of the planned device-side XTC decoder (oracle/xtc_two_phase.c) -------------------------------------
+def xtc_two_phase_decode(block: bytes, natoms: int):
+    """(xyz fp32 [natoms,3] in Angstrom, group bytes) of one compressed XTC coordinate block via the two-phase scheme:
+    serial skeleton walk (1 byte per group) + independent per-group decode."""
+    L = lib()
+    buf = np.frombuffer(block, dtype=np.uint8)
+    codes = np.zeros(natoms, dtype=np.uint8)
+    L.xtc_skeleton.restype = C.c_int
+    ng = L.xtc_skeleton(_p(buf), C.c_size_t(buf.size), C.c_int(natoms), _p(codes), C.c_int(codes.size))
+    if ng <= 0:
+        raise ValueError("malformed XTC coordinate block")
+    xyz = np.zeros((natoms, 3), dtype=np.float32)
+    L.xtc_decode_from_skeleton.restype = C.c_int
+    ok = L.xtc_decode_from_skeleton(_p(buf), C.c_size_t(buf.size), C.c_int(natoms), _p(codes), C.c_int(ng), _p(xyz))
+    if not ok:
+        raise ValueError("skeleton does not match the block")
+    return xyz, codes[:ng].copy()
