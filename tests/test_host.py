@@ -413,3 +413,29 @@ def test_xtc_writer_and_reader_conform_to_the_reference_fixture():
         off += 56 + len(blk)
     assert off == len(raw)
     f.close()
+
+
+def test_c_example_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/mddf_dcd.c: the C ABI from plain C (header is valid C, every symbol links); without a CUDA device the
+    program must stop at cmx_create with the library's error -- there is no CPU fallback behind the ABI."""
+    from common import namd, write_dcd
+    from cmx_b200 import engine
+    engine.build()
+    exe = str(tmp_path / "mddf_dcd")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "mddf_dcd.c"),
+                    "-L", os.path.dirname(engine.LIB_PATH), "-lcmx_b200", "-Wl,-rpath," + os.path.dirname(engine.LIB_PATH),
+                    "-Wl,--allow-shlib-undefined", "-o", exe], check=True)
+    d = namd()
+    path = str(tmp_path / "t.dcd")
+    write_dcd(path, np.concatenate([d["protein"], d["tmao"]], axis=1), d["cells"])
+    r = subprocess.run([exe, path, "1", "1463", "1464", "2534", "14"], capture_output=True, text=True)
+    assert "3997 atoms, 3 frames" in r.stdout
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        assert r.returncode == 0 and "solvent molecules within" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 1 and "cmx_create" in r.stderr, r.stdout + r.stderr
