@@ -66,14 +66,15 @@ struct NumaPrefer {
 template <class T>
 struct DevBuf {
     T *p = nullptr; size_t n = 0;
-    cudaError_t ensure(size_t want, bool zero = false) {
+    // grow-only; a fresh allocation can be zeroed ON `stream` (ordered before the kernels that will use it)
+    cudaError_t ensure(size_t want, bool zero = false, cudaStream_t stream = nullptr) {
         if (want <= n && p) return cudaSuccess;
         if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; n = 0; }
         size_t cap = want + want / 4 + 64;
         cudaError_t e = cudaMalloc(&p, cap * sizeof(T));
         if (e != cudaSuccess) return e;
         n = cap;
-        if (zero) return cudaMemset(p, 0, cap * sizeof(T));
+        if (zero) return cudaMemsetAsync(p, 0, cap * sizeof(T), stream);
         return cudaSuccess;
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
@@ -83,34 +84,60 @@ struct DevBuf {
 
 struct cmx_feed;   // native DCD feed ring + group-reduction scratch (cmx_feed.inl)
 
-// Everything one in-flight frame needs: its compute stream and scratch buffers.
+// Device scratch of ONE frame in flight on the grid path (the pointers of a GridFrame descriptor).
+struct GridSlot {
+    DevBuf<int> sc, cell_count, cell_start, qcell_count, qcell_start, worklist, rand_worklist, bulk_idx;
+    DevBuf<float4> sorted, qpos, qsorted, res;
+    DevBuf<u64> bits, def_real, def_rand, scan_state;
+    DevBuf<float2> def_real_info, def_rand_info;
+    DevBuf<double> xexact;
+    DevBuf<unsigned short> edt_xy;
+    DevBuf<float> lbd2;
+    DevBuf<MdRec> list;
+    DevBuf<unsigned char> tile_valid;
+    void release() {
+        sc.release(); cell_count.release(); cell_start.release(); qcell_count.release(); qcell_start.release(); worklist.release();
+        rand_worklist.release(); bulk_idx.release(); sorted.release(); qpos.release(); qsorted.release(); res.release(); bits.release();
+        def_real.release(); def_rand.release(); scan_state.release(); def_real_info.release(); def_rand_info.release(); xexact.release();
+        edt_xy.release(); lbd2.release(); list.release(); tile_valid.release();
+    }
+};
+
+// A frame (x one solute molecule) that was submitted and waits for its batch to be launched.
+struct PendingFrame {
+    Geom g;
+    const float *xs, *xv;
+    uint32_t frame;
+    int isolute, skip_mol, nrand_k;
+    double weight;
+};
+
+// One batch of frames in flight: a compute stream, the frame slots of the batch and their descriptors.  Frames are
+// collected until the batch is full (or a sync / weight change / ring wrap-around forces it out), then every kernel of
+// the per-frame sequence is launched ONCE for the whole batch.  Several batch contexts are in flight on their own streams.
 struct FrameCtx {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_end = nullptr;
-    DevBuf<int> d_cell_count, d_cell_start;
-    DevBuf<float4> d_sorted;
-    DevBuf<u64> d_occ;                 // [8 scalars][cull bitmap][row bitmap]
-    DevBuf<float4> d_qpos, d_qsorted, d_res;   // query atoms of the current phase: positions, tile order, results
-    DevBuf<int> d_qcell_count, d_qcell_start;
-    DevBuf<double> d_xexact;
-    DevBuf<unsigned char> d_edt_x;
-    DevBuf<unsigned short> d_edt_xy;
-    DevBuf<float> d_lbd2;
+    cudaEvent_t ev_end = nullptr, ev_fd = nullptr;
+    bool fd_busy = false;
+    std::vector<GridSlot> slots;
+    GridFrame *h_fd = nullptr, *d_fd = nullptr;     // pinned / device descriptor arrays [batch]
+    std::vector<PendingFrame> pending;
+    std::vector<cudaEvent_t> release_events;        // recorded on `stream` once the pending frames' kernels are enqueued
+    // molecule-pair path (one frame per context at a time) and shared odds and ends
     DevBuf<MdRec> d_list;
-    DevBuf<int> d_worklist, d_rand_worklist, d_bulk_idx;
-    DevBuf<u64> d_def_real, d_def_rand;
-    DevBuf<float2> d_def_real_info, d_def_rand_info;
-    DevBuf<int> d_scalars;          // [0] work_count, [1] rand_work_count, [2] def_real, [3] def_rand, [4] n_bulk, [5] rmax bits, [8] sticky overflow
+    DevBuf<int> d_scalars;                          // [8] sticky overflow flag of the pair path
     DevBuf<unsigned char> d_cub_tmp;
     PairScratch pairs;
-    int *h_scalars = nullptr;       // pinned mirror (rmax feedback)
+    int *h_scalars = nullptr;                       // pinned mirror (rmax feedback)
     void release() {
-        d_cell_count.release(); d_cell_start.release(); d_sorted.release(); d_occ.release();
-        d_qpos.release(); d_qsorted.release(); d_res.release(); d_qcell_count.release(); d_qcell_start.release(); d_xexact.release(); d_edt_x.release();
-        d_edt_xy.release(); d_lbd2.release(); d_list.release(); d_worklist.release(); d_rand_worklist.release();
-        d_bulk_idx.release(); d_def_real.release(); d_def_rand.release(); d_def_real_info.release(); d_def_rand_info.release(); d_scalars.release(); d_cub_tmp.release();
+        for (auto &s : slots) s.release();
+        slots.clear();
+        d_list.release(); d_scalars.release(); d_cub_tmp.release();
+        if (h_fd) cudaFreeHost(h_fd);
+        if (d_fd) cudaFree(d_fd);
         if (h_scalars) cudaFreeHost(h_scalars);
         if (ev_end) cudaEventDestroy(ev_end);
+        if (ev_fd) cudaEventDestroy(ev_fd);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -126,7 +153,9 @@ struct cmx_handle {
     int Kdiv = 2;
     double side = 0, sidex = 0, cside = 0, qside = 0;
     cudaStream_t s_copy = nullptr;
-    int64_t submitted = 0;
+    int batch = 1;                  // frames per batch (grid path); 1 on the molecule-pair path
+    int fill = 0;                   // index of the batch context being filled
+    uint32_t scan_epoch = 0;        // launch number of the chained scans (tags their tile states)
     std::vector<Slot> ring;
     int next_slot = 0, acquired = -1;
     // static device data
@@ -140,13 +169,13 @@ struct cmx_handle {
     // per-frame scratch lives in FrameCtx (one per compute stream)
     DevBuf<MdRec> d_rand_list, d_list_all;   // parity hooks (keep_lists => one stream)
     DevBuf<u64> d_stats;            // [0] pair_evals, [1] deferred total
-    std::vector<FrameCtx *> ctx;    // frames are dealt round-robin to the contexts; kernels of different frames overlap
-    FrameCtx *cur = nullptr;
+    std::vector<FrameCtx *> ctx;    // batches are dealt round-robin to the contexts; kernels of different batches overlap
+    FrameCtx *cur = nullptr;        // context whose kernels are being enqueued (launch / prof_* use its stream)
     int active_ctx = 0;             // contexts actually used (option "active_streams"; 0 = all)
     float rmax_bound = 0.f;
     int sample_chunk = 1;           // samples of the random phase per pass (grid path)
     // bookkeeping
-    double cur_weight = 1.0; bool have_weight = false;
+    double w0 = 1.0; bool have_weight = false;   // weight of the first frame: the integer counters are hits at this weight
     double volume_total = 0, sum_weights = 0;
     cmx_stats stats{};
     bool count_pairs = false, profile = false;
@@ -161,6 +190,10 @@ struct cmx_handle {
     int search_grid[2] = {148 * 5, 148 * 4};   // one resident wave of k_tile_search<false/true> (occupancy query at create)
     int search_blocks_env = 0;
     cmx_feed *feed = nullptr;
+    // CMX_TRACE=skip:count -- device timeline of `count` batches after `skip` flushes (events between the launches), printed at sync
+    int trace_skip = -1, trace_count = 0; bool tracing = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> trace_events;
+    bool poll_stop_file = true, stopped_by_file = false;   // native feed: the reference's cooperative stop file
     int numa_node = -1;                        // NUMA node of the GPU (-1 unknown): pinned staging memory is placed there
 };
 
@@ -304,131 +337,209 @@ void prof_collect(cmx_handle *h) {
     h->prof_used = 0;
 }
 
-// one search phase (real or random) over the molecules of a work list: tile the query atoms, search, combine
-template <bool RANDOM>
-int search_phase(cmx_handle *h, const Geom &g, const float *xs, const float *xv, const int *worklist, const int *work_count,
-                 size_t max_atoms, MdRec *list, u64 *deferred, float2 *def_info, int *def_count, int tag, int s0) {
-    FrameCtx &x = *h->cur;
-    size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
-    // (query positions, res and the per-cell counts were produced by k_gen_*)
-    if (nqc + 1 <= CMX_SCAN_SMALL_MAX)
-        launch(h, k_scan_small<TileCountOp>, dim3(1), dim3(CMX_SCAN_THREADS), (const int *)x.d_qcell_count.p, x.d_qcell_start.p, (int)(nqc + 1), TileCountOp());
-    else {
-        size_t tmp_bytes = x.d_cub_tmp.n;
-        cub::TransformInputIterator<int, TileCountOp, const int *> tiles_of((const int *)x.d_qcell_count.p, TileCountOp());
-        CK(cub::DeviceScan::ExclusiveSum(x.d_cub_tmp.p, tmp_bytes, tiles_of, x.d_qcell_start.p, (int)(nqc + 1), x.stream));
-        h->stats.kernel_launches += 2;
+void trace_mark(cmx_handle *h, const char *name) {
+    if (!h->tracing) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->cur->stream);
+    h->trace_events.push_back({name, e});
+}
+void trace_report(cmx_handle *h) {
+    if (h->trace_events.empty()) return;
+    std::vector<std::pair<std::string, double>> agg;
+    double total = 0;
+    for (size_t k = 1; k < h->trace_events.size(); ++k) {
+        float ms = 0;
+        const char *name = h->trace_events[k].first;
+        if (std::string(name) == "begin") continue;
+        if (cudaEventElapsedTime(&ms, h->trace_events[k - 1].second, h->trace_events[k].second) != cudaSuccess) continue;
+        total += ms;
+        bool found = false;
+        for (auto &a : agg) if (a.first == name) { a.second += ms; found = true; }
+        if (!found) agg.push_back({name, (double)ms});
     }
-    // worst case: every atom in a tile of its own cell's last, partially filled tile
-    size_t slots = std::min(max_atoms + 32 * nqc, x.d_qsorted.n);
-    CK(cudaMemsetAsync(x.d_qsorted.p, 0xff, sizeof(float4) * slots, x.stream));
-    int nb = (int)std::min<size_t>((max_atoms + 255) / 256, (size_t)h->num_sms * 8);
-    launch(h, k_qscatter, dim3(std::max(nb, 1)), dim3(256), g, h->P, work_count, (const float4 *)x.d_qpos.p, x.d_qcell_count.p,
-           (const int *)x.d_qcell_start.p, x.d_qsorted.p);
-    cudaEvent_t pe = prof_begin(h, tag);
+    (void)cudaGetLastError();
+    std::fprintf(stderr, "[cmx trace] %zu marks, %.1f us in total (interval = previous mark -> this mark, launch gaps included)\n", h->trace_events.size(), total * 1e3);
+    for (auto &a : agg) std::fprintf(stderr, "[cmx trace] %10.1f us %5.1f%%  %s\n", a.second * 1e3, 100.0 * a.second / std::max(total, 1e-12), a.first.c_str());
+    for (auto &e : h->trace_events) cudaEventDestroy(e.second);
+    h->trace_events.clear();
+}
+
+// number of contexts frames are dealt to (option "active_streams" restricts it for single-stream measurements)
+int nctx_active(const cmx_handle *h) { return h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size(); }
+
+template <class K, class... Args>
+void launch_y(cmx_handle *h, K kernel, unsigned gx, unsigned nb, unsigned threads, Args... args) {
+    kernel<<<dim3(std::max(gx, 1u), nb), dim3(threads), 0, h->cur->stream>>>(args...);
+    h->stats.kernel_launches++;
+}
+
+// tile the query atoms of the batch's work lists, search, combine (one phase: real or random)
+template <bool RANDOM>
+int search_phase(cmx_handle *h, const GridFrame *fd, unsigned nb, size_t max_atoms, size_t nqc_max, int s0) {
+    const unsigned sms = (unsigned)h->num_sms;
+    launch_y(h, k_chain_scan<ScanTiles<RANDOM>>, (unsigned)std::min<size_t>((nqc_max + CMX_SCAN_TILE) / CMX_SCAN_TILE, sms * 2), nb, CMX_SCAN_THREADS,
+             fd, h->P, ++h->scan_epoch);
+    trace_mark(h, RANDOM ? "scan_tiles<rand>" : "scan_tiles<real>");
+    launch_y(h, k_qscatter<RANDOM>, (unsigned)std::min<size_t>((max_atoms + 255) / 256, (size_t)sms * 8), nb, 256u, fd, h->P);
+    trace_mark(h, RANDOM ? "qscatter<rand>" : "qscatter<real>");
+    cudaEvent_t pe = prof_begin(h, RANDOM ? 1 : 0);
     u64 *pev = h->count_pairs ? h->d_stats.p : nullptr;
-    int *tile_queue = (int *)x.d_occ.p + (RANDOM ? 7 : 6);   // per-frame scalars, zeroed with the bitmaps
-    // Each of the n frames in flight gets 1/n of the resident block slots of an SM: the searches of several frames
-    // then share the SMs with the small kernels of the other frames instead of one search filling every register
-    // file for its whole duration (measured on C2, 8 streams: 5 blocks/SM 8.2 k frames/s, 2 -> 8.9 k, 1 -> 9.4 k).
-    const int nfly = h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size();
-    auto grid_of = [&](int k) {
-        if (h->search_blocks_env > 0) return h->num_sms * h->search_blocks_env;
-        int per_sm = h->search_grid[k] / h->num_sms;
-        return h->num_sms * std::max(1, (per_sm + nfly - 1) / nfly);
-    };
-    if (pev) launch(h, k_tile_search<true>, dim3(grid_of(1)), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                    (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue);
-    else launch(h, k_tile_search<false>, dim3(grid_of(0)), dim3(256), g, (const int *)x.d_cell_start.p, (const float4 *)x.d_sorted.p,
-                (const u64 *)(x.d_occ.p + 4 + (size_t)g.ncy * g.ncz * g.cw), (const float4 *)x.d_qsorted.p, (const int *)x.d_qcell_start.p, (int)nqc, x.d_res.p, pev, tile_queue);
+    // The tiles of the whole batch are one queue.  Each of the n batches in flight gets 1/n of the resident block
+    // slots of an SM: the searches of several batches then share the SMs with the small kernels of the others
+    // (measured on C2 in round 1: 5 blocks/SM 8.2 k frames/s, 2 -> 8.9 k, 1 -> 9.4 k with 8 frames in flight).
+    const int nfly = nctx_active(h);
+    const int k = pev ? 1 : 0;
+    int per_sm = h->search_blocks_env > 0 ? h->search_blocks_env : std::max(1, (h->search_grid[k] / h->num_sms + nfly - 1) / nfly);
+    const unsigned grid = sms * (unsigned)per_sm;
+    if (pev) k_tile_search<true, RANDOM><<<grid, 256, 0, h->cur->stream>>>(fd, (int)nb, pev);
+    else k_tile_search<false, RANDOM><<<grid, 256, 0, h->cur->stream>>>(fd, (int)nb, pev);
+    h->stats.kernel_launches++;
     prof_end(h, pe);
-    launch(h, k_finalise<RANDOM>, dim3(h->num_sms * 8), dim3(128), g, h->P, xs, xv, (const float4 *)x.d_res.p,
-           (const double *)(RANDOM ? x.d_xexact.p : nullptr), worklist, work_count, list, deferred, def_info, def_count, s0);
+    trace_mark(h, RANDOM ? "tile_search<rand>" : "tile_search<real>");
+    launch_y(h, k_finalise<RANDOM>, (unsigned)std::min<size_t>((max_atoms / std::max(1, h->P.nv_apm) + 127) / 128, (size_t)sms * 8), nb, 128u, fd, h->P, s0);
+    trace_mark(h, RANDOM ? "finalise<rand>" : "finalise<real>");
     return CMX_OK;
 }
 
-// ---- one frame on the grid path (mddf_frame!, src/mddf.jl:361-429) --------------------------------
-int frame_grid_path(cmx_handle *h, const float *d_solute, const float *d_solvent, uint32_t frame, const Geom &g) {
+// ---- launch the pending frames of one batch context (mddf_frame!, src/mddf.jl:361-429, for every frame of the batch) ----
+int flush_ctx(cmx_handle *h, FrameCtx *x) {
+    if (x->pending.empty()) return CMX_OK;
     const cmx_config &c = h->cfg;
+    h->cur = x;
+    const unsigned nb = (unsigned)x->pending.size();
+    const unsigned sms = (unsigned)h->num_sms;
     const int ns_apm = c.solute_natomspermol, nv_mols = c.solvent_nmols;
-    size_t ncells = (size_t)g.nx * g.ny * g.nz, ncc = (size_t)g.ncx * g.ncy * g.ncz;
-    size_t occ_words = (size_t)g.ncy * g.ncz * g.cw;
-    CK(h->cur->d_cell_count.ensure(ncells + 1, true));
-    CK(h->cur->d_cell_start.ensure(ncells + 1));
-    // [8 per-frame scalars][cull-grid bitmap][row bitmap] share one buffer: one memset per solute molecule
-    CK(h->cur->d_occ.ensure(4 + occ_words + ((size_t)g.ny * g.nz * g.rw)));
-    CK(h->cur->d_edt_xy.ensure(ncc)); CK(h->cur->d_lbd2.ensure(ncc));
-    size_t rowmask_words = (size_t)g.ny * g.nz * g.rw;
-    u64 *occ_p = h->cur->d_occ.p + 4, *rowmask_p = occ_p + occ_words;
-    size_t nqc = (size_t)g.nqx * g.nqy * g.nqz;
-    CK(h->cur->d_qcell_count.ensure(nqc + 1, true)); CK(h->cur->d_qcell_start.ensure(nqc + 1));
-    {   // tile array: atoms + padding of each cell's last tile
-        size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(c.coordination_number_only ? 0 : h->sample_chunk) * h->nv_atoms);
-        CK(h->cur->d_qsorted.ensure(maxq + 32 * nqc));
-    }
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
-    int *sc = (int *)h->cur->d_occ.p;
-    for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
-        const float *xs = d_solute + (size_t)3 * ns_apm * isolute;
-        const int skip = c.autocorrelation ? isolute : -1;
-        int nrand_k = 0;
-        if (c.solute_nmols == 1) nrand_k = nrand;
-        else for (int s = 0; s < nrand; ++s) nrand_k += (ref_solute_host(h, frame, (uint32_t)s) == isolute);
-        CK(cudaMemsetAsync(h->cur->d_occ.p, 0, (4 + occ_words + rowmask_words) * sizeof(u64), h->cur->stream));
-        int tb = 128;
-        launch(h, k_solute_bin<false>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
-               (const int *)nullptr, occ_p, rowmask_p, (float4 *)nullptr);
-        if (ncells + 1 <= CMX_SCAN_SMALL_MAX)
-            launch(h, k_scan_small<IdentityOp>, dim3(1), dim3(CMX_SCAN_THREADS), (const int *)h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), IdentityOp());
-        else {
-            size_t tmp_bytes = h->cur->d_cub_tmp.n;
-            CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, h->cur->d_cell_count.p, h->cur->d_cell_start.p, (int)(ncells + 1), h->cur->stream));
-            h->stats.kernel_launches += 2;
-        }
-        launch(h, k_solute_bin<true>, dim3((ns_apm + tb - 1) / tb), dim3(tb), g, xs, ns_apm, h->cur->d_cell_count.p,
-               (const int *)h->cur->d_cell_start.p, occ_p, rowmask_p, h->cur->d_sorted.p);
-        launch(h, k_edt_xy, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const u64 *)occ_p, h->cur->d_edt_xy.p);
-        launch(h, k_edt_z, dim3((unsigned)((ncc + 255) / 256)), dim3(256), g, (const unsigned short *)h->cur->d_edt_xy.p, h->cur->d_lbd2.p);
-        launch(h, k_filter_real, dim3((nv_mols + 127) / 128), dim3(128), g, h->P, d_solvent, skip,
-               (const float *)h->cur->d_lbd2.p, h->cur->d_list.p, h->cur->d_worklist.p, sc + 0, sc + 5);
-        if (h->stats.frames < 64 || (h->stats.frames & 15) == 0)   // host-side bound for the NEXT frames' cull window (monotone)
-            CK(cudaMemcpyAsync(h->cur->h_scalars + 5, sc + 5, sizeof(int), cudaMemcpyDeviceToHost, h->cur->stream));
-        launch(h, k_gen_real, dim3(h->num_sms * 4), dim3(256), g, h->P, d_solvent, (const float *)h->cur->d_lbd2.p,
-               (const int *)h->cur->d_worklist.p, (const int *)(sc + 0), h->cur->d_qpos.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
-        { int rc = search_phase<false>(h, g, xs, d_solvent, h->cur->d_worklist.p, sc + 0, h->nv_atoms, h->cur->d_list.p,
-                                       h->cur->d_def_real.p, h->cur->d_def_real_info.p, sc + 2, 0, 0); if (rc) return rc; }
-        launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
-               (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-               (const u64 *)h->cur->d_def_real.p, (const float2 *)h->cur->d_def_real_info.p, (const int *)(sc + 2), h->cur->d_list.p, (MdRec *)nullptr,
-               nrand_k == 0 ? h->d_stats.p : (u64 *)nullptr, (const int *)(sc + 2), (const int *)nullptr);
-        if (c.keep_lists)
-            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)isolute * nv_mols, h->cur->d_list.p, sizeof(MdRec) * (size_t)nv_mols,
-                               cudaMemcpyDeviceToDevice, h->cur->stream));
-        if (nrand_k == 0) continue;
-        // bulk list of this solute molecule, ascending molecule index (src/mddf.jl:406-415)
-        size_t tmp_bytes2 = h->cur->d_cub_tmp.n;
-        BulkPred pred{(const MdRec *)h->cur->d_list.p, skip, h->P.usecutoff, h->P.dbulk};
-        CK(cub::DeviceSelect::If(h->cur->d_cub_tmp.p, tmp_bytes2, cub::CountingInputIterator<int>(0), h->cur->d_bulk_idx.p, sc + 4,
-                                 nv_mols, pred, h->cur->stream));
-        h->stats.kernel_launches += 2;
+    if (x->fd_busy) { CK(cudaEventSynchronize(x->ev_fd)); x->fd_busy = false; }   // previous descriptor upload of this context
+    size_t ncells_max = 0, ncull_max = 0, nqc_max = 0, bits_max = 0;
+    bool any_random = false;
+    for (unsigned k = 0; k < nb; ++k) {
+        const PendingFrame &pf = x->pending[k];
+        const Geom &g = pf.g;
+        GridSlot &S = x->slots[k];
+        const size_t ncells = (size_t)g.nx * g.ny * g.nz, ncc = (size_t)g.ncx * g.ncy * g.ncz, nqc = (size_t)g.nqx * g.nqy * g.nqz;
+        const size_t occ_words = (size_t)g.ncy * g.ncz * g.cw, row_words = (size_t)g.ny * g.nz * g.rw;
+        CK(S.cell_count.ensure(ncells + 1, true, x->stream)); CK(S.cell_start.ensure(ncells + 1));
+        CK(S.bits.ensure(occ_words + row_words));
+        CK(S.edt_xy.ensure(ncc)); CK(S.lbd2.ensure(ncc));
+        CK(S.qcell_count.ensure(nqc + 1, true, x->stream)); CK(S.qcell_start.ensure(nqc + 1));
+        const size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(nrand ? h->sample_chunk : 0) * h->nv_atoms);
+        CK(S.qsorted.ensure(maxq + 32 * nqc)); CK(S.tile_valid.ensure(maxq / 32 + nqc + 1));
+        CK(S.scan_state.ensure(std::max(std::max(ncells, nqc) + 1, (size_t)nv_mols) / CMX_SCAN_TILE + 2, true, x->stream));
+        GridFrame &F = x->h_fd[k];
+        F.g = g; F.xs = pf.xs; F.xv = pf.xv;
+        F.sc = S.sc.p; F.bits = S.bits.p; F.occ = S.bits.p; F.rowmask = S.bits.p + occ_words;
+        F.cell_count = S.cell_count.p; F.cell_start = S.cell_start.p; F.sorted = S.sorted.p;
+        F.edt_xy = S.edt_xy.p; F.lbd2 = S.lbd2.p;
+        F.qpos = S.qpos.p; F.qsorted = S.qsorted.p; F.res = S.res.p; F.xexact = S.xexact.p;
+        F.qcell_count = S.qcell_count.p; F.qcell_start = S.qcell_start.p; F.tile_valid = S.tile_valid.p;
+        F.list = S.list.p; F.rand_list = c.keep_lists ? h->d_rand_list.p : nullptr;
+        F.worklist = S.worklist.p; F.rand_worklist = S.rand_worklist.p; F.bulk_idx = S.bulk_idx.p;
+        F.def_real = S.def_real.p; F.def_rand = S.def_rand.p; F.def_real_info = S.def_real_info.p; F.def_rand_info = S.def_rand_info.p;
+        F.scan_state = S.scan_state.p;
+        F.bits_words = (long long)(occ_words + row_words);
+        F.ncells = (int)ncells; F.nqcells = (int)nqc; F.ncull = (int)ncc;
+        F.frame = pf.frame; F.isolute = pf.isolute; F.skip_mol = pf.skip_mol; F.nrand_k = pf.nrand_k; F.pad0 = 0; F.weight = pf.weight; F.pad1 = 0;
+        ncells_max = std::max(ncells_max, ncells); ncull_max = std::max(ncull_max, ncc); nqc_max = std::max(nqc_max, nqc);
+        bits_max = std::max(bits_max, occ_words + row_words);
+        any_random |= pf.nrand_k > 0;
+    }
+    CK(cudaMemcpyAsync(x->d_fd, x->h_fd, sizeof(GridFrame) * nb, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaEventRecord(x->ev_fd, x->stream)); x->fd_busy = true;
+    if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, x->stream)); h->ev_first_set = true; }
+    const GridFrame *fd = x->d_fd;
+    if (h->trace_skip >= 0) { if (h->trace_skip-- == 0) h->tracing = true; }
+    if (h->tracing) { if (h->trace_count-- <= 0) h->tracing = false; }
+    trace_mark(h, "begin");
+    if (c.keep_lists && h->d_rand_list.p && x->pending[0].isolute == 0)   // (keep_lists: one frame x one solute molecule per batch)
+        CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, x->stream));
+    // ---- solute grid + cull grid
+    launch_y(h, k_zero_frame, (unsigned)std::min<size_t>((bits_max + 255) / 256, 64), nb, 256u, fd);
+    trace_mark(h, "zero_frame");
+    launch_y(h, k_solute_bin<false>, (unsigned)((ns_apm + 127) / 128), nb, 128u, fd, ns_apm);
+    trace_mark(h, "solute_bin<count>");
+    launch_y(h, k_chain_scan<ScanCells>, (unsigned)std::min<size_t>((ncells_max + CMX_SCAN_TILE) / CMX_SCAN_TILE, sms * 2), nb, CMX_SCAN_THREADS,
+             fd, h->P, ++h->scan_epoch);
+    trace_mark(h, "scan_cells");
+    launch_y(h, k_solute_bin<true>, (unsigned)((ns_apm + 127) / 128), nb, 128u, fd, ns_apm);
+    trace_mark(h, "solute_bin<scatter>");
+    const unsigned gcull = (unsigned)std::min<size_t>((ncull_max + 255) / 256, (size_t)sms * 16);
+    launch_y(h, k_edt_xy, gcull, nb, 256u, fd);
+    trace_mark(h, "edt_xy");
+    launch_y(h, k_edt_z, gcull, nb, 256u, fd);
+    trace_mark(h, "edt_z");
+    // ---- real phase
+    launch_y(h, k_filter_real, (unsigned)((nv_mols + 127) / 128), nb, 128u, fd, h->P);
+    trace_mark(h, "filter_real");
+    if (h->stats.frames < 64 || (h->stats.frames & 15) < (int64_t)nb)   // host-side bound for the NEXT frames' cull window (monotone)
+        CK(cudaMemcpyAsync(x->h_scalars + 5, x->slots[0].sc.p + SC_RMAX, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
+    launch_y(h, k_gen_real, (unsigned)std::min<size_t>((h->nv_atoms + 255) / 256, (size_t)sms * 4), nb, 256u, fd, h->P);
+    trace_mark(h, "gen_real");
+    { int rc = search_phase<false>(h, fd, nb, h->nv_atoms, nqc_max, 0); if (rc) return rc; }
+    launch_y(h, k_resolve<false>, std::max(16u, sms * 2 / nb), nb, (unsigned)CMX_RESOLVE_THREADS, fd, h->P, h->d_stats.p);
+    trace_mark(h, "resolve<real>");
+    if (c.keep_lists)
+        for (unsigned k = 0; k < nb; ++k)
+            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)x->pending[k].isolute * nv_mols, x->slots[k].list.p, sizeof(MdRec) * (size_t)nv_mols,
+                               cudaMemcpyDeviceToDevice, x->stream));
+    if (any_random) {
+        // bulk list of every frame, ascending molecule index (src/mddf.jl:406-415): an ordered compaction
+        launch_y(h, k_chain_scan<ScanBulk>, (unsigned)std::min<size_t>(((size_t)nv_mols + CMX_SCAN_TILE - 1) / CMX_SCAN_TILE, sms * 2), nb, CMX_SCAN_THREADS,
+                 fd, h->P, ++h->scan_epoch);
+        trace_mark(h, "scan_bulk");
         // the random phase runs over chunks of samples so that the scratch (query atoms of the surviving
         // random molecules) stays bounded for any n_random_samples; normally one chunk
         for (int s0 = 0; s0 < nrand; s0 += h->sample_chunk) {
             const int s1 = std::min(nrand, s0 + h->sample_chunk);
-            if (s0 > 0) { CK(cudaMemsetAsync(sc + 1, 0, sizeof(int), h->cur->stream)); CK(cudaMemsetAsync(sc + 3, 0, sizeof(int), h->cur->stream));
-                          CK(cudaMemsetAsync(sc + 7, 0, sizeof(int), h->cur->stream)); }
-            launch(h, k_filter_rand, dim3((unsigned)((nv_mols + 255) / 256), (unsigned)std::min(s1 - s0, 65535)), dim3(256), g, h->P, frame, isolute, skip,
-                   s0, s1, (const float *)h->cur->d_lbd2.p, (const int *)(sc + 5), h->cur->d_rand_worklist.p, sc + 1);
-            launch(h, k_gen_rand, dim3(h->num_sms * 8), dim3(128), g, h->P, frame, s0, d_solvent, (const float *)h->cur->d_lbd2.p,
-                   (const int *)h->cur->d_rand_worklist.p, (const int *)(sc + 1), (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-                   h->cur->d_qpos.p, h->cur->d_xexact.p, h->cur->d_res.p, h->cur->d_qcell_count.p);
-            { int rc = search_phase<true>(h, g, xs, d_solvent, h->cur->d_rand_worklist.p, sc + 1, (size_t)(s1 - s0) * h->nv_atoms,
-                                          c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->cur->d_def_rand.p, h->cur->d_def_rand_info.p,
-                                          sc + 3, 1, s0); if (rc) return rc; }
-            launch(h, k_resolve, dim3(h->num_sms * 2), dim3(CMX_RESOLVE_THREADS), g, h->P, frame, xs, d_solvent, (const float4 *)h->cur->d_sorted.p,
-                   (const int *)h->cur->d_cell_start.p, (int)ncells, (const int *)h->cur->d_bulk_idx.p, (const int *)(sc + 4),
-                   (const u64 *)h->cur->d_def_rand.p, (const float2 *)h->cur->d_def_rand_info.p, (const int *)(sc + 3), (MdRec *)nullptr,
-                   c.keep_lists ? h->d_rand_list.p : (MdRec *)nullptr, h->d_stats.p, (const int *)(s0 == 0 ? sc + 2 : nullptr), (const int *)(sc + 3));
+            if (s0 > 0) { k_reset_rand<<<nb, 32, 0, x->stream>>>(fd); h->stats.kernel_launches++; }
+            k_filter_rand<<<dim3((unsigned)((nv_mols + 255) / 256), nb, (unsigned)std::min(s1 - s0, 64)), 256, 0, x->stream>>>(fd, h->P, s0, s1);
+            h->stats.kernel_launches++;
+            trace_mark(h, "filter_rand");
+            const size_t max_items = (size_t)(s1 - s0) * (size_t)nv_mols;
+            launch_y(h, k_gen_rand, (unsigned)std::min<size_t>((max_items + 127) / 128, (size_t)sms * 8), nb, 128u, fd, h->P, s0);
+    trace_mark(h, "gen_rand");
+            { int rc = search_phase<true>(h, fd, nb, (size_t)(s1 - s0) * h->nv_atoms, nqc_max, s0); if (rc) return rc; }
+            launch_y(h, k_resolve<true>, std::max(16u, sms * 2 / nb), nb, (unsigned)CMX_RESOLVE_THREADS, fd, h->P, h->d_stats.p);
+    trace_mark(h, "resolve<rand>");
+        }
+    }
+    for (cudaEvent_t e : x->release_events) CK(cudaEventRecord(e, x->stream));
+    x->release_events.clear();
+    x->pending.clear();
+    CK(cudaGetLastError());
+    return CMX_OK;
+}
+
+int flush_all(cmx_handle *h) {
+    for (FrameCtx *x : h->ctx) { int rc = flush_ctx(h, x); if (rc) return rc; }
+    return CMX_OK;
+}
+
+// an event that is recorded when a pending frame's kernels are enqueued: make sure that has happened
+int flush_if_pending(cmx_handle *h, cudaEvent_t e) {
+    for (FrameCtx *x : h->ctx)
+        for (cudaEvent_t p : x->release_events)
+            if (p == e) return flush_ctx(h, x);
+    return CMX_OK;
+}
+
+// ---- one frame on the grid path: queue it (x each solute molecule) into the batch being filled ----------------------
+int queue_grid_frame(cmx_handle *h, const float *d_solute, const float *d_solvent, uint32_t frame, const Geom &g, double weight, cudaEvent_t release) {
+    const cmx_config &c = h->cfg;
+    const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
+    for (int isolute = 0; isolute < c.solute_nmols; ++isolute) {
+        FrameCtx *x = h->ctx[(size_t)h->fill];
+        PendingFrame pf;
+        pf.g = g; pf.xs = d_solute + (size_t)3 * c.solute_natomspermol * isolute; pf.xv = d_solvent; pf.frame = frame;
+        pf.isolute = isolute; pf.skip_mol = c.autocorrelation ? isolute : -1; pf.weight = weight;
+        pf.nrand_k = 0;
+        if (c.solute_nmols == 1) pf.nrand_k = nrand;
+        else for (int s = 0; s < nrand; ++s) pf.nrand_k += (ref_solute_host(h, frame, (uint32_t)s) == isolute);
+        x->pending.push_back(pf);
+        if (release && isolute == c.solute_nmols - 1) x->release_events.push_back(release);
+        if ((int)x->pending.size() >= h->batch) {
+            // a frame's solute molecules may straddle batches: its buffers are released with the LAST of them
+            int rc = flush_ctx(h, x); if (rc) return rc;
+            h->fill = (h->fill + 1) % nctx_active(h);
         }
     }
     return CMX_OK;
@@ -445,41 +556,37 @@ __global__ void k_emit(const u64 *cnt, const double *acc, double *out, size_t n,
     out[k] = (acc ? acc[k] : 0.0) + s * (double)cnt[k];
 }
 
-__global__ void k_fold(const u64 *cnt, double *acc, size_t n, size_t half_lo, size_t half_hi, double w) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    double s = (k >= half_lo && k < half_hi) ? w / 2 : w;
-    acc[k] += s * (double)cnt[k];
-}
-
 int sync_all(cmx_handle *h) {
+    { int rc = flush_all(h); if (rc) return rc; }
     CK(cudaStreamSynchronize(h->s_copy));
     for (FrameCtx *x : h->ctx) CK(cudaStreamSynchronize(x->stream));
     return CMX_OK;
 }
 
-int fold_weight(cmx_handle *h) {
-    { int rc = sync_all(h); if (rc) return rc; }   // every stream adds into the same integer block
-    // acc += w * cnt ; cnt = 0  (the counters are sums of frame weights, src/update_counters.jl:47,60)
-    if (!h->acc_used) { CK(h->d_acc.ensure(h->cnt_len, true)); CK(cudaMemsetAsync(h->d_acc.p, 0, sizeof(double) * h->cnt_len, h->cur->stream)); h->acc_used = true; }
-    size_t nb = h->nbins, lo = 4 * nb, hi = 4 * nb + 2 * nb * h->cfg.n_groups_solute;
-    if (!h->cfg.autocorrelation) lo = hi = 0;
-    launch(h, k_fold, dim3((unsigned)((h->cnt_len + 255) / 256)), dim3(256), (const u64 *)h->d_cnt.p, h->d_acc.p, h->cnt_len, lo, hi, h->cur_weight);
-    CK(cudaMemsetAsync(h->d_cnt.p, 0, sizeof(u64) * h->cnt_len, h->cur->stream));
-    CK(cudaStreamSynchronize(h->cur->stream));
+// A frame whose weight differs from the first weight of the run: from here on the kernels add w (fp64 atomics) into
+// the fp64 twin of the accumulator block instead of counting integer hits.  The integer block keeps the hits of the
+// frames before the switch (all of weight w0) and is scaled once, at the end.  Nothing is synchronised.
+int enter_acc_mode(cmx_handle *h) {
+    if (h->acc_used) return CMX_OK;
+    { int rc = flush_all(h); if (rc) return rc; }     // the pending frames were queued for the integer counters
+    CK(h->d_acc.ensure(h->cnt_len));
+    // every compute stream may add into it: zero it before any of them continues
+    CK(cudaMemsetAsync(h->d_acc.p, 0, sizeof(double) * h->d_acc.n, h->ctx[0]->stream));
+    CK(cudaStreamSynchronize(h->ctx[0]->stream));
+    h->P.acc = h->d_acc.p;
+    h->acc_used = true;
     return CMX_OK;
 }
 
 int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, int64_t frame_index, double weight,
-                  const double cell[9]) {
+                  const double cell[9], cudaEvent_t release) {
     if (!(weight > 0) && weight != 0) return fail(h, CMX_ERR_ARG, "frame weight must be finite and non-negative");
     if (weight == 0) return fail(h, CMX_ERR_ARG, "zero-weight frames must be skipped by the caller (src/mddf.jl:102)");
     Geom g;
     int rc = build_geom(h, cell, g);
     if (rc) return rc;
-    h->cur = h->ctx[(size_t)(h->submitted++ % (int64_t)(h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size()))];
-    if (h->have_weight && weight != h->cur_weight) { rc = fold_weight(h); if (rc) return rc; }
-    h->cur_weight = weight; h->have_weight = true;
+    if (!h->have_weight) { h->w0 = weight; h->have_weight = true; }
+    if (weight != h->w0 && !h->acc_used) { rc = enter_acc_mode(h); if (rc) return rc; }
     // rmax feedback from earlier frames (pinned mirror, may lag)
     float seen = 0.f;
     for (FrameCtx *x : h->ctx) { float v = 0.f; std::memcpy(&v, x->h_scalars + 5, sizeof(float)); seen = std::max(seen, v); }
@@ -489,12 +596,18 @@ int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, 
     g.dwin = std::min(15, (int)std::ceil((h->cut_eff + g.tau + h->rmax_bound + 1e-3) / h->cside) + 2);
     // the transform marks everything at >= (dwin-1) cells as "far": only valid while that exceeds the thresholds
     if ((g.dwin - 1) * h->cside < h->cut_eff + g.tau + h->rmax_bound + 1e-3) g.rmax_bound = -1.f;   // random cull disabled
-    if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, h->cur->stream)); h->ev_first_set = true; }
     uint32_t frame = (uint32_t)(frame_index & 0xffffffffll);
-    if (h->cfg.keep_lists && h->d_rand_list.p) CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, h->cur->stream));
     h->last_g = g; h->last_dsol = d_solute; h->last_dsolv = d_solvent;
-    rc = h->path == 1 ? frame_grid_path(h, d_solute, d_solvent, frame, g)
-                      : frame_pair_path(h, d_solute, d_solvent, frame, g);
+    if (h->path == 1) rc = queue_grid_frame(h, d_solute, d_solvent, frame, g, weight, release);
+    else {
+        h->cur = h->ctx[(size_t)h->fill];
+        h->fill = (h->fill + 1) % nctx_active(h);
+        if (!h->ev_first_set) { CK(cudaEventRecord(h->ev_first, h->cur->stream)); h->ev_first_set = true; }
+        if (h->cfg.keep_lists && h->d_rand_list.p) CK(cudaMemsetAsync(h->d_rand_list.p, 0, sizeof(MdRec) * h->d_rand_list.n, h->cur->stream));
+        h->P.w = weight;
+        rc = frame_pair_path(h, d_solute, d_solvent, frame, g);
+        if (rc == CMX_OK && release) CK(cudaEventRecord(release, h->cur->stream));
+    }
     if (rc) return rc;
     CK(cudaGetLastError());
     // update_volume!, src/mddf.jl:350-352
@@ -567,9 +680,10 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     h->num_sms = prop.multiProcessorCount;
     {
         int b0 = 0, b1 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_tile_search<false>, 256, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_tile_search<true>, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_tile_search<false, true>, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_tile_search<true, true>, 256, 0));
         h->search_grid[0] = h->num_sms * std::max(1, b0); h->search_grid[1] = h->num_sms * std::max(1, b1);
+        if (const char *e = std::getenv("CMX_TRACE")) { int a = 0, b = 1; if (std::sscanf(e, "%d:%d", &a, &b) >= 1) { h->trace_skip = a; h->trace_count = b; } }
         if (const char *e = std::getenv("CMX_SEARCH_BLOCKS_PER_SM")) h->search_blocks_env = std::max(1, atoi(e));   // experiments only
     }
     h->nbins = std::max(1, (int)std::ceil(c.cutoff / c.binstep));   // setbin(cutoff, binstep), src/results.jl:131
@@ -596,20 +710,32 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     if (const char *e = std::getenv("CMX_QSIDE")) h->qside = std::max(1.0, atof(e));
     if (const char *e = std::getenv("CMX_CULLDIV")) h->cside = (h->cut_eff + 0.02) / std::max(1.0, atof(e));
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
-    int nctx = c.n_streams > 0 ? c.n_streams : (h->nv_atoms + h->ns_atoms > 2000000 ? 4 : 8);
-    if (c.keep_lists) nctx = 1;                  // the parity hooks read the scratch of the last frame
+    // Frames per batch (grid path): enough frames per launch that the small kernels of the sequence fill the GPU and
+    // the launch count per frame drops below 2; large systems fill the GPU on their own and their slots are big.
+    const size_t natoms_in = h->nv_atoms + (c.autocorrelation ? 0 : h->ns_atoms);
+    int batch = c.batch_frames > 0 ? c.batch_frames : (int)std::min<size_t>(16, std::max<size_t>(1, (size_t)4000000 / std::max<size_t>(natoms_in, 1)));
+    if (const char *e = std::getenv("CMX_BATCH")) { int v = atoi(e); if (v > 0) batch = std::min(v, CMX_MAX_BATCH); }   // experiments only
+    if (h->path == 2) batch = 1;
+    int nctx = c.n_streams > 0 ? c.n_streams : (h->path == 2 ? (natoms_in > 2000000 ? 4 : 8) : (batch > 1 ? 3 : 4));
+    if (c.keep_lists) { nctx = 1; batch = 1; }   // the parity hooks read the scratch of the last frame
     if (nctx > 16) return fail(h, CMX_ERR_ARG, "n_streams must be <= 16");
+    if (batch > CMX_MAX_BATCH) return fail(h, CMX_ERR_ARG, "batch_frames must be <= 32");
+    h->batch = batch;
     for (int k = 0; k < nctx; ++k) {
         FrameCtx *x = new FrameCtx();
         h->ctx.push_back(x);
         CK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&x->ev_end));
+        CK(cudaEventCreateWithFlags(&x->ev_fd, cudaEventDisableTiming));
         CK(cudaHostAlloc(&x->h_scalars, sizeof(int) * 8, cudaHostAllocDefault));
         std::memset(x->h_scalars, 0, sizeof(int) * 8);
+        CK(cudaHostAlloc(&x->h_fd, sizeof(GridFrame) * batch, cudaHostAllocDefault));
+        CK(cudaMalloc(&x->d_fd, sizeof(GridFrame) * batch));
     }
     h->cur = h->ctx[0];
     CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_last));
-    int slots = c.ring_slots > 0 ? c.ring_slots : 3;
+    // staging ring of acquire/submit: by default every frame of every batch in flight has a slot (+1 being filled)
+    int slots = c.ring_slots > 0 ? c.ring_slots : std::max(3, batch * nctx + 1);
     h->ring.resize(slots);
     h->numa_node = gpu_numa_node(c.device);
     NumaPrefer numa_guard(h->numa_node);
@@ -661,34 +787,37 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     h->sample_chunk = (int)std::max<size_t>(1, std::min<size_t>(std::max<size_t>(nrand, 1), (size_t)(48.0e6 / (double)h->nv_atoms)));
     const size_t nchunk = (size_t)h->sample_chunk;
     CK(h->d_stats.ensure(8, true));
+    P.cnt_base = h->d_cnt.p; P.acc = nullptr; P.w = 1.0;
+    if (c.keep_lists) {
+        if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
+        CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));
+    }
     for (FrameCtx *x_ : h->ctx) {
         h->cur = x_;
-        CK(h->cur->d_scalars.ensure(16, true)); 
-        CK(h->cur->d_list.ensure(nvm));
-        CK(h->cur->d_bulk_idx.ensure(nvm));
-        CK(h->cur->d_worklist.ensure(nvm)); CK(h->cur->d_rand_worklist.ensure(std::max<size_t>(nchunk * nvm, 1)));
-        CK(h->cur->d_def_real.ensure(nvm)); CK(h->cur->d_def_rand.ensure(std::max<size_t>(nchunk * nvm, 1)));
-    CK(h->cur->d_def_real_info.ensure(nvm)); CK(h->cur->d_def_rand_info.ensure(std::max<size_t>(nchunk * nvm, 1)));
-        if (c.keep_lists) {
-            if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
-            CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));
-        }
+        CK(x_->d_scalars.ensure(16, true));
         if (h->path == 1) {
-            CK(h->cur->d_sorted.ensure(27 * (size_t)c.solute_natomspermol));
-            size_t maxq = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms);
-            CK(h->cur->d_qpos.ensure(maxq)); CK(h->cur->d_qsorted.ensure(maxq)); CK(h->cur->d_res.ensure(maxq));
-            CK(h->cur->d_xexact.ensure(std::max<size_t>(3 * nchunk * h->nv_atoms, 1)));
+            x_->slots.resize((size_t)h->batch);
+            const size_t maxq = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms);
+            for (GridSlot &S : x_->slots) {
+                CK(S.sc.ensure(SC_COUNT, true));
+                CK(S.list.ensure(nvm)); CK(S.bulk_idx.ensure(nvm));
+                CK(S.worklist.ensure(nvm)); CK(S.rand_worklist.ensure(std::max<size_t>(nchunk * nvm, 1)));
+                CK(S.def_real.ensure(nvm)); CK(S.def_rand.ensure(std::max<size_t>(nchunk * nvm, 1)));
+                CK(S.def_real_info.ensure(nvm)); CK(S.def_rand_info.ensure(std::max<size_t>(nchunk * nvm, 1)));
+                CK(S.sorted.ensure(27 * (size_t)c.solute_natomspermol));
+                CK(S.qpos.ensure(maxq)); CK(S.res.ensure(maxq));
+                CK(S.xexact.ensure(std::max<size_t>(3 * nchunk * h->nv_atoms, 1)));
+            }
         } else {
+            CK(x_->d_list.ensure(nvm));
             int rc = pairs_create(h); if (rc) return rc;
+            // cub temp storage of the anchor-cell scan
+            size_t t1 = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, t1, (int *)nullptr, (int *)nullptr, 1 << 20);
+            CK(x_->d_cub_tmp.ensure(t1 + 1024));
         }
     }
     h->cur = h->ctx[0];
-    // cub temp storage sized for the largest call we make
-    size_t t1 = 0, t2 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, t1, (int *)nullptr, (int *)nullptr, 1 << 28);
-    cub::DeviceSelect::If(nullptr, t2, cub::CountingInputIterator<int>(0), (int *)nullptr, (int *)nullptr, (int)std::max<size_t>(nvm, 1),
-                          BulkPred{nullptr, -1, 0, 0.0});
-    for (FrameCtx *x_ : h->ctx) CK(x_->d_cub_tmp.ensure(std::max(t1, t2) + 1024));
     CK(cudaDeviceSynchronize());
     return CMX_OK;
 }
@@ -707,7 +836,11 @@ int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solv
     CK(cudaSetDevice(h->device));
     if (h->acquired >= 0) return fail(h, CMX_ERR_STATE, "cmx_acquire_frame_buffer: previous slot not submitted");
     Slot &s = h->ring[h->next_slot];
-    if (s.in_flight) { CK(cudaEventSynchronize(s.consumed)); s.in_flight = false; }
+    if (s.in_flight) {
+        // the slot's previous frame may still wait in a batch that is not launched yet (ring shorter than the batches)
+        { int rc = flush_if_pending(h, s.consumed); if (rc) return rc; }
+        CK(cudaEventSynchronize(s.consumed)); s.in_flight = false;
+    }
     h->acquired = h->next_slot;
     h->next_slot = (h->next_slot + 1) % (int)h->ring.size();
     if (h->cfg.autocorrelation) { if (solute_xyz) *solute_xyz = s.h_in; if (solvent_xyz) *solvent_xyz = s.h_in; }
@@ -723,13 +856,13 @@ int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, cons
     h->acquired = -1;
     CK(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * h->in_floats, cudaMemcpyHostToDevice, h->s_copy));
     CK(cudaEventRecord(s.h2d_done, h->s_copy));
-    FrameCtx *next = h->ctx[(size_t)(h->submitted % (int64_t)(h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size()))];
+    FrameCtx *next = h->ctx[(size_t)h->fill];     // the context whose batch this frame joins: its kernels come later on this stream
     CK(cudaStreamWaitEvent(next->stream, s.h2d_done, 0));
     h->stats.h2d_bytes += (int64_t)(sizeof(float) * h->in_floats);
     const float *dsol = s.d_in, *dsolv = h->cfg.autocorrelation ? s.d_in : s.d_in + 3 * h->ns_atoms;
-    int rc = submit_common(h, dsol, dsolv, frame_index, weight, cell);
-    // the slot is reusable once the frame's kernels are done (even on error, to keep the ring consistent)
-    cudaEventRecord(s.consumed, next->stream);
+    // the slot is reusable once the frame's kernels are done: `consumed` is recorded behind them
+    int rc = submit_common(h, dsol, dsolv, frame_index, weight, cell, s.consumed);
+    if (rc != CMX_OK) { (void)flush_all(h); cudaEventRecord(s.consumed, next->stream); }   // keep the ring consistent
     s.in_flight = true;
     return rc;
 }
@@ -740,12 +873,13 @@ int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const 
     CK(cudaSetDevice(h->device));
     const float *dsol = h->cfg.autocorrelation ? d_solvent_xyz : d_solute_xyz;
     if (!dsol) return fail(h, CMX_ERR_ARG, "cmx_submit_frame_device: null solute pointer");
-    return submit_common(h, dsol, d_solvent_xyz, frame_index, weight, cell);
+    return submit_common(h, dsol, d_solvent_xyz, frame_index, weight, cell, nullptr);
 }
 
 int32_t cmx_sync(cmx_handle *h) {
     if (!h) return CMX_ERR_ARG;
     CK(cudaSetDevice(h->device));
+    { int rc = flush_all(h); if (rc) return rc; }
     if (h->ev_first_set) for (FrameCtx *x : h->ctx) CK(cudaEventRecord(x->ev_end, x->stream));
     { int rc = sync_all(h); if (rc) return rc; }
     if (h->ev_first_set) {
@@ -755,6 +889,7 @@ int32_t cmx_sync(cmx_handle *h) {
         h->stats.gpu_ms_total += best; h->ev_first_set = false;
     }
     prof_collect(h);
+    trace_report(h);
     for (auto &s : h->ring) s.in_flight = false;
     int sticky = 0;
     for (FrameCtx *x : h->ctx) { int v = 0; CK(cudaMemcpy(&v, x->d_scalars.p + 8, sizeof(int), cudaMemcpyDeviceToHost)); sticky |= v; }
@@ -773,7 +908,7 @@ int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
     if (!h || !out) return CMX_ERR_ARG;
     int rc = cmx_sync(h); if (rc) return rc;
     size_t n = h->cnt_len, nb = h->nbins;
-    const double w = h->have_weight ? h->cur_weight : 1.0;
+    const double w = h->have_weight ? h->w0 : 1.0;
     const size_t gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
     size_t lo = 4 * nb, hi = 4 * nb + 2 * gs;
     if (!h->cfg.autocorrelation) lo = hi = 0;
@@ -856,7 +991,7 @@ int32_t cmx_reset(cmx_handle *h) {
     CK(cudaMemset(h->d_cnt.p, 0, sizeof(u64) * h->d_cnt.n));
     if (h->acc_used) CK(cudaMemset(h->d_acc.p, 0, sizeof(double) * h->d_acc.n));
     CK(cudaMemset(h->d_stats.p, 0, sizeof(u64) * 8));
-    h->acc_used = false; h->have_weight = false; h->cur_weight = 1.0;
+    h->acc_used = false; h->P.acc = nullptr; h->have_weight = false; h->w0 = 1.0;
     h->volume_total = 0; h->sum_weights = 0;
     h->stats = cmx_stats{};
     return CMX_OK;
@@ -878,9 +1013,10 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
         int rc = cmx_sync(h); if (rc) return rc;
         int v = (int)value;
         if (v < 0 || v > (int)h->ctx.size()) return fail(h, CMX_ERR_ARG, "active_streams out of range");
-        h->active_ctx = v;
+        h->active_ctx = v; h->fill = 0;
     }
     else if (n == "group_lanes") { /* accepted, ignored */ }
+    else if (n == "poll_stop_file") h->poll_stop_file = value != 0;
     else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
     return CMX_OK;
 }

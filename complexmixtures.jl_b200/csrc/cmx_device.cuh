@@ -52,7 +52,11 @@ struct Prob {
     double cutoff, dbulk, binstep;
     uint32_t seed_lo, seed_hi;
     const int *sol_off, *sol_ids, *solv_off, *solv_ids;   // CSR position -> groups (device)
-    u64 *md, *md_r, *rdf, *rdf_r, *gsol, *gsol_r, *gsolv, *gsolv_r;   // run accumulators
+    u64 *md, *md_r, *rdf, *rdf_r, *gsol, *gsol_r, *gsolv, *gsolv_r;   // run accumulators (integer: hits at the first weight seen)
+    const u64 *cnt_base;      // start of the contiguous accumulator block (= md)
+    double *acc;              // fp64 twin of the block, same layout: sums of w for frames whose weight differs from the
+                              // first one (nullptr while every frame has had the same weight)
+    double w;                 // molecule-pair path: weight of the frame being processed
 };
 
 // MinimumDistance record kept per solvent molecule (i local to the solute molecule, j global)
@@ -203,30 +207,38 @@ struct RandMol {
 };
 
 // ---- counters: update_counters!, src/update_counters.jl:43-88 ----------------------------------
-__device__ __forceinline__ void group_add(u64 *arr, int nbins, int ibin, int pos, int apm, int custom,
-                                          const int *off, const int *ids, u64 inc) {
-    if (!custom) atomicAdd(&arr[(size_t)(pos % apm) * nbins + ibin], inc);            // atom_type, :9
-    else for (int q = off[pos]; q < off[pos + 1]; ++q) atomicAdd(&arr[(size_t)ids[q] * nbins + ibin], inc);
+// The counters are sums of frame weights (:47,60).  While every frame has the same weight they are kept as exact
+// integers (hits) and scaled once at the end; frames with another weight add w (w/2 for the group counts of an
+// autocorrelation, :52-53) straight into the fp64 twin of the block -- no fold, no synchronisation between frames.
+__device__ __forceinline__ void bump(const Prob &P, u64 *cell, u64 inc, double w) {
+    if (P.acc == nullptr) atomicAdd(cell, inc);
+    else atomicAdd(P.acc + (cell - P.cnt_base), w * (double)inc);
+}
+__device__ __forceinline__ void group_add(const Prob &P, u64 *arr, int nbins, int ibin, int pos, int apm, int custom,
+                                          const int *off, const int *ids, u64 inc, double w) {
+    if (!custom) bump(P, &arr[(size_t)(pos % apm) * nbins + ibin], inc, w);            // atom_type, :9
+    else for (int q = off[pos]; q < off[pos + 1]; ++q) bump(P, &arr[(size_t)ids[q] * nbins + ibin], inc, w);
 }
 
-// One molecule within the cutoff.  Integer increments; the frame weight (and the 1/2 of the
-// autocorrelation group counts, :48-53) is applied when the integers are folded to fp64.
-// `mult` = 2 when one evaluated molecule pair stands for both ordered pairs (symmetric
-// autocorrelation pass).
-__device__ __forceinline__ void count_hit(const Prob &P, bool random, double d, int i, int j, u64 mult) {
+// One molecule within the cutoff.  `w` is the frame weight (only used in fp64 mode); `mult` = 2 when one evaluated
+// molecule pair stands for both ordered pairs (symmetric autocorrelation pass).
+// NOTE (reference quirk kept on purpose, src/update_counters.jl:27): `i` is the atom index WITHIN the current solute
+// molecule, so with custom groups and several solute molecules every hit is credited through the group map of the
+// FIRST molecule's atoms; `j` is global in the solvent selection.
+__device__ __forceinline__ void count_hit(const Prob &P, double w, bool random, double d, int i, int j, u64 mult) {
     int ib = setbin0(d, P.binstep, P.nbins);
-    atomicAdd(&(random ? P.md_r : P.md)[ib], mult);
+    bump(P, &(random ? P.md_r : P.md)[ib], mult, w);
     u64 *gs = random ? P.gsol_r : P.gsol;
     if (P.autocorr) {
-        group_add(gs, P.nbins, ib, i, P.ns_apm, P.custom_sol, P.sol_off, P.sol_ids, mult);
-        group_add(gs, P.nbins, ib, j, P.ns_apm, P.custom_sol, P.sol_off, P.sol_ids, mult);
+        group_add(P, gs, P.nbins, ib, i, P.ns_apm, P.custom_sol, P.sol_off, P.sol_ids, mult, 0.5 * w);
+        group_add(P, gs, P.nbins, ib, j, P.ns_apm, P.custom_sol, P.sol_off, P.sol_ids, mult, 0.5 * w);
     } else {
-        group_add(gs, P.nbins, ib, i, P.ns_apm, P.custom_sol, P.sol_off, P.sol_ids, mult);
-        group_add(random ? P.gsolv_r : P.gsolv, P.nbins, ib, j, P.nv_apm, P.custom_solv, P.solv_off, P.solv_ids, mult);
+        group_add(P, gs, P.nbins, ib, i, P.ns_apm, P.custom_sol, P.sol_off, P.sol_ids, mult, w);
+        group_add(P, random ? P.gsolv_r : P.gsolv, P.nbins, ib, j, P.nv_apm, P.custom_solv, P.solv_off, P.solv_ids, mult, w);
     }
 }
-__device__ __forceinline__ void count_ref(const Prob &P, bool random, double dref) {
-    atomicAdd(&(random ? P.rdf_r : P.rdf)[setbin0(dref, P.binstep, P.nbins)], 1ull);
+__device__ __forceinline__ void count_ref(const Prob &P, double w, bool random, double dref) {
+    bump(P, &(random ? P.rdf_r : P.rdf)[setbin0(dref, P.binstep, P.nbins)], 1ull, w);
 }
 
 // inbulk, src/mddf.jl:55-57

@@ -296,7 +296,8 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
     // read until its frame's kernels have finished), bounded to ~4 GB of pinned memory
     const int nctx = h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size();
     const int64_t cap = std::max<int64_t>(3, (int64_t)(4.0e9 / (double)src.slot_bytes));
-    const int S = (int)std::min<int64_t>(std::max(2 * nctx + 2, T + 2), cap);
+    // (a frame also occupies its slot while it waits in a batch that is not launched yet: B frames per context)
+    const int S = (int)std::min<int64_t>(std::max((nctx + 1) * h->batch + 2, T + 2), cap);
     { int rc = feed_prepare(h, src.natoms, src.slot_bytes, solute_indices, solvent_indices, S); if (rc) return rc; }
     cmx_feed &F = *h->feed;
     std::mutex mu;
@@ -333,6 +334,9 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
     int rc = CMX_OK;
     const size_t ns = h->cfg.autocorrelation ? 0 : h->ns_atoms;
     for (int64_t k = 0; k < nframes && rc == CMX_OK; ++k) {
+        // cooperative interrupt of the reference (src/mddf.jl:301-304): a file named stop_complexmixtures in the working
+        // directory ends the frame loop; the frames enqueued so far are finished and reported (cmx_stats.frames)
+        if ((k & 7) == 0 && h->poll_stop_file && access("stop_complexmixtures", F_OK) == 0) { h->stopped_by_file = true; break; }
         FeedSlot &s = F.slots[(size_t)(k % S)];
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -341,7 +345,7 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
         }
         double cell[9];
         std::memcpy(cell, s.cell, sizeof cell);
-        FrameCtx *next = h->ctx[(size_t)(h->submitted % (int64_t)(h->active_ctx > 0 ? h->active_ctx : (int)h->ctx.size()))];
+        FrameCtx *next = h->ctx[(size_t)h->fill];   // the context whose batch this frame joins
         cudaError_t e = cudaSuccess;
         auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
         if (s.used) step(cudaStreamWaitEvent(h->s_copy, s.gathered, 0));            // d_raw free again
@@ -353,7 +357,10 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
             cv.notify_all();
         }
         step(cudaStreamWaitEvent(next->stream, s.h2d_done, 0));
-        if (s.used) step(cudaStreamWaitEvent(next->stream, s.consumed, 0));         // d_xyz free again
+        if (s.used) {                                                               // d_xyz free again
+            if (flush_if_pending(h, s.consumed) != CMX_OK) { rc = CMX_ERR_CUDA; break; }
+            step(cudaStreamWaitEvent(next->stream, s.consumed, 0));
+        }
         if (e == cudaSuccess) {
             const unsigned nblk = (unsigned)((F.n_idx + 255) / 256);
             if (src.layout == 0) k_gather_dcd<<<nblk, 256, 0, next->stream>>>(s.d_raw, (long long)src.natoms, F.d_idx, (int)F.n_idx, s.d_xyz);
@@ -364,11 +371,12 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
         if (e != cudaSuccess) { h->err = std::string(src.what) + ": " + cudaGetErrorString(e); rc = CMX_ERR_CUDA; break; }
         h->stats.h2d_bytes += (int64_t)fb;
         const float *dsol = s.d_xyz, *dsolv = s.d_xyz + 3 * ns;
-        rc = submit_common(h, dsol, dsolv, frames[k] + 1, weights ? weights[k] : 1.0, cell);
-        cudaEventRecord(s.consumed, next->stream);
+        // `consumed` is recorded behind the frame's kernels, i.e. when its batch is launched
+        rc = submit_common(h, dsol, dsolv, frames[k] + 1, weights ? weights[k] : 1.0, cell, s.consumed);
+        if (rc != CMX_OK) { (void)flush_all(h); cudaEventRecord(s.consumed, next->stream); }
         s.used = true;
     }
-    if (rc != CMX_OK) {
+    if (rc != CMX_OK || h->stopped_by_file) {
         std::lock_guard<std::mutex> lk(mu);
         abort_flag = true;
         cv.notify_all();
@@ -434,7 +442,7 @@ int32_t cmx_reduce_groups(cmx_handle *h, int32_t which, int32_t n_groups, const 
         prof_end(h, pe);
     }
     // frame weight as in cmx_finish; the group counts of an autocorrelation carry w/2 (src/update_counters.jl:52-53)
-    const double w = h->have_weight ? h->cur_weight : 1.0;
+    const double w = h->have_weight ? h->w0 : 1.0;
     const double scale = (h->cfg.autocorrelation && which < 2) ? w / 2 : w;
     launch(h, k_reduce_emit, dim3((unsigned)((nout + 255) / 256)), dim3(256), (const u64 *)F.red_cnt.p,
            (const double *)(h->acc_used ? F.red_acc.p : nullptr), nout, scale, F.red_out.p);

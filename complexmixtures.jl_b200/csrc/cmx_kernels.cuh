@@ -20,11 +20,80 @@
 //      an exact fp64 resolve kernel, so the counts equal the fp64 oracle's bit for bit.
 //   The random phase generates a random molecule from its Philox counters only if its centre
 //   survives the cull; the random box as a whole is never materialised.
+//
+// Launch structure: every kernel has a FRAME dimension (blockIdx.y = frame of the batch).  The host
+// collects up to B frames, uploads B frame descriptors (GridFrame: geometry + the frame's scratch
+// pointers) in one copy and launches each kernel ONCE for the whole batch, so the launch count per
+// frame is (kernels per batch) / B.  Scans and the ordered bulk compaction are single-pass chained
+// scans (decoupled look-back) written here: no library kernel is on the path.
 #pragma once
 #include "cmx_device.cuh"
 
 namespace cmx {
 
+// per-frame scalars (GridFrame::sc), zeroed by k_zero_frame
+enum {
+    SC_WORK = 0, SC_RWORK = 1, SC_DEF_REAL = 2, SC_DEF_RAND = 3, SC_NBULK = 4, SC_RMAX = 5, SC_TQ_REAL = 6, SC_TQ_RAND = 7,
+    SC_SCAN_CELLS = 8, SC_SCAN_TILES_REAL = 9, SC_SCAN_TILES_RAND = 10, SC_SCAN_BULK = 11, SC_COUNT = 16
+};
+
+// One frame (x one solute molecule) in flight on the device: geometry, inputs and the scratch of its slot.
+// An array of these (one per frame of the batch) lives in device memory; kernels pick theirs with blockIdx.y.
+struct GridFrame {
+    Geom g;
+    const float *xs, *xv;          // the solute molecule, all solvent molecules (fp32 xyz as read)
+    int *sc;                       // SC_COUNT scalars
+    u64 *bits;                     // [cull bitmap][row bitmap], zeroed per frame
+    u64 *occ, *rowmask;            // the two parts of `bits`
+    int *cell_count, *cell_start;  // solute grid
+    float4 *sorted;
+    unsigned short *edt_xy;
+    float *lbd2;
+    float4 *qpos, *qsorted, *res;  // query atoms of the current phase: positions, tile order, results
+    double *xexact;
+    int *qcell_count, *qcell_start;
+    unsigned char *tile_valid;     // valid lanes of every tile (a cell's last tile is partially filled)
+    MdRec *list, *rand_list;       // real-phase list of this solute molecule; random lists only for the parity hooks
+    int *worklist, *rand_worklist, *bulk_idx;
+    u64 *def_real, *def_rand;
+    float2 *def_real_info, *def_rand_info;
+    u64 *scan_state;               // tile states of the chained scans
+    long long bits_words;
+    int ncells, nqcells, ncull;    // sizes of this frame's grids
+    uint32_t frame;                // Philox frame key
+    int isolute, skip_mol, nrand_k, pad0;
+    double weight, pad1;           // frame weight (fp64 accumulation once the weights vary)
+};
+static_assert(sizeof(GridFrame) % 16 == 0, "GridFrame is copied with 16-byte loads");
+
+// the block's frame descriptor -> shared memory (a few hundred bytes; every field is then a broadcast read)
+#define CMX_FRAME(F)                                                                                         \
+    __shared__ __align__(16) GridFrame F##_sh;                                                               \
+    {                                                                                                        \
+        const int4 *src_ = reinterpret_cast<const int4 *>(fds + blockIdx.y);                                 \
+        int4 *dst_ = reinterpret_cast<int4 *>(&F##_sh);                                                      \
+        for (int k_ = threadIdx.x; k_ < (int)(sizeof(GridFrame) / 16); k_ += blockDim.x) dst_[k_] = __ldg(src_ + k_); \
+    }                                                                                                        \
+    __syncthreads();                                                                                         \
+    const GridFrame &F = F##_sh;                                                                             \
+    const Geom &g = F.g;                                                                                     \
+    (void)g;
+
+// ---------------------------------------------------------------------------------------------
+// per-frame reset: scalars and the two bitmaps (one launch per batch instead of a memset per frame)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_zero_frame(const GridFrame *__restrict__ fds) {
+    CMX_FRAME(F)
+    const long long n = F.bits_words;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) F.bits[k] = 0ull;
+    if (blockIdx.x == 0 && threadIdx.x < SC_COUNT) F.sc[threadIdx.x] = 0;
+}
+
+// between two chunks of random samples: the counters of the random phase
+__global__ void k_reset_rand(const GridFrame *__restrict__ fds) {
+    const GridFrame &F = fds[blockIdx.x];
+    if (threadIdx.x == 0) { F.sc[SC_RWORK] = 0; F.sc[SC_DEF_RAND] = 0; F.sc[SC_TQ_RAND] = 0; F.sc[SC_SCAN_TILES_RAND] = 0; }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Solute grid: bin the solute molecule (plus periodic images inside the extended box) into the grid
@@ -46,11 +115,11 @@ __device__ __forceinline__ void coarse_cell_of(const Geom &g, float px, float py
 // SCATTER=false: count images per cell and mark coarse occupancy; SCATTER=true: write the
 // cell-sorted float4 array (cell_count is consumed as the per-cell fill counter).
 template <bool SCATTER>
-__global__ void k_solute_bin(Geom g, const float *__restrict__ xs, int natoms, int *__restrict__ cell_count,
-                             const int *__restrict__ cell_start, u64 *__restrict__ occ_bits,
-                             u64 *__restrict__ rowmask, float4 *__restrict__ sorted) {
+__global__ void k_solute_bin(const GridFrame *__restrict__ fds, int natoms) {
+    CMX_FRAME(F)
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= natoms) return;
+    const float *xs = F.xs;
     double wx, wy, wz;
     wrap_to_cell(g, (double)xs[3 * a], (double)xs[3 * a + 1], (double)xs[3 * a + 2], wx, wy, wz);
     for (int n2 = -1; n2 <= 1; ++n2)
@@ -64,16 +133,132 @@ __global__ void k_solute_bin(Geom g, const float *__restrict__ xs, int natoms, i
                 float px = (float)(rx - g.ctr[0]), py = (float)(ry - g.ctr[1]), pz = (float)(rz - g.ctr[2]);
                 int c = fine_cell_of(g, px, py, pz);
                 if (!SCATTER) {
-                    atomicAdd(&cell_count[c], 1);
+                    atomicAdd(&F.cell_count[c], 1);
                     int fx = c % g.nx, frow = c / g.nx;
-                    atomicOr(&rowmask[(size_t)frow * g.rw + (fx >> 6)], 1ull << (fx & 63));
+                    atomicOr(&F.rowmask[(size_t)frow * g.rw + (fx >> 6)], 1ull << (fx & 63));
                     int cx, cy, cz; coarse_cell_of(g, px, py, pz, cx, cy, cz);
-                    atomicOr(&occ_bits[(size_t)(cz * g.ncy + cy) * g.cw + (cx >> 6)], 1ull << (cx & 63));
+                    atomicOr(&F.occ[(size_t)(cz * g.ncy + cy) * g.cw + (cx >> 6)], 1ull << (cx & 63));
                 } else {
-                    int slot = cell_start[c] + atomicSub(&cell_count[c], 1) - 1;
-                    sorted[slot] = make_float4(px, py, pz, __int_as_float(a));
+                    int slot = F.cell_start[c] + atomicSub(&F.cell_count[c], 1) - 1;
+                    F.sorted[slot] = make_float4(px, py, pz, __int_as_float(a));
                 }
             }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass chained scan (decoupled look-back), one launch for arrays of any size and for every frame of the
+// batch (blockIdx.y).  A tile is CMX_SCAN_TILE consecutive items; blocks take tiles in order from a per-frame
+// counter (so a tile's predecessors are always running or done), publish their aggregate, look back over the
+// predecessors' states for their exclusive prefix and publish the inclusive one.  State word = epoch (30 bits) |
+// flag (2 bits: 1 aggregate, 2 inclusive prefix) | value (32 bits); the epoch is a per-launch number, so the state
+// array is never reset.  The policy supplies the item values and consumes (item, value, exclusive prefix):
+//   ScanCells      exclusive sum of the solute-grid cell counts -> cell_start
+//   ScanTiles<R>   per query cell: tiles = ceil(count / 32) -> first tile of the cell, and the valid-lane count of
+//                  each of its tiles (no sentinel fill of the tile array)
+//   ScanBulk       inbulk (src/mddf.jl:55-57) of every solvent molecule -> bulk list in ascending molecule order
+//                  (src/mddf.jl:406-415) + n_bulk: an ordered stream compaction
+// ---------------------------------------------------------------------------------------------
+#define CMX_SCAN_THREADS 256
+#define CMX_SCAN_ITEMS 8
+#define CMX_SCAN_TILE (CMX_SCAN_THREADS * CMX_SCAN_ITEMS)
+
+struct ScanCells {
+    static __device__ __forceinline__ int counter() { return SC_SCAN_CELLS; }
+    static __device__ __forceinline__ int n(const GridFrame &F, const Prob &) { return F.ncells + 1; }
+    static __device__ __forceinline__ int load(const GridFrame &F, const Prob &, int i) { return F.cell_count[i]; }
+    static __device__ __forceinline__ void store(const GridFrame &F, const Prob &, int i, int, int excl) { F.cell_start[i] = excl; }
+    static __device__ __forceinline__ void total(const GridFrame &, int) {}
+};
+template <bool RANDOM>
+struct ScanTiles {
+    static __device__ __forceinline__ int counter() { return RANDOM ? SC_SCAN_TILES_RAND : SC_SCAN_TILES_REAL; }
+    static __device__ __forceinline__ int n(const GridFrame &F, const Prob &) { return F.nqcells + 1; }
+    static __device__ __forceinline__ int load(const GridFrame &F, const Prob &, int i) { return (F.qcell_count[i] + 31) >> 5; }
+    static __device__ __forceinline__ void store(const GridFrame &F, const Prob &, int i, int v, int excl) {
+        F.qcell_start[i] = excl;
+        if (v) {
+            int cnt = F.qcell_count[i];
+            for (int t = 0; t < v; ++t) F.tile_valid[excl + t] = (unsigned char)min(32, cnt - 32 * t);
+        }
+    }
+    static __device__ __forceinline__ void total(const GridFrame &, int) {}
+};
+struct ScanBulk {
+    static __device__ __forceinline__ int counter() { return SC_SCAN_BULK; }
+    static __device__ __forceinline__ int n(const GridFrame &, const Prob &P) { return P.nv_mols; }
+    static __device__ __forceinline__ int load(const GridFrame &F, const Prob &P, int m) {
+        if (m == F.skip_mol) return 0;      // autocorrelation: the solute itself, src/mddf.jl:409
+        return inbulk(P, F.list[m]) ? 1 : 0;
+    }
+    static __device__ __forceinline__ void store(const GridFrame &F, const Prob &, int m, int v, int excl) { if (v) F.bulk_idx[excl] = m; }
+    static __device__ __forceinline__ void total(const GridFrame &F, int sum) { F.sc[SC_NBULK] = sum; }
+};
+
+__device__ __forceinline__ u64 scan_pack(uint32_t epoch, uint32_t flag, int value) {
+    return ((u64)epoch << 34) | ((u64)flag << 32) | (u64)(uint32_t)value;
+}
+
+template <class Policy>
+__global__ void __launch_bounds__(CMX_SCAN_THREADS)
+k_chain_scan(const GridFrame *__restrict__ fds, Prob P, uint32_t epoch) {
+    CMX_FRAME(F)
+    __shared__ int s_tile, s_prefix, warp_sums[CMX_SCAN_THREADS / 32];
+    const int n = Policy::n(F, P);
+    const int ntiles = (n + CMX_SCAN_TILE - 1) / CMX_SCAN_TILE;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    volatile u64 *state = F.scan_state;
+    while (true) {
+        __syncthreads();     // s_tile / s_prefix / warp_sums of the previous tile are no longer read
+        if (threadIdx.x == 0) s_tile = atomicAdd(&F.sc[Policy::counter()], 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) return;
+        const int i0 = tile * CMX_SCAN_TILE + threadIdx.x * CMX_SCAN_ITEMS;
+        int v[CMX_SCAN_ITEMS];
+        int mine = 0;
+#pragma unroll
+        for (int k = 0; k < CMX_SCAN_ITEMS; ++k) { v[k] = (i0 + k < n) ? Policy::load(F, P, i0 + k) : 0; mine += v[k]; }
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = lane < CMX_SCAN_THREADS / 32 ? warp_sums[lane] : 0, wi = ws;
+#pragma unroll
+            for (int o = 1; o < CMX_SCAN_THREADS / 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            if (lane < CMX_SCAN_THREADS / 32) warp_sums[lane] = wi - ws;      // exclusive prefix of the warp totals
+            const int agg = __shfl_sync(0xffffffffu, wi, CMX_SCAN_THREADS / 32 - 1);
+            int excl = 0;
+            if (tile == 0) {
+                if (lane == 0) state[0] = scan_pack(epoch, 2u, agg);
+            } else {
+                if (lane == 0) state[tile] = scan_pack(epoch, 1u, agg);
+                int look = tile - 1;                                           // nearest predecessor handled by lane 0
+                while (true) {
+                    const int idx = look - lane;
+                    u64 s = scan_pack(epoch, 2u, 0);                          // before the first tile: prefix 0
+                    if (idx >= 0) {
+                        do { s = state[idx]; } while ((uint32_t)(s >> 34) != epoch || ((s >> 32) & 3ull) == 0ull);
+                    }
+                    const unsigned full = __ballot_sync(0xffffffffu, ((s >> 32) & 3ull) == 2ull);
+                    const int stop = full ? __ffs(full) - 1 : 32;            // first lane that holds an inclusive prefix
+                    int val = (lane <= stop) ? (int)(uint32_t)s : 0;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                    excl += val;
+                    if (full) break;
+                    look -= 32;
+                }
+                if (lane == 0) state[tile] = scan_pack(epoch, 2u, excl + agg);
+            }
+            if (lane == 0) { s_prefix = excl; if (tile == ntiles - 1) Policy::total(F, excl + agg); }
+        }
+        __syncthreads();
+        int run = s_prefix + warp_sums[wid] + (incl - mine);
+#pragma unroll
+        for (int k = 0; k < CMX_SCAN_ITEMS; ++k) { if (i0 + k < n) Policy::store(F, P, i0 + k, v[k], run); run += v[k]; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -107,33 +292,35 @@ __device__ __forceinline__ int edt_x_of(const Geom &g, const u64 *__restrict__ o
 
 // passes X and Y in one kernel: the X distance of the 2*dwin+1 rows of the window is recomputed from the row
 // bitmaps (a handful of bit operations each) instead of being written and re-read by a separate launch
-__global__ void k_edt_xy(Geom g, const u64 *__restrict__ occ_bits, unsigned short *__restrict__ exy) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int ncc = g.ncx * g.ncy * g.ncz;
-    if (c >= ncc) return;
-    int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
-    int D = g.dwin, best = 3 * D * D;
-    for (int dy = -D; dy <= D; ++dy) {
-        int ry = cy + dy;
-        if (ry < 0 || ry >= g.ncy) continue;
-        best = min(best, edt_f(edt_x_of(g, occ_bits, cz * g.ncy + ry, cx)) + edt_f(abs(dy)));
+__global__ void k_edt_xy(const GridFrame *__restrict__ fds) {
+    CMX_FRAME(F)
+    const int ncc = F.ncull;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncc; c += gridDim.x * blockDim.x) {
+        int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
+        int D = g.dwin, best = 3 * D * D;
+        for (int dy = -D; dy <= D; ++dy) {
+            int ry = cy + dy;
+            if (ry < 0 || ry >= g.ncy) continue;
+            best = min(best, edt_f(edt_x_of(g, F.occ, cz * g.ncy + ry, cx)) + edt_f(abs(dy)));
+        }
+        F.edt_xy[c] = (unsigned short)best;
     }
-    exy[c] = (unsigned short)best;
 }
 
-__global__ void k_edt_z(Geom g, const unsigned short *__restrict__ exy, float *__restrict__ lbd2) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    int ncc = g.ncx * g.ncy * g.ncz;
-    if (c >= ncc) return;
-    int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
-    int D = g.dwin, best = 3 * D * D;
-    for (int dz = -D; dz <= D; ++dz) {
-        int rz = cz + dz;
-        if (rz < 0 || rz >= g.ncz) continue;
-        best = min(best, (int)exy[(rz * g.ncy + cy) * g.ncx + cx] + edt_f(abs(dz)));
+__global__ void k_edt_z(const GridFrame *__restrict__ fds) {
+    CMX_FRAME(F)
+    const int ncc = F.ncull;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncc; c += gridDim.x * blockDim.x) {
+        int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
+        int D = g.dwin, best = 3 * D * D;
+        for (int dz = -D; dz <= D; ++dz) {
+            int rz = cz + dz;
+            if (rz < 0 || rz >= g.ncz) continue;
+            best = min(best, (int)F.edt_xy[(rz * g.ncy + cy) * g.ncx + cx] + edt_f(abs(dz)));
+        }
+        // anything at or beyond the window is "far": the window is sized so that D*cside exceeds every threshold
+        F.lbd2[c] = best >= D * D ? CUDART_INF_F : (float)best * g.cside * g.cside;
     }
-    // anything at or beyond the window is "far": the window is sized so that D*cside exceeds every threshold
-    lbd2[c] = best >= D * D ? CUDART_INF_F : (float)best * g.cside * g.cside;
 }
 
 __device__ __forceinline__ float cull_lb2(const Geom &g, const float *__restrict__ lbd2, float px, float py, float pz) {
@@ -145,20 +332,19 @@ __device__ __forceinline__ float cull_lb2(const Geom &g, const float *__restrict
 // Real-phase cull: the solvent molecules of the frame; survivors -> work list.  Also the largest
 // centroid-to-atom distance of any molecule (bound used to cull random placements).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_filter_real(Geom g, Prob P, const float *__restrict__ xv, int skip_mol,
-                              const float *__restrict__ lbd2, MdRec *__restrict__ list,
-                              int *__restrict__ worklist, int *__restrict__ work_count, int *__restrict__ rmax_bits) {
+__global__ void k_filter_real(const GridFrame *__restrict__ fds, Prob P) {
+    CMX_FRAME(F)
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     bool near = false;
     float r2max = 0.f;
     if (m < P.nv_mols) {
-        const float *x = xv + (size_t)3 * P.nv_apm * m;
+        const float *x = F.xv + (size_t)3 * P.nv_apm * m;
         double rx = x[3 * P.iref], ry = x[3 * P.iref + 1], rz = x[3 * P.iref + 2];
         double sx = 0, sy = 0, sz = 0;
         for (int k = 0; k < P.nv_apm; ++k) {
             double px = x[3 * k], py = x[3 * k + 1], pz = x[3 * k + 2];
             double wx, wy, wz; wrap_to_cell(g, px, py, pz, wx, wy, wz);
-            near |= cull_lb2(g, lbd2, (float)(wx - g.ctr[0]), (float)(wy - g.ctr[1]), (float)(wz - g.ctr[2])) <= g.cut_hi2;
+            near |= cull_lb2(g, F.lbd2, (float)(wx - g.ctr[0]), (float)(wy - g.ctr[1]), (float)(wz - g.ctr[2])) <= g.cut_hi2;
             double dx = px - rx, dy = py - ry, dz = pz - rz;
             min_image64(g, dx, dy, dz);
             sx += dx; sy += dy; sz += dz;
@@ -170,21 +356,21 @@ __global__ void k_filter_real(Geom g, Prob P, const float *__restrict__ xv, int 
             dx -= sx; dy -= sy; dz -= sz;
             r2max = fmaxf(r2max, (float)(dx * dx + dy * dy + dz * dz));
         }
-        if (m == skip_mol) near = false;   // autocorrelation: the solute molecule itself (minimum_distances.jl:90)
+        if (m == F.skip_mol) near = false;   // autocorrelation: the solute molecule itself (minimum_distances.jl:90)
         MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
-        list[m] = e;
+        F.list[m] = e;
     }
     // warp-aggregated append
     unsigned ball = __ballot_sync(0xffffffffu, near);
     int lane = threadIdx.x & 31;
     int base = 0;
-    if (lane == 0 && ball) base = atomicAdd(work_count, __popc(ball));
+    if (lane == 0 && ball) base = atomicAdd(&F.sc[SC_WORK], __popc(ball));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (near) worklist[base + __popc(ball & ((1u << lane) - 1))] = m;
+    if (near) F.worklist[base + __popc(ball & ((1u << lane) - 1))] = m;
     // block max of the molecule radius (rounded up)
     float r = sqrtf(r2max) * 1.000001f + 1e-6f;
     for (int o = 16; o; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
-    if (lane == 0 && r > 0.f) atomicMax(rmax_bits, __float_as_int(r));
+    if (lane == 0 && r > 0.f) atomicMax(&F.sc[SC_RMAX], __float_as_int(r));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -202,120 +388,63 @@ __device__ __forceinline__ int query_cell_of(const Geom &g, float px, float py, 
 }
 
 // position (fp32, grid-relative) + lower bound of its squared distance to the solute; results reset
-__device__ __forceinline__ void emit_query(const Geom &g, const float *__restrict__ lbd2, double ex, double ey, double ez,
-                                           size_t qid, float4 *__restrict__ qpos, float4 *__restrict__ res,
-                                           int *__restrict__ qcell_count) {
+__device__ __forceinline__ void emit_query(const GridFrame &F, double ex, double ey, double ez, size_t qid) {
+    const Geom &g = F.g;
     double wx, wy, wz; wrap_to_cell(g, ex, ey, ez, wx, wy, wz);
     float px = (float)(wx - g.ctr[0]), py = (float)(wy - g.ctr[1]), pz = (float)(wz - g.ctr[2]);
-    float lb = cull_lb2(g, lbd2, px, py, pz);
-    qpos[qid] = make_float4(px, py, pz, lb);
-    res[qid] = make_float4(CUDART_INF_F, CUDART_INF_F, __int_as_float(-1), 0.f);
-    if (lb <= g.cut_hi2) atomicAdd(&qcell_count[query_cell_of(g, px, py, pz)], 1);
+    float lb = cull_lb2(g, F.lbd2, px, py, pz);
+    F.qpos[qid] = make_float4(px, py, pz, lb);
+    F.res[qid] = make_float4(CUDART_INF_F, CUDART_INF_F, __int_as_float(-1), 0.f);
+    if (lb <= g.cut_hi2) atomicAdd(&F.qcell_count[query_cell_of(g, px, py, pz)], 1);
 }
 
-__global__ void k_gen_real(Geom g, Prob P, const float *__restrict__ xv, const float *__restrict__ lbd2,
-                           const int *__restrict__ worklist, const int *__restrict__ work_count, float4 *__restrict__ qpos,
-                           float4 *__restrict__ res, int *__restrict__ qcell_count) {
+__global__ void k_gen_real(const GridFrame *__restrict__ fds, Prob P) {
+    CMX_FRAME(F)
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)(*work_count) * P.nv_apm;
+    long long total = (long long)F.sc[SC_WORK] * P.nv_apm;
     for (; t < total; t += (long long)gridDim.x * blockDim.x) {
         int w = (int)(t / P.nv_apm), k = (int)(t - (long long)w * P.nv_apm);
-        const float *x = xv + ((size_t)worklist[w] * P.nv_apm + k) * 3;
-        emit_query(g, lbd2, (double)x[0], (double)x[1], (double)x[2], (size_t)t, qpos, res, qcell_count);
+        const float *x = F.xv + ((size_t)F.worklist[w] * P.nv_apm + k) * 3;
+        emit_query(F, (double)x[0], (double)x[1], (double)x[2], (size_t)t);
     }
 }
 
 __global__ void __launch_bounds__(128)
-k_gen_rand(Geom g, Prob P, uint32_t frame, int s0, const float *__restrict__ xv, const float *__restrict__ lbd2,
-           const int *__restrict__ worklist, const int *__restrict__ work_count, const int *__restrict__ bulk_idx,
-           const int *__restrict__ n_bulk_ptr, float4 *__restrict__ qpos, double *__restrict__ xexact,
-           float4 *__restrict__ res, int *__restrict__ qcell_count) {
-    const int count = *work_count;
+k_gen_rand(const GridFrame *__restrict__ fds, Prob P, int s0) {
+    CMX_FRAME(F)
+    const int count = F.sc[SC_RWORK];
+    const int nb = F.sc[SC_NBULK];
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
-        int item = worklist[w];
+        int item = F.rand_worklist[w];
         int sl = item / P.nv_mols, mol = item - sl * P.nv_mols;
         int sample = s0 + sl;
-        uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
-        uint4 r1 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 1u, P.seed_lo, P.seed_hi);
-        int nb = *n_bulk_ptr;
-        int jmol = nb > 0 ? bulk_idx[pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
-        RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
+        uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 0u, P.seed_lo, P.seed_hi);
+        uint4 r1 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 1u, P.seed_lo, P.seed_hi);
+        int jmol = nb > 0 ? F.bulk_idx[pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
+        RandMol rm; rm.init(g, F.xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
         for (int k = 0; k < P.nv_apm; ++k) {
             double ex, ey, ez; rm.get(g, k, ex, ey, ez);
             size_t o = (size_t)w * P.nv_apm + k;
-            xexact[3 * o] = ex; xexact[3 * o + 1] = ey; xexact[3 * o + 2] = ez;
-            emit_query(g, lbd2, ex, ey, ez, o, qpos, res, qcell_count);
+            F.xexact[3 * o] = ex; F.xexact[3 * o + 1] = ey; F.xexact[3 * o + 2] = ez;
+            emit_query(F, ex, ey, ez, o);
         }
     }
 }
 
-// tiles never straddle query cells: a cell with n query atoms owns ceil(n/32) tiles
-struct TileCountOp { __host__ __device__ __forceinline__ int operator()(int n) const { return (n + 31) >> 5; } };
-
-// Exclusive scan of a SMALL array (cell / tile counts of one frame: tens of thousands of ints) by ONE block in ONE
-// launch -- the two-kernel decoupled look-back scan of cub only pays off for the large grids (C4, C5), where the
-// host keeps using it.  Four items per thread per pass (16-byte loads when aligned), carry kept in shared memory.
-#define CMX_SCAN_THREADS 1024
-#define CMX_SCAN_SMALL_MAX (1 << 17)
-template <class Op>
-__global__ void __launch_bounds__(CMX_SCAN_THREADS)
-k_scan_small(const int *__restrict__ in, int *__restrict__ out, int n, Op op) {
-    __shared__ int warp_sums[32];
-    __shared__ int carry_s;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += 4 * CMX_SCAN_THREADS) {
-        const int i0 = base + 4 * threadIdx.x;
-        const int carry = carry_s;     // stable here: written between the two barriers below, read again only after the third
-        int v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? op(in[i0 + k]) : 0;
-        const int mine = v[0] + v[1] + v[2] + v[3];
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) warp_sums[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int ws = warp_sums[lane], wi = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-            warp_sums[lane] = wi - ws;             // exclusive prefix of the warp totals
-            if (lane == 31) carry_s = carry + wi;  // every thread took its copy of the old value before the barrier above
-        }
-        __syncthreads();
-        int run = carry + warp_sums[wid] + (incl - mine);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = run; run += v[k]; }
-        __syncthreads();                            // warp_sums / carry_s are rewritten by the next pass
-    }
-}
-struct IdentityOp { __host__ __device__ __forceinline__ int operator()(int n) const { return n; } };
-
-// bulk molecules of the current solute molecule (inbulk, src/mddf.jl:55-57; the solute itself is skipped in
-// an autocorrelation, :409) -- predicate of the ordered stream compaction
-struct BulkPred {
-    const MdRec *list; int skip_mol, usecutoff; double dbulk;
-    __device__ __forceinline__ bool operator()(int m) const {
-        if (m == skip_mol) return false;
-        const MdRec e = list[m];
-        return usecutoff ? ((e.flags & 1) && e.d > dbulk) : !(e.flags & 1);
-    }
-};
-
-// scatter the counted query atoms into their cell's tiles: qsorted[tile*32 + rank] = {x, y, z, query id};
-// the unused slots of a cell's last tile keep the id -1 (the array is pre-filled with 0xff bytes)
-__global__ void k_qscatter(Geom g, Prob P, const int *__restrict__ work_count, const float4 *__restrict__ qpos,
-                           int *__restrict__ qcell_count, const int *__restrict__ tile_start, float4 *__restrict__ qsorted) {
+// scatter the counted query atoms into their cell's tiles: qsorted[tile*32 + rank] = {x, y, z, query id}; the
+// ranks of a cell with n atoms are 0..n-1, so the valid lanes of its tiles are the ones k_chain_scan<ScanTiles>
+// recorded in tile_valid -- the unused lanes of a cell's last tile are never written nor read
+template <bool RANDOM>
+__global__ void k_qscatter(const GridFrame *__restrict__ fds, Prob P) {
+    CMX_FRAME(F)
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)(*work_count) * P.nv_apm;
+    long long total = (long long)F.sc[RANDOM ? SC_RWORK : SC_WORK] * P.nv_apm;
     for (; t < total; t += (long long)gridDim.x * blockDim.x) {
-        float4 q = qpos[t];
+        float4 q = F.qpos[t];
         if (q.w <= g.cut_hi2) {
             int c = query_cell_of(g, q.x, q.y, q.z);
-            size_t slot = (size_t)tile_start[c] * 32 + (size_t)(atomicSub(&qcell_count[c], 1) - 1);
-            qsorted[slot] = make_float4(q.x, q.y, q.z, __int_as_float((int)t));
+            size_t slot = (size_t)F.qcell_start[c] * 32 + (size_t)(atomicSub(&F.qcell_count[c], 1) - 1);
+            F.qsorted[slot] = make_float4(q.x, q.y, q.z, __int_as_float((int)t));
         }
     }
 }
@@ -328,47 +457,73 @@ __global__ void k_qscatter(Geom g, Prob P, const int *__restrict__ work_count, c
 // bitmask), then visited nearest-first; after every row the tile bound shrinks to the largest
 // best-distance of its lanes.  Each lane keeps best / second-best squared distance and the solute
 // atom of the best: res[query] = {b1, b2, atom}.
+// The tiles of ALL frames of the batch form one queue (frames differ in how many tiles survive the
+// cull): a warp takes the next (frame, tile) with one atomic, so the batch is balanced as a whole.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int fkey(float x) { int i = __float_as_int(x); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
 __device__ __forceinline__ float warp_minf(float x) { return fkey_inv(__reduce_min_sync(0xffffffffu, fkey(x))); }
 __device__ __forceinline__ float warp_maxf(float x) { return fkey_inv(__reduce_max_sync(0xffffffffu, fkey(x))); }
 
+// what the search needs of a frame, in shared memory for every frame of the batch
+struct SearchFrame {
+    const int *cell_start; const float4 *sorted; const u64 *rowmask; const float4 *qsorted; const unsigned char *tile_valid;
+    float4 *res;
+    float gmin[3], side, inv_side, inv_sidex, search2, tol_d2;
+    int nx, ny, nz, rw, tile_end;     // tile_end: end of this frame's range in the batch-wide tile numbering
+};
+#define CMX_MAX_BATCH 32
 #define CMX_ROWS_PER_LANE 4
-template <bool COUNT>
+template <bool COUNT, bool RANDOM>
 __global__ void __launch_bounds__(256)
-k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restrict__ sorted,
-              const u64 *__restrict__ rowmask, const float4 *__restrict__ qsorted, const int *__restrict__ qcell_start,
-              int nqcells, float4 *__restrict__ res, u64 *__restrict__ pair_evals, int *__restrict__ tile_queue) {
+k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ pair_evals) {
+    __shared__ SearchFrame sf[CMX_MAX_BATCH];
+    __shared__ float4 stage[8][32];               // per warp: one chunk of solute atoms
     const int lane = threadIdx.x & 31;
-    const int ntiles = qcell_start[nqcells];     // exclusive scan of the per-cell tile counts
+    if (threadIdx.x < nframes) {
+        const GridFrame &F = fds[threadIdx.x];
+        SearchFrame s;
+        s.cell_start = F.cell_start; s.sorted = F.sorted; s.rowmask = F.rowmask; s.qsorted = F.qsorted; s.tile_valid = F.tile_valid; s.res = F.res;
+        s.gmin[0] = F.g.gmin[0]; s.gmin[1] = F.g.gmin[1]; s.gmin[2] = F.g.gmin[2];
+        s.side = F.g.side; s.inv_side = F.g.inv_side; s.inv_sidex = F.g.inv_sidex; s.search2 = F.g.search2; s.tol_d2 = F.g.tol_d2;
+        s.nx = F.g.nx; s.ny = F.g.ny; s.nz = F.g.nz; s.rw = F.g.rw;
+        s.tile_end = F.qcell_start[F.nqcells];    // exclusive scan of the per-cell tile counts: total tiles of the frame
+        sf[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int k = 0; k < nframes; ++k) { run += sf[k].tile_end; sf[k].tile_end = run; } }
+    __syncthreads();
+    const int ntiles_all = sf[nframes - 1].tile_end;
+    int *tile_queue = fds[0].sc + (RANDOM ? SC_TQ_RAND : SC_TQ_REAL);
     const float slack = 2e-3f;
     unsigned long long npairs = 0;
-    __shared__ float4 stage[8][32];               // per warp: one chunk of solute atoms
     float4 *st = stage[threadIdx.x >> 5];
-    // tiles differ widely in cost (distance to the solute): the resident warps pull them from a queue (zeroed with
-    // the frame's scalars) instead of owning a fixed share, and the grid is exactly one resident wave
     while (true) {
-        int tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_queue, 1);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
-        float4 q = __ldg(&qsorted[(size_t)tile * 32 + lane]);
-        const bool valid = __float_as_int(q.w) >= 0;
-        {   // unused slots shadow the tile's first query (always present)
-            float x0 = __shfl_sync(0xffffffffu, q.x, 0), y0 = __shfl_sync(0xffffffffu, q.y, 0), z0 = __shfl_sync(0xffffffffu, q.z, 0);
-            if (!valid) { q.x = x0; q.y = y0; q.z = z0; }
-        }
+        int gt = 0;
+        if (lane == 0) gt = atomicAdd(tile_queue, 1);
+        gt = __shfl_sync(0xffffffffu, gt, 0);
+        if (gt >= ntiles_all) break;
+        int fi = 0;
+        while (gt >= sf[fi].tile_end) ++fi;
+        const SearchFrame &S = sf[fi];
+        const int tile = gt - (fi ? sf[fi - 1].tile_end : 0);
+        const int nvalid = S.tile_valid[tile];
+        const bool valid = lane < nvalid;
+        float4 q = __ldg(&S.qsorted[(size_t)tile * 32 + (valid ? lane : 0)]);   // unused lanes shadow the tile's first query
         const float xmin = warp_minf(q.x), xmax = warp_maxf(q.x), ymin = warp_minf(q.y), ymax = warp_maxf(q.y),
                     zmin = warp_minf(q.z), zmax = warp_maxf(q.z);
         float b1 = CUDART_INF_F, b2 = CUDART_INF_F; int bi = -1;
-        float bound = g.search2;
+        float bound = S.search2;
+        const float gmin0 = S.gmin[0], gmin1 = S.gmin[1], gmin2 = S.gmin[2], side = S.side, inv_side = S.inv_side, inv_sidex = S.inv_sidex;
+        const int nx = S.nx, ny = S.ny, nz = S.nz, rw = S.rw;
         const float reach = sqrtf(bound) + slack;
-        const int ry_lo = max((int)floorf((ymin - reach - g.gmin[1]) * g.inv_side), 0);
-        const int ry_hi = min((int)floorf((ymax + reach - g.gmin[1]) * g.inv_side), g.ny - 1);
-        const int rz_lo = max((int)floorf((zmin - reach - g.gmin[2]) * g.inv_side), 0);
-        const int rz_hi = min((int)floorf((zmax + reach - g.gmin[2]) * g.inv_side), g.nz - 1);
+        const int ry_lo = max((int)floorf((ymin - reach - gmin1) * inv_side), 0);
+        const int ry_hi = min((int)floorf((ymax + reach - gmin1) * inv_side), ny - 1);
+        const int rz_lo = max((int)floorf((zmin - reach - gmin2) * inv_side), 0);
+        const int rz_hi = min((int)floorf((zmax + reach - gmin2) * inv_side), nz - 1);
         const int nry = ry_hi - ry_lo + 1, nrows = nry * (rz_hi - rz_lo + 1);
+        const int *__restrict__ cell_start = S.cell_start;
+        const float4 *__restrict__ sorted = S.sorted;
         for (int chunk = 0; chunk < nrows; chunk += 32 * CMX_ROWS_PER_LANE) {
             // ---- probe: lane handles rows chunk + u*32 + lane
             float rd[CMX_ROWS_PER_LANE];
@@ -380,16 +535,16 @@ k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restri
                 if (r < nrows) {
                     int rzq = r / nry;
                     int ry = ry_lo + (r - rzq * nry), rz = rz_lo + rzq;
-                    rrow[u] = rz * g.ny + ry;
-                    float y0 = g.gmin[1] + ry * g.side, z0 = g.gmin[2] + rz * g.side;
-                    float gy = fmaxf(fmaxf(y0 - ymax, ymin - (y0 + g.side)) - slack, 0.f);
-                    float gz = fmaxf(fmaxf(z0 - zmax, zmin - (z0 + g.side)) - slack, 0.f);
+                    rrow[u] = rz * ny + ry;
+                    float y0 = gmin1 + ry * side, z0 = gmin2 + rz * side;
+                    float gy = fmaxf(fmaxf(y0 - ymax, ymin - (y0 + side)) - slack, 0.f);
+                    float gz = fmaxf(fmaxf(z0 - zmax, zmin - (z0 + side)) - slack, 0.f);
                     float r2 = gy * gy + gz * gz;
                     if (r2 <= bound) {
                         float hx = sqrtf(bound - r2) + slack;
-                        int cxl = max((int)floorf((xmin - hx - g.gmin[0]) * g.inv_sidex), 0);
-                        int cxh = min((int)floorf((xmax + hx - g.gmin[0]) * g.inv_sidex), g.nx - 1);
-                        const u64 *mrow = rowmask + (size_t)(rz * g.ny + ry) * g.rw;
+                        int cxl = max((int)floorf((xmin - hx - gmin0) * inv_sidex), 0);
+                        int cxh = min((int)floorf((xmax + hx - gmin0) * inv_sidex), nx - 1);
+                        const u64 *mrow = S.rowmask + (size_t)(rz * ny + ry) * rw;
                         bool any = false;
                         for (int w = cxl >> 6; w <= (cxh >> 6) && cxl <= cxh; ++w) {
                             u64 m = __ldg(&mrow[w]);
@@ -415,10 +570,10 @@ k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restri
                     for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) if (u == um) rd[u] = CUDART_INF_F;
                 }
                 float hx = sqrtf(bound - wm) + slack;
-                int cxl = max((int)floorf((xmin - hx - g.gmin[0]) * g.inv_sidex), 0);
-                int cxh = min((int)floorf((xmax + hx - g.gmin[0]) * g.inv_sidex), g.nx - 1);
+                int cxl = max((int)floorf((xmin - hx - gmin0) * inv_sidex), 0);
+                int cxh = min((int)floorf((xmax + hx - gmin0) * inv_sidex), nx - 1);
                 if (cxl > cxh) continue;
-                int rowbase = row * g.nx;
+                int rowbase = row * nx;
                 int a = __ldg(&cell_start[rowbase + cxl]), b = __ldg(&cell_start[rowbase + cxh + 1]);
                 // the row's atoms are fetched 32 at a time with one coalesced load (next chunk prefetched into
                 // registers), staged in shared memory and then read by every lane as broadcasts
@@ -440,11 +595,11 @@ k_tile_search(Geom g, const int *__restrict__ cell_start, const float4 *__restri
                     }
                 }
                 if (COUNT) npairs += (unsigned long long)(b - a);
-                float mine = valid ? fminf(b1 + g.tol_d2, g.search2) : 0.f;
+                float mine = valid ? fminf(b1 + S.tol_d2, S.search2) : 0.f;
                 bound = fminf(bound, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mine))));
             }
         }
-        if (valid) res[__float_as_int(q.w)] = make_float4(b1, b2, __int_as_float(bi), 0.f);
+        if (valid) S.res[__float_as_int(q.w)] = make_float4(b1, b2, __int_as_float(bi), 0.f);
     }
     if (COUNT && pair_evals) {
         npairs *= 32ull;
@@ -469,34 +624,35 @@ __device__ __forceinline__ int classify(const Geom &g, float b1, float b2) {
 // ---------------------------------------------------------------------------------------------
 template <bool RANDOM>
 __global__ void __launch_bounds__(128)
-k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict__ xv, const float4 *__restrict__ res,
-           const double *__restrict__ xexact, const int *__restrict__ worklist, const int *__restrict__ work_count,
-           MdRec *__restrict__ list, u64 *__restrict__ deferred, float2 *__restrict__ deferred_info,
-           int *__restrict__ deferred_count, int s0) {
-    const int count = *work_count;
+k_finalise(const GridFrame *__restrict__ fds, Prob P, int s0) {
+    CMX_FRAME(F)
+    const int count = F.sc[RANDOM ? SC_RWORK : SC_WORK];
+    const int *worklist = RANDOM ? F.rand_worklist : F.worklist;
+    const float *xs = F.xs, *xv = F.xv;
+    MdRec *list = RANDOM ? F.rand_list : F.list;
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
         const int item = worklist[w];
         int sample = 0, mol = item;
         if (RANDOM) { int sl = item / P.nv_mols; mol = item - sl * P.nv_mols; sample = s0 + sl; }
-        const float4 *r = res + (size_t)w * P.nv_apm;
+        const float4 *r = F.res + (size_t)w * P.nv_apm;
         float best = CUDART_INF_F, second = CUDART_INF_F; int bi = -1, bk = -1;
         for (int k = 0; k < P.nv_apm; ++k) {
-            float4 a = __ldg(&r[k]);
+            float4 a = r[k];
             if (a.x < best) { second = fminf(fminf(second, best), a.y); best = a.x; bi = __float_as_int(a.z); bk = k; }
             else second = fminf(second, a.x);
         }
         int cls = classify(g, best, second);
         if (cls == 0) continue;   // list entry stays "not within"
-        float4 rr = __ldg(&r[P.iref]);
+        float4 rr = r[P.iref];
         int rcls = classify(g, rr.x, rr.y);
         if (cls == 2 || rcls == 2) {
-            int slot = atomicAdd(deferred_count, 1);
-            deferred[slot] = ((u64)(RANDOM ? 1 + sample : 0) << 32) | (u64)(uint32_t)mol;
-            deferred_info[slot] = make_float2(best, rr.x);   // fp32 bounds: the exact kernel only looks at atoms that can matter
+            int slot = atomicAdd(&F.sc[RANDOM ? SC_DEF_RAND : SC_DEF_REAL], 1);
+            (RANDOM ? F.def_rand : F.def_real)[slot] = ((u64)(RANDOM ? 1 + sample : 0) << 32) | (u64)(uint32_t)mol;
+            (RANDOM ? F.def_rand_info : F.def_real_info)[slot] = make_float2(best, rr.x);   // fp32 bounds: the exact kernel only looks at atoms that can matter
             continue;
         }
         auto pos = [&](int k, double &ex, double &ey, double &ez) {
-            if (RANDOM) { const double *xe = xexact + ((size_t)P.nv_apm * w + k) * 3; ex = xe[0]; ey = xe[1]; ez = xe[2]; }
+            if (RANDOM) { const double *xe = F.xexact + ((size_t)P.nv_apm * w + k) * 3; ex = xe[0]; ey = xe[1]; ez = xe[2]; }
             else { const float *xr = xv + ((size_t)P.nv_apm * mol + k) * 3; ex = (double)xr[0]; ey = (double)xr[1]; ez = (double)xr[2]; }
         };
         double ex, ey, ez;
@@ -510,8 +666,8 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
             e.dref = dist_pbc64(g, (double)xs[3 * ri], (double)xs[3 * ri + 1], (double)xs[3 * ri + 2], ex, ey, ez);
             e.flags |= 2;
         }
-        count_hit(P, RANDOM, e.d, e.i, e.j, 1ull);
-        if (e.flags & 2) count_ref(P, RANDOM, e.dref);
+        count_hit(P, F.weight, RANDOM, e.d, e.i, e.j, 1ull);
+        if (e.flags & 2) count_ref(P, F.weight, RANDOM, e.dref);
         if (list) list[RANDOM ? (size_t)sample * P.nv_mols + mol : (size_t)mol] = e;
     }
 }
@@ -519,43 +675,44 @@ k_finalise(Geom g, Prob P, const float *__restrict__ xs, const float *__restrict
 // ---------------------------------------------------------------------------------------------
 // Random-phase cull: the random placements, by the position of their centre
 // ---------------------------------------------------------------------------------------------
-// grid.y = sample, grid.x covers the slots; the centre is evaluated in fp32 (its error, ~1e-5 A, is far
+// grid.z strides the samples, grid.x covers the slots; the centre is evaluated in fp32 (its error, ~1e-5 A, is far
 // below the 1e-3 A margin of the test); survivors are appended with one global atomic per block
 __global__ void __launch_bounds__(256)
-k_filter_rand(Geom g, Prob P, uint32_t frame, int isolute, int skip_mol, int s0, int s1, const float *__restrict__ lbd2,
-              const int *__restrict__ rmax_bits, int *__restrict__ worklist, int *__restrict__ work_count) {
+k_filter_rand(const GridFrame *__restrict__ fds, Prob P, int s0, int s1) {
+    CMX_FRAME(F)
     __shared__ int s_count, s_base;
+    if (F.nrand_k == 0) return;                  // this solute molecule is the reference of no sample of the frame
     const int mol = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int sample = s0 + blockIdx.y; sample < s1; sample += gridDim.y) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    bool near = false;
-    if (mol < P.nv_mols && mol != skip_mol) {
-        bool mine = P.ns_mols == 1 || ref_solute_of_sample(P, frame, (uint32_t)sample) == isolute;
-        if (mine) {
-            float rmax = __int_as_float(*rmax_bits);
-            if (rmax > g.rmax_bound) near = true;   // transform window not valid for this radius: no culling
-            else {
-                uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
-                const float sc = 1.0f / 4294967296.0f;
-                float u0 = ((float)r0.y + 0.5f) * sc, u1 = ((float)r0.z + 0.5f) * sc, u2 = ((float)r0.w + 0.5f) * sc;
-                float cx_ = (float)g.m[0] * u0 + (float)g.m[3] * u1 + (float)g.m[6] * u2 - (float)g.ctr[0];
-                float cy_ = (float)g.m[1] * u0 + (float)g.m[4] * u1 + (float)g.m[7] * u2 - (float)g.ctr[1];
-                float cz_ = (float)g.m[2] * u0 + (float)g.m[5] * u1 + (float)g.m[8] * u2 - (float)g.ctr[2];
-                float lim = g.cut_hi + rmax + 2e-3f;
-                near = cull_lb2(g, lbd2, cx_, cy_, cz_) <= lim * lim;
+    const float rmax = __int_as_float(F.sc[SC_RMAX]);
+    for (int sample = s0 + blockIdx.z; sample < s1; sample += gridDim.z) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        bool near = false;
+        if (mol < P.nv_mols && mol != F.skip_mol) {
+            bool mine = P.ns_mols == 1 || ref_solute_of_sample(P, F.frame, (uint32_t)sample) == F.isolute;
+            if (mine) {
+                if (rmax > g.rmax_bound) near = true;   // transform window not valid for this radius: no culling
+                else {
+                    uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 0u, P.seed_lo, P.seed_hi);
+                    const float sc = 1.0f / 4294967296.0f;
+                    float u0 = ((float)r0.y + 0.5f) * sc, u1 = ((float)r0.z + 0.5f) * sc, u2 = ((float)r0.w + 0.5f) * sc;
+                    float cx_ = (float)g.m[0] * u0 + (float)g.m[3] * u1 + (float)g.m[6] * u2 - (float)g.ctr[0];
+                    float cy_ = (float)g.m[1] * u0 + (float)g.m[4] * u1 + (float)g.m[7] * u2 - (float)g.ctr[1];
+                    float cz_ = (float)g.m[2] * u0 + (float)g.m[5] * u1 + (float)g.m[8] * u2 - (float)g.ctr[2];
+                    float lim = g.cut_hi + rmax + 2e-3f;
+                    near = cull_lb2(g, F.lbd2, cx_, cy_, cz_) <= lim * lim;
+                }
             }
         }
-    }
-    unsigned ball = __ballot_sync(0xffffffffu, near);
-    int lane = threadIdx.x & 31, wbase = 0;
-    if (lane == 0 && ball) wbase = atomicAdd(&s_count, __popc(ball));
-    __syncthreads();
-    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(work_count, s_count);
-    __syncthreads();
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (near) worklist[s_base + wbase + __popc(ball & ((1u << lane) - 1))] = (sample - s0) * P.nv_mols + mol;   // item within the chunk
+        unsigned ball = __ballot_sync(0xffffffffu, near);
+        int lane = threadIdx.x & 31, wbase = 0;
+        if (lane == 0 && ball) wbase = atomicAdd(&s_count, __popc(ball));
+        __syncthreads();
+        if (threadIdx.x == 0 && s_count) s_base = atomicAdd(&F.sc[SC_RWORK], s_count);
+        __syncthreads();
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (near) F.rand_worklist[s_base + wbase + __popc(ball & ((1u << lane) - 1))] = (sample - s0) * P.nv_mols + mol;   // item within the chunk
     }
 }
 
@@ -578,7 +735,7 @@ __device__ __forceinline__ bool better(double d, int j, int i, const ExactBest &
 template <class Mol>
 __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const float *__restrict__ xs,
                                             const float4 *__restrict__ sorted, const int *__restrict__ cell_start,
-                                            const Mol &mol, int molidx, bool random, float2 info, MdRec *out, ExactBest *sh) {
+                                            const Mol &mol, int molidx, bool random, double weight, float2 info, MdRec *out, ExactBest *sh) {
     const float capd = g.cut_hi + 4.f * g.tau;
     float lim_m = fminf(sqrtf(info.x) + 4.f * g.tau, capd), lim_r = fminf(sqrtf(info.y) + 4.f * g.tau, capd);
     lim_m *= lim_m; lim_r *= lim_r;
@@ -633,8 +790,8 @@ __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const 
         if (r.d <= g.cutd) {
             e.d = r.d; e.i = r.i; e.j = r.j; e.flags = 1;
             if (r.dref <= g.cutd) { e.dref = r.dref; e.flags |= 2; }
-            count_hit(P, random, e.d, e.i, e.j, 1ull);
-            if (e.flags & 2) count_ref(P, random, e.dref);
+            count_hit(P, weight, random, e.d, e.i, e.j, 1ull);
+            if (e.flags & 2) count_ref(P, weight, random, e.dref);
         }
         if (out) *out = e;
     }
@@ -642,31 +799,33 @@ __device__ __forceinline__ void resolve_one(const Geom &g, const Prob &P, const 
 }
 
 #define CMX_RESOLVE_THREADS 256
+// RANDOM=false: the real-phase deferred molecules (their list entries feed the bulk list, so this runs before the
+// bulk compaction); RANDOM=true: the random-phase ones.  stats[1] accumulates the number of deferred molecules.
+template <bool RANDOM>
 __global__ void __launch_bounds__(CMX_RESOLVE_THREADS)
-k_resolve(Geom g, Prob P, uint32_t frame, const float *__restrict__ xs, const float *__restrict__ xv,
-          const float4 *__restrict__ sorted, const int *__restrict__ cell_start, int ncells, const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk_ptr, const u64 *__restrict__ deferred,
-          const float2 *__restrict__ deferred_info, const int *__restrict__ deferred_count, MdRec *__restrict__ list,
-          MdRec *__restrict__ rand_list, u64 *__restrict__ stats, const int *__restrict__ stat_a, const int *__restrict__ stat_b) {
+k_resolve(const GridFrame *__restrict__ fds, Prob P, u64 *__restrict__ stats) {
+    CMX_FRAME(F)
     __shared__ ExactBest sh[CMX_RESOLVE_THREADS];
-    int count = *deferred_count;
-    if (stats && blockIdx.x == 0 && threadIdx.x == 0)   // run statistics: molecules that took the exact path
-        atomicAdd(&stats[1], (u64)(stat_a ? *stat_a : 0) + (u64)(stat_b ? *stat_b : 0));
-    (void)ncells;
+    const int count = F.sc[RANDOM ? SC_DEF_RAND : SC_DEF_REAL];
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0 && count) atomicAdd(&stats[1], (u64)count);
+    const u64 *deferred = RANDOM ? F.def_rand : F.def_real;
+    const float2 *deferred_info = RANDOM ? F.def_rand_info : F.def_real_info;
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         u64 item = deferred[w];
         const float2 info = deferred_info[w];
         int phase = (int)(item >> 32), mol = (int)(item & 0xffffffffu);
-        if (phase == 0) {
-            RealMolG rl; rl.m.x = xv + (size_t)3 * P.nv_apm * mol;
-            resolve_one(g, P, xs, sorted, cell_start, rl, mol, false, info, list ? &list[mol] : nullptr, sh);
+        if (!RANDOM) {
+            RealMolG rl; rl.m.x = F.xv + (size_t)3 * P.nv_apm * mol;
+            resolve_one(g, P, F.xs, F.sorted, F.cell_start, rl, mol, false, F.weight, info, &F.list[mol], sh);
         } else {
             int sample = phase - 1;
-            uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 0u, P.seed_lo, P.seed_hi);
-            uint4 r1 = philox4x32((uint32_t)mol, (uint32_t)sample, frame, 1u, P.seed_lo, P.seed_hi);
-            int nb = *n_bulk_ptr;
-            int jmol = nb > 0 ? bulk_idx[pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
-            RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
-            resolve_one(g, P, xs, sorted, cell_start, rm, mol, true, info, rand_list ? &rand_list[(size_t)sample * P.nv_mols + mol] : nullptr, sh);
+            uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 0u, P.seed_lo, P.seed_hi);
+            uint4 r1 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 1u, P.seed_lo, P.seed_hi);
+            int nb = F.sc[SC_NBULK];
+            int jmol = nb > 0 ? F.bulk_idx[pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
+            RandMol rm; rm.init(g, F.xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
+            resolve_one(g, P, F.xs, F.sorted, F.cell_start, rm, mol, true, F.weight, info,
+                        F.rand_list ? &F.rand_list[(size_t)sample * P.nv_mols + mol] : nullptr, sh);
         }
     }
 }

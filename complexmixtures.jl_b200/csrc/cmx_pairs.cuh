@@ -225,11 +225,11 @@ __device__ __forceinline__ void finish_pair(const Geom &g, const PairGeom &pg, c
     if (!single_image_ok || cls == 2 || rcls == 2 || (SYM && qcls == 2)) { defer_pair(deferred, def_count, cap, 0, a, b); return; }
     const float *xa = xs + (size_t)3 * P.ns_apm * a, *xb = xv + (size_t)3 * P.nv_apm * b;
     double d = exact_atoms(g, xa, F.i, xb, F.j);
-    count_hit(P, false, d, F.i, b * P.nv_apm + F.j, 1ull);
-    if (rcls == 1) count_ref(P, false, exact_atoms(g, xa, F.ri, xb, P.iref));
+    count_hit(P, P.w, false, d, F.i, b * P.nv_apm + F.j, 1ull);
+    if (rcls == 1) count_ref(P, P.w, false, exact_atoms(g, xa, F.ri, xb, P.iref));
     if (SYM) {   // the ordered pair (solute b, solvent a)
-        count_hit(P, false, d, F.j, a * P.nv_apm + F.i, 1ull);
-        if (qcls == 1) count_ref(P, false, exact_atoms(g, xb, F.qj, xa, P.iref));
+        count_hit(P, P.w, false, d, F.j, a * P.nv_apm + F.i, 1ull);
+        if (qcls == 1) count_ref(P, P.w, false, exact_atoms(g, xb, F.qj, xa, P.iref));
     }
 }
 
@@ -457,12 +457,12 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, int s0, int ns, const
     double ex, ey, ez; rm.get(g, bk, ex, ey, ez);
     MdRec e; e.pad = 0; e.flags = 1; e.i = bi; e.j = slot * P.nv_apm + bk; e.dref = CUDART_INF;
     e.d = dist_pbc64(g, (double)xa[3 * bi], (double)xa[3 * bi + 1], (double)xa[3 * bi + 2], ex, ey, ez);
-    count_hit(P, true, e.d, e.i, e.j, 1ull);
+    count_hit(P, P.w, true, e.d, e.i, e.j, 1ull);
     if (rcls == 1) {
         rm.get(g, P.iref, ex, ey, ez);
         e.dref = dist_pbc64(g, (double)xa[3 * ri], (double)xa[3 * ri + 1], (double)xa[3 * ri + 2], ex, ey, ez);
         e.flags |= 2;
-        count_ref(P, true, e.dref);
+        count_ref(P, P.w, true, e.dref);
     }
     if (rand_list) rand_list[(size_t)s * P.nv_mols + slot] = e;
 }
@@ -482,10 +482,10 @@ __global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, int s0, const flo
         if (phase == 0) {
             const float *xb = xv + (size_t)3 * P.nv_apm * b;
             MdRec e = exact_list_entry(g, P, xa, xb, b);
-            if (e.flags & 1) { count_hit(P, false, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, false, e.dref); }
+            if (e.flags & 1) { count_hit(P, P.w, false, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, P.w, false, e.dref); }
             if (P.autocorr) {   // the other ordered pair: solute b, solvent a
                 MdRec f = exact_list_entry(g, P, xb, xa, a);
-                if (f.flags & 1) { count_hit(P, false, f.d, f.i, f.j, 1ull); if (f.flags & 2) count_ref(P, false, f.dref); }
+                if (f.flags & 1) { count_hit(P, P.w, false, f.d, f.i, f.j, 1ull); if (f.flags & 2) count_ref(P, P.w, false, f.dref); }
             }
         } else {
             int sl = phase - 1, s = s0 + sl, slot = b;    // sl: sample within the chunk
@@ -506,7 +506,7 @@ __global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, int s0, const flo
                     }
                 }
             }
-            if (e.flags & 1) { count_hit(P, true, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, true, e.dref); }
+            if (e.flags & 1) { count_hit(P, P.w, true, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, P.w, true, e.dref); }
             if (rand_list) rand_list[(size_t)s * P.nv_mols + slot] = e;
         }
     }

@@ -41,7 +41,7 @@ class CmxConfig(C.Structure):
                 ("n_random_samples", C.c_int32), ("coordination_number_only", C.c_int32), ("lcell", C.c_int32),
                 ("n_groups_solute", C.c_int32), ("n_groups_solvent", C.c_int32), ("path", C.c_int32),
                 ("ring_slots", C.c_int32), ("keep_lists", C.c_int32), ("group_lanes", C.c_int32),
-                ("n_streams", C.c_int32), ("reserved0", C.c_int32),
+                ("n_streams", C.c_int32), ("batch_frames", C.c_int32),
                 ("cutoff", C.c_double), ("dbulk", C.c_double), ("binstep", C.c_double), ("seed", C.c_uint64),
                 ("solute_group_offsets", C.c_void_p), ("solute_group_ids", C.c_void_p),
                 ("solvent_group_offsets", C.c_void_p), ("solvent_group_ids", C.c_void_p)]
@@ -220,7 +220,7 @@ class Engine:
 
     def __init__(self, *, solute, solvent, options, irefatom: int, autocorrelation: bool,
                  coordination_number_only: bool = False, device: int = 0, path: int = 0, keep_lists: bool = False,
-                 ring_slots: int = 3, group_lanes: int = 0, n_streams: int = 0):
+                 ring_slots: int = 0, group_lanes: int = 0, n_streams: int = 0, batch_frames: int = 0):
         self.lib = load_library()
         cfg = CmxConfig()
         cfg.struct_size = C.sizeof(CmxConfig)
@@ -236,6 +236,7 @@ class Engine:
         cfg.n_groups_solute, cfg.n_groups_solvent = solute.n_groups, solvent.n_groups
         cfg.path, cfg.ring_slots, cfg.keep_lists, cfg.group_lanes = path, ring_slots, int(keep_lists), group_lanes
         cfg.n_streams = n_streams
+        cfg.batch_frames = batch_frames
         cfg.cutoff, cfg.dbulk, cfg.binstep = options.cutoff, options.dbulk, options.binstep
         cfg.seed = options.seed if options.seed > 0 else 0
         self._keep = []

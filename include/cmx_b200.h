@@ -54,11 +54,11 @@ typedef struct cmx_config {
     int32_t n_groups_solute;          /* rows of solute_group_count (natomspermol or #groups)     */
     int32_t n_groups_solvent;
     int32_t path;                     /* 0 auto, 1 grid path (large solute molecule), 2 molecule-pair path */
-    int32_t ring_slots;               /* pinned staging slots of acquire/submit (0 -> 3)         */
+    int32_t ring_slots;               /* pinned staging slots of acquire/submit (0 -> one per frame of every batch in flight + 1) */
     int32_t keep_lists;               /* keep per-frame minimum-distance lists for cmx_read_*    */
     int32_t group_lanes;              /* reserved (ignored: the search works on 32-query tiles)  */
-    int32_t n_streams;                /* frames in flight on separate compute streams (0 -> 8; 4 above 2 M atoms) */
-    int32_t reserved0;
+    int32_t n_streams;                /* batches in flight on separate compute streams (0 -> auto)             */
+    int32_t batch_frames;             /* frames per kernel launch on the grid path (0 -> auto: 16 for small systems ... 1 above 4 M atoms; <= 32) */
     double cutoff;                    /* Options.cutoff                                          */
     double dbulk;                     /* Options.dbulk                                           */
     double binstep;                   /* Options.binstep                                         */

@@ -20,7 +20,7 @@ struct CmxConfig
     solute_nmols::Int32; solute_natomspermol::Int32; solvent_nmols::Int32; solvent_natomspermol::Int32
     autocorrelation::Int32; irefatom::Int32; usecutoff::Int32; n_random_samples::Int32
     coordination_number_only::Int32; lcell::Int32; n_groups_solute::Int32; n_groups_solvent::Int32
-    path::Int32; ring_slots::Int32; keep_lists::Int32; group_lanes::Int32; n_streams::Int32; reserved0::Int32
+    path::Int32; ring_slots::Int32; keep_lists::Int32; group_lanes::Int32; n_streams::Int32; batch_frames::Int32
     cutoff::Float64; dbulk::Float64; binstep::Float64; seed::UInt64
     solute_group_offsets::Ptr{Int32}; solute_group_ids::Ptr{Int32}
     solvent_group_offsets::Ptr{Int32}; solvent_group_ids::Ptr{Int32}
