@@ -151,8 +151,9 @@ struct cmx_handle {
     size_t ns_atoms = 0, nv_atoms = 0, in_floats = 0;
     double cut_eff = 0;
     int Kdiv = 2;
-    double side = 0, sidex = 0, cside = 0, qside = 0;
+    double side = 0, sidex = 0, cside = 0, qside = 0, ring_width = 2.5;
     cudaStream_t s_copy = nullptr;
+    size_t hist_smem = 0;           // bytes of the shared-memory histograms (HistPriv) of the counting kernels
     int batch = 1;                  // frames per batch (grid path); 1 on the molecule-pair path
     int fill = 0;                   // index of the batch context being filled
     uint32_t scan_epoch = 0;        // launch number of the chained scans (tags their tile states)
@@ -278,6 +279,7 @@ int build_geom(cmx_handle *h, const double cell[9], Geom &g) {
     g.search2 = (float)((h->cut_eff + tau) * (h->cut_eff + tau) * (1.0 + 1e-6));
     g.tol_d2 = (float)(2.0 * h->cut_eff * tau + tau * tau);
     g.cutd = h->cut_eff;
+    g.ring = (float)h->ring_width;
     double margin = h->cut_eff + tau + 0.05;
     for (int k = 0; k < 3; ++k) {
         g.elo[k] = lo[k] - margin; g.ehi[k] = hi[k] + margin; g.ctr[k] = 0.5 * (lo[k] + hi[k]);
@@ -390,12 +392,17 @@ int search_phase(cmx_handle *h, const GridFrame *fd, unsigned nb, size_t max_ato
     const int k = pev ? 1 : 0;
     int per_sm = h->search_blocks_env > 0 ? h->search_blocks_env : std::max(1, (h->search_grid[k] / h->num_sms + nfly - 1) / nfly);
     const unsigned grid = sms * (unsigned)per_sm;
-    if (pev) k_tile_search<true, RANDOM><<<grid, 256, 0, h->cur->stream>>>(fd, (int)nb, pev);
-    else k_tile_search<false, RANDOM><<<grid, 256, 0, h->cur->stream>>>(fd, (int)nb, pev);
+    if (pev) k_tile_search<true, RANDOM><<<grid, CMX_SEARCH_WARPS * 32, CMX_SEARCH_SMEM, h->cur->stream>>>(fd, (int)nb, pev);
+    else k_tile_search<false, RANDOM><<<grid, CMX_SEARCH_WARPS * 32, CMX_SEARCH_SMEM, h->cur->stream>>>(fd, (int)nb, pev);
     h->stats.kernel_launches++;
     prof_end(h, pe);
     trace_mark(h, RANDOM ? "tile_search<rand>" : "tile_search<real>");
-    launch_y(h, k_finalise<RANDOM>, (unsigned)std::min<size_t>((max_atoms / std::max(1, h->P.nv_apm) + 127) / 128, (size_t)sms * 8), nb, 128u, fd, h->P, s0);
+    {   // persistent blocks (their private histograms are flushed once)
+        unsigned gfin = sms * 4;   // (measured on C4: 74 blocks 270 us per batch, 296 -> 90, 592 -> 70, 1184 -> 72; the flush is not the limit)
+        if (const char *e = std::getenv("CMX_FIN_BLOCKS")) gfin = (unsigned)std::max(1, atoi(e));   // experiments only
+        k_finalise<RANDOM><<<gfin, CMX_FIN_THREADS, h->hist_smem, h->cur->stream>>>(fd, (int)nb, h->P, s0);
+        h->stats.kernel_launches++;
+    }
     trace_mark(h, RANDOM ? "finalise<rand>" : "finalise<real>");
     return CMX_OK;
 }
@@ -680,8 +687,12 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     h->num_sms = prop.multiProcessorCount;
     {
         int b0 = 0, b1 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_tile_search<false, true>, 256, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_tile_search<true, true>, 256, 0));
+        CK(cudaFuncSetAttribute(k_tile_search<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMX_SEARCH_SMEM));
+        CK(cudaFuncSetAttribute(k_tile_search<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMX_SEARCH_SMEM));
+        CK(cudaFuncSetAttribute(k_tile_search<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMX_SEARCH_SMEM));
+        CK(cudaFuncSetAttribute(k_tile_search<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CMX_SEARCH_SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_tile_search<false, true>, CMX_SEARCH_WARPS * 32, CMX_SEARCH_SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_tile_search<true, true>, CMX_SEARCH_WARPS * 32, CMX_SEARCH_SMEM));
         h->search_grid[0] = h->num_sms * std::max(1, b0); h->search_grid[1] = h->num_sms * std::max(1, b1);
         if (const char *e = std::getenv("CMX_TRACE")) { int a = 0, b = 1; if (std::sscanf(e, "%d:%d", &a, &b) >= 1) { h->trace_skip = a; h->trace_count = b; } }
         if (const char *e = std::getenv("CMX_SEARCH_BLOCKS_PER_SM")) h->search_blocks_env = std::max(1, atoi(e));   // experiments only
@@ -707,6 +718,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     // tuning overrides (experiments only)
     if (const char *e = std::getenv("CMX_ROWDIV")) { h->Kdiv = std::max(1, atoi(e)); h->side = (h->cut_eff + 0.02) / h->Kdiv; }
     if (const char *e = std::getenv("CMX_XSIDE")) h->sidex = std::max(0.5, atof(e));
+    if (const char *e = std::getenv("CMX_RING")) h->ring_width = std::max(0.0, atof(e));
     if (const char *e = std::getenv("CMX_QSIDE")) h->qside = std::max(1.0, atof(e));
     if (const char *e = std::getenv("CMX_CULLDIV")) h->cside = (h->cut_eff + 0.02) / std::max(1.0, atof(e));
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
@@ -788,6 +800,16 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     const size_t nchunk = (size_t)h->sample_chunk;
     CK(h->d_stats.ensure(8, true));
     P.cnt_base = h->d_cnt.p; P.acc = nullptr; P.w = 1.0;
+    // shared-memory histograms: md and rdf always; group rows while all rows fit in 64 KB next to them
+    {
+        const size_t row = sizeof(unsigned) * nb, budget = 64 * 1024;
+        P.priv_sol = (c.autocorrelation || h->path == 2) && row * (2 + (size_t)c.n_groups_solute) <= budget;
+        P.priv_solv = !c.autocorrelation && row * (2 + (size_t)c.n_groups_solvent + (P.priv_sol ? (size_t)c.n_groups_solute : 0)) <= budget;
+        h->hist_smem = row * (size_t)hist_rows(P);
+        if (h->hist_smem > 200 * 1024) return fail(h, CMX_ERR_ARG, "too many histogram bins for the shared-memory counters (cutoff / binstep > 25000)");
+        CK(cudaFuncSetAttribute(k_finalise<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hist_smem));
+        CK(cudaFuncSetAttribute(k_finalise<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->hist_smem));
+    }
     if (c.keep_lists) {
         if (h->path == 1) CK(h->d_list_all.ensure((size_t)c.solute_nmols * nvm));
         CK(h->d_rand_list.ensure(std::max<size_t>(nrand * nvm, 1)));

@@ -34,12 +34,12 @@ namespace cmx {
 // per-frame scalars (GridFrame::sc), zeroed by k_zero_frame
 enum {
     SC_WORK = 0, SC_RWORK = 1, SC_DEF_REAL = 2, SC_DEF_RAND = 3, SC_NBULK = 4, SC_RMAX = 5, SC_TQ_REAL = 6, SC_TQ_RAND = 7,
-    SC_SCAN_CELLS = 8, SC_SCAN_TILES_REAL = 9, SC_SCAN_TILES_RAND = 10, SC_SCAN_BULK = 11, SC_COUNT = 16
+    SC_SCAN_CELLS = 8, SC_SCAN_TILES_REAL = 9, SC_SCAN_TILES_RAND = 10, SC_SCAN_BULK = 11, SC_FQ_REAL = 12, SC_FQ_RAND = 13, SC_COUNT = 16
 };
 
 // One frame (x one solute molecule) in flight on the device: geometry, inputs and the scratch of its slot.
 // An array of these (one per frame of the batch) lives in device memory; kernels pick theirs with blockIdx.y.
-struct GridFrame {
+struct alignas(16) GridFrame {
     Geom g;
     const float *xs, *xv;          // the solute molecule, all solvent molecules (fp32 xyz as read)
     int *sc;                       // SC_COUNT scalars
@@ -92,7 +92,7 @@ __global__ void k_zero_frame(const GridFrame *__restrict__ fds) {
 // between two chunks of random samples: the counters of the random phase
 __global__ void k_reset_rand(const GridFrame *__restrict__ fds) {
     const GridFrame &F = fds[blockIdx.x];
-    if (threadIdx.x == 0) { F.sc[SC_RWORK] = 0; F.sc[SC_DEF_RAND] = 0; F.sc[SC_TQ_RAND] = 0; F.sc[SC_SCAN_TILES_RAND] = 0; }
+    if (threadIdx.x == 0) { F.sc[SC_RWORK] = 0; F.sc[SC_DEF_RAND] = 0; F.sc[SC_TQ_RAND] = 0; F.sc[SC_SCAN_TILES_RAND] = 0; F.sc[SC_FQ_RAND] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -451,14 +451,21 @@ __global__ void k_qscatter(const GridFrame *__restrict__ fds, Prob P) {
 
 // ---------------------------------------------------------------------------------------------
 // The search.  One warp per tile of 32 query atoms that are neighbours in space (consecutive in
-// query-cell order).  Every lane owns one query; all lanes walk the SAME solute atoms (broadcast
-// 16-byte loads of the cell-sorted solute), so there is no divergence and one row probe serves 32
-// queries.  Rows of the solute grid inside the tile's reach are probed in lane-parallel (occupancy
-// bitmask), then visited nearest-first; after every row the tile bound shrinks to the largest
-// best-distance of its lanes.  Each lane keeps best / second-best squared distance and the solute
-// atom of the best: res[query] = {b1, b2, atom}.
+// query-cell order); every lane owns one query.  Rows of the solute grid ((y,z) columns of cells)
+// inside the tile's reach are probed in lane-parallel (occupancy bitmask -> lower bound rd of the
+// squared distance from the tile to the row).  The rows are then consumed in RINGS of increasing
+// distance: all rows with rd <= (sqrt(nearest remaining rd) + ring)^2 are taken at once; each lane
+// works out the cell range of ITS rows (no warp-serial per-row bookkeeping), a warp prefix sum lays the
+// ranges out back to back, the lanes copy their ranges into the warp's staging buffer in shared
+// memory, and ALL lanes then sweep the staged atoms (broadcast reads) in one uninterrupted loop.
+// The loop handles two solute atoms per step with the packed fp32 instructions of sm_100
+// (FADD2 / FMUL2 / FFMA2, staged atoms are stored pair-transposed so that both operands are register
+// pairs) and 3-input min/max; each lane keeps best / second-best squared distance and the solute atom
+// of the best: res[query] = {b1, b2, atom}.  After every ring the tile bound shrinks to the largest
+// best-distance of its lanes, which ends the walk as soon as no remaining row can matter.
 // The tiles of ALL frames of the batch form one queue (frames differ in how many tiles survive the
-// cull): a warp takes the next (frame, tile) with one atomic, so the batch is balanced as a whole.
+// cull): a warp takes the next (frame, tile) with one atomic -- issued one tile ahead, so its latency
+// is hidden -- and the batch is balanced as a whole.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int fkey(float x) { int i = __float_as_int(x); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float fkey_inv(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
@@ -469,23 +476,41 @@ __device__ __forceinline__ float warp_maxf(float x) { return fkey_inv(__reduce_m
 struct SearchFrame {
     const int *cell_start; const float4 *sorted; const u64 *rowmask; const float4 *qsorted; const unsigned char *tile_valid;
     float4 *res;
-    float gmin[3], side, inv_side, inv_sidex, search2, tol_d2;
+    float gmin[3], side, inv_side, inv_sidex, search2, tol_d2, ring;
     int nx, ny, nz, rw, tile_end;     // tile_end: end of this frame's range in the batch-wide tile numbering
 };
 #define CMX_MAX_BATCH 32
 #define CMX_ROWS_PER_LANE 4
+#define CMX_SEARCH_WARPS 8
+#ifndef CMX_STAGE
+#define CMX_STAGE 256                 // solute atoms staged per warp and sweep (pair-transposed: 16 B per atom)
+// (measured, C4 / C2 frames/s: 4 blocks/SM x 256 staged x unroll 4: 3464 / 10452; unroll 2: 3395 / 10231; 3 blocks x 384: 3198 / 9685;
+//  2 blocks x 512: 3119 / 9186 -- occupancy beats staging depth)
+#endif
+#ifndef CMX_SEARCH_MINBLOCKS
+#define CMX_SEARCH_MINBLOCKS 4
+#endif
+#ifndef CMX_SWEEP_UNROLL
+#define CMX_SWEEP_UNROLL 4
+#endif
+constexpr int kSweepUnroll = CMX_SWEEP_UNROLL;
+#define CMX_SEG_MAX (32 * CMX_ROWS_PER_LANE)
+#define CMX_WARP_SMEM (CMX_STAGE * 16 + CMX_SEG_MAX * 4 + CMX_STAGE + 16)   // staged atoms, segment table, owner marks, carry
+#define CMX_SEARCH_SMEM (CMX_SEARCH_WARPS * CMX_WARP_SMEM)
+
 template <bool COUNT, bool RANDOM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CMX_SEARCH_WARPS * 32, CMX_SEARCH_MINBLOCKS)
 k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ pair_evals) {
     __shared__ SearchFrame sf[CMX_MAX_BATCH];
-    __shared__ float4 stage[8][32];               // per warp: one chunk of solute atoms
+    // per warp: CMX_STAGE atoms as pairs {x0,x1,y0,y1},{z0,z1,w0,w1}
+    extern __shared__ __align__(16) unsigned char search_smem[];      // per warp: CMX_WARP_SMEM bytes (dynamic)
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < nframes) {
         const GridFrame &F = fds[threadIdx.x];
         SearchFrame s;
         s.cell_start = F.cell_start; s.sorted = F.sorted; s.rowmask = F.rowmask; s.qsorted = F.qsorted; s.tile_valid = F.tile_valid; s.res = F.res;
         s.gmin[0] = F.g.gmin[0]; s.gmin[1] = F.g.gmin[1]; s.gmin[2] = F.g.gmin[2];
-        s.side = F.g.side; s.inv_side = F.g.inv_side; s.inv_sidex = F.g.inv_sidex; s.search2 = F.g.search2; s.tol_d2 = F.g.tol_d2;
+        s.side = F.g.side; s.inv_side = F.g.inv_side; s.inv_sidex = F.g.inv_sidex; s.search2 = F.g.search2; s.tol_d2 = F.g.tol_d2; s.ring = F.g.ring;
         s.nx = F.g.nx; s.ny = F.g.ny; s.nz = F.g.nz; s.rw = F.g.rw;
         s.tile_end = F.qcell_start[F.nqcells];    // exclusive scan of the per-cell tile counts: total tiles of the frame
         sf[threadIdx.x] = s;
@@ -497,12 +522,17 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
     int *tile_queue = fds[0].sc + (RANDOM ? SC_TQ_RAND : SC_TQ_REAL);
     const float slack = 2e-3f;
     unsigned long long npairs = 0;
-    float4 *st = stage[threadIdx.x >> 5];
+    unsigned char *wsm = search_smem + (size_t)(threadIdx.x >> 5) * CMX_WARP_SMEM;
+    float *st = reinterpret_cast<float *>(wsm);                                   // CMX_STAGE atoms, pair-transposed
+    int *seg_src = reinterpret_cast<int *>(wsm + CMX_STAGE * 16);                 // per segment: (first cell-sorted atom) - (position in the ring's flattened order)
+    unsigned char *owner = wsm + CMX_STAGE * 16 + CMX_SEG_MAX * 4;                // per staged position: 1 + segment that STARTS there, else 0
+    int *carry = reinterpret_cast<int *>(wsm + CMX_STAGE * 16 + CMX_SEG_MAX * 4 + CMX_STAGE);
+    int gt_next = 0;
+    if (lane == 0) gt_next = atomicAdd(tile_queue, 1);
     while (true) {
-        int gt = 0;
-        if (lane == 0) gt = atomicAdd(tile_queue, 1);
-        gt = __shfl_sync(0xffffffffu, gt, 0);
+        const int gt = __shfl_sync(0xffffffffu, gt_next, 0);
         if (gt >= ntiles_all) break;
+        if (lane == 0) gt_next = atomicAdd(tile_queue, 1);      // the next tile's ticket travels while this tile is searched
         int fi = 0;
         while (gt >= sf[fi].tile_end) ++fi;
         const SearchFrame &S = sf[fi];
@@ -512,6 +542,7 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
         float4 q = __ldg(&S.qsorted[(size_t)tile * 32 + (valid ? lane : 0)]);   // unused lanes shadow the tile's first query
         const float xmin = warp_minf(q.x), xmax = warp_maxf(q.x), ymin = warp_minf(q.y), ymax = warp_maxf(q.y),
                     zmin = warp_minf(q.z), zmax = warp_maxf(q.z);
+        const float2 nqx = make_float2(-q.x, -q.x), nqy = make_float2(-q.y, -q.y), nqz = make_float2(-q.z, -q.z);
         float b1 = CUDART_INF_F, b2 = CUDART_INF_F; int bi = -1;
         float bound = S.search2;
         const float gmin0 = S.gmin[0], gmin1 = S.gmin[1], gmin2 = S.gmin[2], side = S.side, inv_side = S.inv_side, inv_sidex = S.inv_sidex;
@@ -556,46 +587,113 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
                     }
                 }
             }
-            // ---- visit the occupied rows nearest-first
+            // ---- consume the occupied rows in rings of increasing distance
             while (true) {
-                float m = rd[0]; int um = 0, rowm = rrow[0];
+                float m = rd[0];
 #pragma unroll
-                for (int u = 1; u < CMX_ROWS_PER_LANE; ++u) if (rd[u] < m) { m = rd[u]; um = u; rowm = rrow[u]; }
-                float wm = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(m)));   // rd >= 0: bit order == value order
+                for (int u = 1; u < CMX_ROWS_PER_LANE; ++u) m = fminf(m, rd[u]);
+                const float wm = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(m)));   // rd >= 0: bit order == value order
                 if (!(wm <= bound)) break;
-                int wl = __ffs(__ballot_sync(0xffffffffu, m == wm)) - 1;
-                const int row = __shfl_sync(0xffffffffu, rowm, wl);
-                if (lane == wl) {
+                const float rt = sqrtf(wm) + S.ring;
+                const float lim = fminf(rt * rt, bound);
+                // my rows of this ring -> cell ranges [aa, aa + na)
+                int aa[CMX_ROWS_PER_LANE], na[CMX_ROWS_PER_LANE];
+                int mytotal = 0;
 #pragma unroll
-                    for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) if (u == um) rd[u] = CUDART_INF_F;
-                }
-                float hx = sqrtf(bound - wm) + slack;
-                int cxl = max((int)floorf((xmin - hx - gmin0) * inv_sidex), 0);
-                int cxh = min((int)floorf((xmax + hx - gmin0) * inv_sidex), nx - 1);
-                if (cxl > cxh) continue;
-                int rowbase = row * nx;
-                int a = __ldg(&cell_start[rowbase + cxl]), b = __ldg(&cell_start[rowbase + cxh + 1]);
-                // the row's atoms are fetched 32 at a time with one coalesced load (next chunk prefetched into
-                // registers), staged in shared memory and then read by every lane as broadcasts
-                float4 nxt = (a + lane < b) ? __ldg(&sorted[a + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int base = a; base < b; base += 32) {
-                    __syncwarp();
-                    st[lane] = nxt;
-                    __syncwarp();
-                    int nb = base + 32;
-                    if (nb + lane < b) nxt = __ldg(&sorted[nb + lane]);
-                    int n = min(32, b - base);
-#pragma unroll 4
-                    for (int j = 0; j < n; ++j) {
-                        float4 s = st[j];
-                        float dx = s.x - q.x, dy = s.y - q.y, dz = s.z - q.z;
-                        float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                        b2 = fminf(b2, fmaxf(d2, b1));
-                        if (d2 < b1) { b1 = d2; bi = __float_as_int(s.w); }
+                for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
+                    aa[u] = 0; na[u] = 0;
+                    if (rd[u] <= lim) {
+                        float hx = sqrtf(bound - rd[u]) + slack;
+                        int cxl = max((int)floorf((xmin - hx - gmin0) * inv_sidex), 0);
+                        int cxh = min((int)floorf((xmax + hx - gmin0) * inv_sidex), nx - 1);
+                        if (cxl <= cxh) {
+                            int rowbase = rrow[u] * nx;
+                            aa[u] = __ldg(&cell_start[rowbase + cxl]);
+                            na[u] = __ldg(&cell_start[rowbase + cxh + 1]) - aa[u];
+                        }
+                        rd[u] = CUDART_INF_F;
+                        mytotal += na[u];
                     }
                 }
-                if (COUNT) npairs += (unsigned long long)(b - a);
-                float mine = valid ? fminf(b1 + S.tol_d2, S.search2) : 0.f;
+                int incl = mytotal;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const int myfirst = incl - mytotal;
+                if (COUNT) npairs += (unsigned long long)total;
+                // segment table: my ranges' positions in the flattened order of the ring
+                int pu[CMX_ROWS_PER_LANE];
+                {
+                    int p = myfirst;
+#pragma unroll
+                    for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
+                        pu[u] = p;
+                        if (na[u] > 0) seg_src[lane * CMX_ROWS_PER_LANE + u] = aa[u] - p;
+                        p += na[u];
+                    }
+                }
+                for (int base = 0; base < total; base += CMX_STAGE) {
+                    const int cnt = min(CMX_STAGE, total - base);
+                    __syncwarp();
+                    // ---- stage [base, base + cnt) of the flattened order, ALL lanes copying (element base + c0 + lane):
+                    // the lanes that own ranges mark where they start; a max-scan over the marks tells every element its range
+                    for (int e = lane; e < cnt; e += 32) owner[e] = 0;
+                    if (lane == 0) *carry = 0;
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < CMX_ROWS_PER_LANE; ++u)
+                        if (na[u] > 0) {
+                            if (pu[u] >= base && pu[u] < base + cnt) owner[pu[u] - base] = (unsigned char)(lane * CMX_ROWS_PER_LANE + u + 1);
+                            else if (pu[u] < base && pu[u] + na[u] > base) *carry = lane * CMX_ROWS_PER_LANE + u + 1;   // straddles the window start
+                        }
+                    __syncwarp();
+                    int run = *carry;
+                    for (int c0 = 0; c0 < cnt; c0 += 32) {
+                        const int e = c0 + lane;
+                        int id = e < cnt ? (int)owner[e] : 0;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, id, o); if (lane >= o) id = max(id, t); }
+                        id = max(id, run);
+                        run = __shfl_sync(0xffffffffu, id, 31);
+                        if (e < cnt) {
+                            const float4 a = __ldg(&sorted[seg_src[id - 1] + base + e]);
+                            float *d = st + (e >> 1) * 8 + (e & 1);
+                            d[0] = a.x; d[2] = a.y; d[4] = a.z; d[6] = a.w;
+                        }
+                    }
+                    if ((cnt & 1) && lane == 0) {          // odd count: the pair's second atom is infinitely far away
+                        float *d = st + (cnt >> 1) * 8 + 1;
+                        d[0] = 1e18f; d[2] = 1e18f; d[4] = 1e18f; d[6] = __int_as_float(-1);
+                    }
+                    __syncwarp();
+                    // ---- sweep: two staged atoms per step; only the PAIR that holds the new minimum is recorded, the
+                    // atom is identified after the sweep (b1 improves O(log n) times, the sweep visits n atoms)
+                    const float4 *sp = reinterpret_cast<const float4 *>(st);
+                    const int npair = (cnt + 1) >> 1;
+                    int bj = -1;
+#pragma unroll kSweepUnroll
+                    for (int j = 0; j < npair; ++j) {
+                        const float4 xy = sp[2 * j];
+                        const float2 zz = *reinterpret_cast<const float2 *>(&sp[2 * j + 1]);
+                        const float2 dx = __fadd2_rn(make_float2(xy.x, xy.y), nqx);
+                        const float2 dy = __fadd2_rn(make_float2(xy.z, xy.w), nqy);
+                        const float2 dz = __fadd2_rn(zz, nqz);
+                        const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+                        const float lo = fminf(d2.x, d2.y), hi = fmaxf(d2.x, d2.y);
+                        b2 = fminf(b2, fminf(fmaxf(b1, lo), hi));       // second smallest of {b1, b2, d2.x, d2.y}
+                        bj = lo < b1 ? j : bj;
+                        b1 = fminf(b1, lo);
+                    }
+                    if (bj >= 0) {      // which atom of pair bj: the same arithmetic gives the same two numbers
+                        const float4 xy = sp[2 * bj], zw = sp[2 * bj + 1];
+                        const float2 dx = __fadd2_rn(make_float2(xy.x, xy.y), nqx);
+                        const float2 dy = __fadd2_rn(make_float2(xy.z, xy.w), nqy);
+                        const float2 dz = __fadd2_rn(make_float2(zw.x, zw.y), nqz);
+                        const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+                        bi = d2.x <= d2.y ? __float_as_int(zw.z) : __float_as_int(zw.w);
+                    }
+                }
+                const float mine = valid ? fminf(b1 + S.tol_d2, S.search2) : 0.f;
                 bound = fminf(bound, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mine))));
             }
         }
@@ -621,17 +719,45 @@ __device__ __forceinline__ int classify(const Geom &g, float b1, float b2) {
 // Finalisation: per molecule, combine its atoms' results (update_md, src/minimum_distances.jl:30-39), finalise
 // the winning pair and the reference-atom pair in fp64 with the reference's arithmetic, histogram
 // (update_counters!, src/update_counters.jl:43-88) -- or defer an ambiguous molecule to the exact kernel.
+// The work items of ALL frames of the batch are one queue of 256-item chunks; a block keeps pulling chunks, counts
+// into its shared-memory histograms (HistPriv) and flushes them once -- the hits of several frames per flush.
 // ---------------------------------------------------------------------------------------------
+#define CMX_FIN_THREADS 256
 template <bool RANDOM>
-__global__ void __launch_bounds__(128)
-k_finalise(const GridFrame *__restrict__ fds, Prob P, int s0) {
-    CMX_FRAME(F)
-    const int count = F.sc[RANDOM ? SC_RWORK : SC_WORK];
-    const int *worklist = RANDOM ? F.rand_worklist : F.worklist;
-    const float *xs = F.xs, *xv = F.xv;
-    MdRec *list = RANDOM ? F.rand_list : F.list;
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
-        const int item = worklist[w];
+__global__ void __launch_bounds__(CMX_FIN_THREADS)
+k_finalise(const GridFrame *__restrict__ fds, int nframes, Prob P, int s0) {
+    extern __shared__ unsigned hist_smem[];
+    __shared__ __align__(16) GridFrame F_sh;
+    __shared__ int s_end[CMX_MAX_BATCH];       // chunks of frames 0..k, cumulative
+    __shared__ int s_chunk;
+    HistPriv H = hist_init(P, hist_smem);
+    if (threadIdx.x < nframes) s_end[threadIdx.x] = (fds[threadIdx.x].sc[RANDOM ? SC_RWORK : SC_WORK] + CMX_FIN_THREADS - 1) / CMX_FIN_THREADS;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int k = 0; k < nframes; ++k) { run += s_end[k]; s_end[k] = run; } }
+    __syncthreads();
+    const int nchunks = s_end[nframes - 1];
+    int *queue = fds[0].sc + (RANDOM ? SC_FQ_RAND : SC_FQ_REAL);
+    int cur = -1;
+    const GridFrame &F = F_sh;
+    const Geom &g = F.g;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_chunk = atomicAdd(queue, 1);
+        __syncthreads();
+        const int chunk = s_chunk;
+        if (chunk >= nchunks) break;
+        int fi = 0;
+        while (chunk >= s_end[fi]) ++fi;
+        if (fi != cur) {     // (uniform in the block) this chunk belongs to another frame: fetch its descriptor
+            const int4 *src_ = reinterpret_cast<const int4 *>(fds + fi);
+            int4 *dst_ = reinterpret_cast<int4 *>(&F_sh);
+            for (int k_ = threadIdx.x; k_ < (int)(sizeof(GridFrame) / 16); k_ += blockDim.x) dst_[k_] = __ldg(src_ + k_);
+            cur = fi;
+            __syncthreads();
+        }
+        const int w = (chunk - (fi ? s_end[fi - 1] : 0)) * CMX_FIN_THREADS + threadIdx.x;
+        if (w >= F.sc[RANDOM ? SC_RWORK : SC_WORK]) continue;
+        const int item = (RANDOM ? F.rand_worklist : F.worklist)[w];
         int sample = 0, mol = item;
         if (RANDOM) { int sl = item / P.nv_mols; mol = item - sl * P.nv_mols; sample = s0 + sl; }
         const float4 *r = F.res + (size_t)w * P.nv_apm;
@@ -651,9 +777,10 @@ k_finalise(const GridFrame *__restrict__ fds, Prob P, int s0) {
             (RANDOM ? F.def_rand_info : F.def_real_info)[slot] = make_float2(best, rr.x);   // fp32 bounds: the exact kernel only looks at atoms that can matter
             continue;
         }
+        const float *xs = F.xs;
         auto pos = [&](int k, double &ex, double &ey, double &ez) {
             if (RANDOM) { const double *xe = F.xexact + ((size_t)P.nv_apm * w + k) * 3; ex = xe[0]; ey = xe[1]; ez = xe[2]; }
-            else { const float *xr = xv + ((size_t)P.nv_apm * mol + k) * 3; ex = (double)xr[0]; ey = (double)xr[1]; ez = (double)xr[2]; }
+            else { const float *xr = F.xv + ((size_t)P.nv_apm * mol + k) * 3; ex = (double)xr[0]; ey = (double)xr[1]; ez = (double)xr[2]; }
         };
         double ex, ey, ez;
         pos(bk, ex, ey, ez);
@@ -666,10 +793,12 @@ k_finalise(const GridFrame *__restrict__ fds, Prob P, int s0) {
             e.dref = dist_pbc64(g, (double)xs[3 * ri], (double)xs[3 * ri + 1], (double)xs[3 * ri + 2], ex, ey, ez);
             e.flags |= 2;
         }
-        count_hit(P, F.weight, RANDOM, e.d, e.i, e.j, 1ull);
-        if (e.flags & 2) count_ref(P, F.weight, RANDOM, e.dref);
+        count_hit_priv(P, H, F.weight, RANDOM, e.d, e.i, e.j, 1ull);
+        if (e.flags & 2) count_ref_priv(P, H, F.weight, RANDOM, e.dref);
+        MdRec *list = RANDOM ? F.rand_list : F.list;
         if (list) list[RANDOM ? (size_t)sample * P.nv_mols + mol : (size_t)mol] = e;
     }
+    hist_flush(P, H, RANDOM);
 }
 
 // ---------------------------------------------------------------------------------------------

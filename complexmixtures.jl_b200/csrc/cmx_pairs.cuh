@@ -350,16 +350,43 @@ __device__ __forceinline__ MdRec exact_list_entry(const Geom &g, const Prob &P, 
     return e;
 }
 
+// the same list entry computed by a whole warp: the lanes stride over the atom pairs and the partial results are merged
+// with the rule "smallest (d, j, i)" (every lane returns the entry)
+__device__ __forceinline__ MdRec exact_list_entry_warp(const Geom &g, const Prob &P, const float *xa, const float *xb, int b) {
+    const int lane = threadIdx.x & 31;
+    double bd = CUDART_INF, bref = CUDART_INF; int bi = 0x7fffffff, bj = 0x7fffffff;
+    const int npair = P.ns_apm * P.nv_apm;
+    for (int p = lane; p < npair; p += 32) {
+        const int j = p / P.ns_apm, i = p - j * P.ns_apm;
+        const double d = exact_atoms(g, xa, i, xb, j);
+        if (d <= g.cutd) {
+            const int jg = b * P.nv_apm + j;
+            if (d < bd || (d == bd && (jg < bj || (jg == bj && i < bi)))) { bd = d; bi = i; bj = jg; }
+            if (j == P.iref && d < bref) bref = d;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, o), oref = __shfl_xor_sync(0xffffffffu, bref, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o), oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (od < bd || (od == bd && (oj < bj || (oj == bj && oi < bi)))) { bd = od; bi = oi; bj = oj; }
+        bref = fmin(bref, oref);
+    }
+    MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
+    if (bd <= g.cutd) { e.d = bd; e.i = bi; e.j = bj; e.flags = 1; if (bref <= g.cutd) { e.dref = bref; e.flags |= 2; } }
+    return e;
+}
+
 // grid.y = list index within the current chunk of samples; solute molecule = fixed_a (>= 0) or the reference
 // solute of sample s0 + blockIdx.y
 __global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fixed_a, int s0, const float *__restrict__ xs,
                             const float *__restrict__ xv, MolData sol, MolData solv, MdRec *__restrict__ lists) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.nv_mols) return;
-    int s = blockIdx.y;
-    int a = fixed_a >= 0 ? fixed_a : ref_solute_of_sample(P, frame, (uint32_t)(s0 + s));
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int s = blockIdx.y;
+    const int a = fixed_a >= 0 ? fixed_a : ref_solute_of_sample(P, frame, (uint32_t)(s0 + s));
     MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
-    if (!(P.autocorr && b == a)) {
+    bool heavy = false;
+    if (b < P.nv_mols && !(P.autocorr && b == a)) {
         double dx = solv.anchor[3 * (size_t)b] - sol.anchor[3 * (size_t)a], dy = solv.anchor[3 * (size_t)b + 1] - sol.anchor[3 * (size_t)a + 1],
                dz = solv.anchor[3 * (size_t)b + 2] - sol.anchor[3 * (size_t)a + 2];
         min_image64(g, dx, dy, dz);
@@ -367,10 +394,18 @@ __global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fix
         double dn = sqrt(dx * dx + dy * dy + dz * dz);
         // |v0| > lim implies the true anchor distance > lim whenever lim < half the smallest width;
         // otherwise the anchor test is not a valid bound: evaluate everything
-        if (dn <= lim || lim >= pg.half_wmin)
-            e = exact_list_entry(g, P, xs + (size_t)3 * P.ns_apm * a, xv + (size_t)3 * P.nv_apm * b, b);
+        heavy = dn <= lim || lim >= pg.half_wmin;
     }
-    lists[(size_t)s * P.nv_mols + b] = e;
+    // the few molecules that pass the anchor test are evaluated by the whole warp, one after the other
+    unsigned todo = __ballot_sync(0xffffffffu, heavy);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int bb = __shfl_sync(0xffffffffu, b, src);
+        const MdRec r = exact_list_entry_warp(g, P, xs + (size_t)3 * P.ns_apm * a, xv + (size_t)3 * P.nv_apm * bb, bb);
+        if (lane == src) e = r;
+    }
+    if (b < P.nv_mols) lists[(size_t)s * P.nv_mols + b] = e;
 }
 
 // ordered compaction of the bulk molecules of each sample's list (one block per sample)
@@ -468,24 +503,27 @@ k_pair_random(Geom g, PairGeom pg, Prob P, uint32_t frame, int s0, int ns, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// exact resolve of deferred pairs (one thread per item: molecules on this path are small)
+// exact resolve of deferred pairs: one WARP per item (the lanes share the ns_apm x nv_apm exact fp64 distances; one
+// thread per item made the kernel as long as one thread's ~400 serial fp64 distances)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, int s0, const float *__restrict__ xs, const float *__restrict__ xv,
-                               const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk,
-                               const u64 *__restrict__ deferred, const int *__restrict__ def_count, size_t def_cap,
-                               MdRec *__restrict__ rand_list) {
-    int count = min((long long)*def_count, (long long)def_cap);
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < count; w += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(128)
+k_pair_resolve(Geom g, Prob P, uint32_t frame, int s0, const float *__restrict__ xs, const float *__restrict__ xv,
+               const int *__restrict__ bulk_idx, const int *__restrict__ n_bulk,
+               const u64 *__restrict__ deferred, const int *__restrict__ def_count, size_t def_cap,
+               MdRec *__restrict__ rand_list) {
+    const int count = (int)min((long long)*def_count, (long long)def_cap);
+    const int lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += nwarp) {
         u64 item = deferred[w];
         int phase = (int)(item >> 48), a = (int)((item >> 24) & 0xffffffull), b = (int)(item & 0xffffffull);
         const float *xa = xs + (size_t)3 * P.ns_apm * a;
         if (phase == 0) {
             const float *xb = xv + (size_t)3 * P.nv_apm * b;
-            MdRec e = exact_list_entry(g, P, xa, xb, b);
-            if (e.flags & 1) { count_hit(P, P.w, false, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, P.w, false, e.dref); }
+            MdRec e = exact_list_entry_warp(g, P, xa, xb, b);
+            if (lane == 0 && (e.flags & 1)) { count_hit(P, P.w, false, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, P.w, false, e.dref); }
             if (P.autocorr) {   // the other ordered pair: solute b, solvent a
-                MdRec f = exact_list_entry(g, P, xb, xa, a);
-                if (f.flags & 1) { count_hit(P, P.w, false, f.d, f.i, f.j, 1ull); if (f.flags & 2) count_ref(P, P.w, false, f.dref); }
+                MdRec f = exact_list_entry_warp(g, P, xb, xa, a);
+                if (lane == 0 && (f.flags & 1)) { count_hit(P, P.w, false, f.d, f.i, f.j, 1ull); if (f.flags & 2) count_ref(P, P.w, false, f.dref); }
             }
         } else {
             int sl = phase - 1, s = s0 + sl, slot = b;    // sl: sample within the chunk
@@ -494,20 +532,31 @@ __global__ void k_pair_resolve(Geom g, Prob P, uint32_t frame, int s0, const flo
             int nb = n_bulk[sl];
             int jmol = nb > 0 ? bulk_idx[(size_t)sl * P.nv_mols + pick(r0.x, (uint32_t)nb)] : (int)pick(r0.x, (uint32_t)P.nv_mols);
             RandMol rm; rm.init(g, xv + (size_t)3 * P.nv_apm * jmol, P.nv_apm, P.iref, r0, r1);
-            MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
-            for (int k = 0; k < P.nv_apm; ++k) {
+            double bd = CUDART_INF, bref = CUDART_INF; int bi = 0x7fffffff, bj = 0x7fffffff;
+            const int npair = P.ns_apm * P.nv_apm;
+            for (int p = lane; p < npair; p += 32) {
+                const int k = p / P.ns_apm, i = p - k * P.ns_apm;
                 double ex, ey, ez; rm.get(g, k, ex, ey, ez);
-                int jg = slot * P.nv_apm + k;
-                for (int i = 0; i < P.ns_apm; ++i) {
-                    double d = dist_pbc64(g, (double)xa[3 * i], (double)xa[3 * i + 1], (double)xa[3 * i + 2], ex, ey, ez);
-                    if (d <= g.cutd) {
-                        if (d < e.d || (d == e.d && (jg < e.j || (jg == e.j && i < e.i)))) { e.d = d; e.i = i; e.j = jg; e.flags |= 1; }
-                        if (k == P.iref && d < e.dref) { e.dref = d; e.flags |= 2; }
-                    }
+                const int jg = slot * P.nv_apm + k;
+                const double d = dist_pbc64(g, (double)xa[3 * i], (double)xa[3 * i + 1], (double)xa[3 * i + 2], ex, ey, ez);
+                if (d <= g.cutd) {
+                    if (d < bd || (d == bd && (jg < bj || (jg == bj && i < bi)))) { bd = d; bi = i; bj = jg; }
+                    if (k == P.iref && d < bref) bref = d;
                 }
             }
-            if (e.flags & 1) { count_hit(P, P.w, true, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, P.w, true, e.dref); }
-            if (rand_list) rand_list[(size_t)s * P.nv_mols + slot] = e;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o), oref = __shfl_xor_sync(0xffffffffu, bref, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o), oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (od < bd || (od == bd && (oj < bj || (oj == bj && oi < bi)))) { bd = od; bi = oi; bj = oj; }
+                bref = fmin(bref, oref);
+            }
+            if (lane == 0) {
+                MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
+                if (bd <= g.cutd) { e.d = bd; e.i = bi; e.j = bj; e.flags = 1; if (bref <= g.cutd) { e.dref = bref; e.flags |= 2; } }
+                if (e.flags & 1) { count_hit(P, P.w, true, e.d, e.i, e.j, 1ull); if (e.flags & 2) count_ref(P, P.w, true, e.dref); }
+                if (rand_list) rand_list[(size_t)s * P.nv_mols + slot] = e;
+            }
         }
     }
 }

@@ -27,7 +27,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, _SRC[0]]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CMX_NVCC_EXTRA", "").split() + ["-o", LIB_PATH, _SRC[0]]   # (extra -D flags: tuning experiments)
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

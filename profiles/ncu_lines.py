@@ -17,7 +17,14 @@ for r in rows:
     if r[0] == "Kernel Name": cur = {"name": r[1], "hdr": None, "rows": []}; blocks.append(cur)
     elif r[0] == "Address": cur["hdr"] = r
     elif cur is not None and cur["hdr"] is not None: cur["rows"].append(r)
-blk = [b for b in blocks if re.search(kre, b["name"])][int(os.environ.get("NCU_INDEX", "0"))]
+cands = [b for b in blocks if re.search(kre, b["name"])]
+if os.environ.get("NCU_PICK") == "max":   # the matching launch that executed the most instructions
+    def _n(b):
+        k = b["hdr"].index("Instructions Executed")
+        return sum(int(r[k] or 0) for r in b["rows"])
+    blk = max(cands, key=_n)
+else:
+    blk = cands[int(os.environ.get("NCU_INDEX", "0"))]
 h = blk["hdr"]; ia, ii, isamp, ithr = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples"), h.index("Thread Instructions Executed")
 base = int(blk["rows"][0][ia], 16)
 tmp = tempfile.mkdtemp()
@@ -27,7 +34,7 @@ dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)]
 # find the function whose demangled-ish name matches: use the mangled fragment from the kernel name
 name = blk["name"]
 m = re.search(r"k_\w+", name); short = m.group(0)
-targs = re.findall(r"\((?:int|bool)\)(\d+)", name)
+targs = re.findall(r"\((?:int|bool)\)(\d+)", name.split("(const")[0].split("(cmx::")[0])
 line_of, cur_line, infun, off_re = {}, None, False, re.compile(r"/\*([0-9a-f]{4,})\*/\s+(\S.*?);")
 for ln in dis.splitlines():
     if ln.startswith("//--------------------- .text."):
