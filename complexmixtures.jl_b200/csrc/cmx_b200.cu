@@ -12,10 +12,15 @@
 #include <cctype>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -167,6 +172,7 @@ struct cmx_handle {
     DevBuf<double> d_emit;          // staging of cmx_finish
     size_t cnt_len = 0;
     bool acc_used = false;
+    bool emit_valid = false;        // d_emit holds the (possibly all-reduced) f64 counters that cmx_finish writes out
     // per-frame scratch lives in FrameCtx (one per compute stream)
     DevBuf<MdRec> d_rand_list, d_list_all;   // parity hooks (keep_lists => one stream)
     DevBuf<u64> d_stats;            // [0] pair_evals, [1] deferred total
@@ -191,14 +197,28 @@ struct cmx_handle {
     int search_grid[2] = {148 * 5, 148 * 4};   // one resident wave of k_tile_search<false/true> (occupancy query at create)
     int search_blocks_env = 0;
     cmx_feed *feed = nullptr;
+    // group handle (cmx_group.inl): one child per device; a group owns no device state of its own
+    std::vector<cmx_handle *> children;
+    int next_child = 0;
+    cmx_handle *acquired_child = nullptr;
     // CMX_TRACE=skip:count -- device timeline of `count` batches after `skip` flushes (events between the launches), printed at sync
     int trace_skip = -1, trace_count = 0; bool tracing = false;
     std::vector<std::pair<const char *, cudaEvent_t>> trace_events;
+    bool sync_destroy = false;      // option "sync_destroy": free everything on the caller's thread
     bool poll_stop_file = true, stopped_by_file = false;   // native feed: the reference's cooperative stop file
     int numa_node = -1;                        // NUMA node of the GPU (-1 unknown): pinned staging memory is placed there
 };
 
 namespace {
+
+#define CK_G(call)                                                                                 \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return CMX_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -210,6 +230,22 @@ namespace {
     } while (0)
 
 int fail(cmx_handle *h, int code, const std::string &msg) { h->err = msg; return code; }
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+// cudaEventSynchronize with the blocked time booked as back-pressure (cmx_stats.host_wait_ms)
+cudaError_t wait_event(cmx_handle *h, cudaEvent_t e) {
+    if (cudaEventQuery(e) == cudaSuccess) return cudaSuccess;
+    (void)cudaGetLastError();
+    const double t0 = now_ms();
+    cudaError_t r = cudaEventSynchronize(e);
+    h->stats.host_wait_ms += now_ms() - t0;
+    return r;
+}
+struct SubmitTimer {   // cmx_stats.host_submit_ms
+    cmx_handle *h; double t0;
+    explicit SubmitTimer(cmx_handle *h_) : h(h_), t0(now_ms()) {}
+    ~SubmitTimer() { h->stats.host_submit_ms += now_ms() - t0; }
+};
 
 // molecule-pair path (cmx_pairs_host.inl)
 void feed_destroy(cmx_handle *h);
@@ -416,7 +452,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     const unsigned sms = (unsigned)h->num_sms;
     const int ns_apm = c.solute_natomspermol, nv_mols = c.solvent_nmols;
     const int nrand = c.coordination_number_only ? 0 : c.n_random_samples;
-    if (x->fd_busy) { CK(cudaEventSynchronize(x->ev_fd)); x->fd_busy = false; }   // previous descriptor upload of this context
+    if (x->fd_busy) { CK(wait_event(h, x->ev_fd)); x->fd_busy = false; }   // previous descriptor upload of this context
     size_t ncells_max = 0, ncull_max = 0, nqc_max = 0, bits_max = 0;
     bool any_random = false;
     for (unsigned k = 0; k < nb; ++k) {
@@ -425,6 +461,18 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
         GridSlot &S = x->slots[k];
         const size_t ncells = (size_t)g.nx * g.ny * g.nz, ncc = (size_t)g.ncx * g.ncy * g.ncz, nqc = (size_t)g.nqx * g.nqy * g.nqz;
         const size_t occ_words = (size_t)g.ncy * g.ncz * g.cw, row_words = (size_t)g.ny * g.nz * g.rw;
+        {   // static-size scratch of the slot, allocated when the slot is first used (a no-op afterwards)
+            const size_t nvm = (size_t)nv_mols, nchunk = (size_t)(nrand ? h->sample_chunk : 0);
+            const size_t maxq0 = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms);
+            CK(S.sc.ensure(SC_COUNT, true, x->stream));
+            CK(S.list.ensure(nvm)); CK(S.bulk_idx.ensure(nvm));
+            CK(S.worklist.ensure(nvm)); CK(S.rand_worklist.ensure(std::max<size_t>(nchunk * nvm, 1)));
+            CK(S.def_real.ensure(nvm)); CK(S.def_rand.ensure(std::max<size_t>(nchunk * nvm, 1)));
+            CK(S.def_real_info.ensure(nvm)); CK(S.def_rand_info.ensure(std::max<size_t>(nchunk * nvm, 1)));
+            CK(S.sorted.ensure(27 * (size_t)c.solute_natomspermol));
+            CK(S.qpos.ensure(maxq0)); CK(S.res.ensure(maxq0));
+            CK(S.xexact.ensure(std::max<size_t>(3 * nchunk * h->nv_atoms, 1)));
+        }
         CK(S.cell_count.ensure(ncells + 1, true, x->stream)); CK(S.cell_start.ensure(ncells + 1));
         CK(S.bits.ensure(occ_words + row_words));
         CK(S.edt_xy.ensure(ncc)); CK(S.lbd2.ensure(ncc));
@@ -512,6 +560,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     for (cudaEvent_t e : x->release_events) CK(cudaEventRecord(e, x->stream));
     x->release_events.clear();
     x->pending.clear();
+    h->stats.batches++;
     CK(cudaGetLastError());
     return CMX_OK;
 }
@@ -592,6 +641,7 @@ int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, 
     Geom g;
     int rc = build_geom(h, cell, g);
     if (rc) return rc;
+    h->emit_valid = false;
     if (!h->have_weight) { h->w0 = weight; h->have_weight = true; }
     if (weight != h->w0 && !h->acc_used) { rc = enter_acc_mode(h); if (rc) return rc; }
     // rmax feedback from earlier frames (pinned mirror, may lag)
@@ -631,6 +681,9 @@ int submit_common(cmx_handle *h, const float *d_solute, const float *d_solvent, 
 
 #include "cmx_pairs_host.inl"
 
+extern "C" { static int create_impl(cmx_handle *h, const cmx_config *cfg); }
+#include "cmx_group.inl"
+
 // ==================================================================================================
 // C ABI
 // ==================================================================================================
@@ -640,11 +693,33 @@ const char *cmx_version(void) { return "cmx_b200 0.1.0 (sm_100a)"; }
 
 const char *cmx_last_error(cmx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int32_t cmx_destroy(cmx_handle *h) {
-    if (!h) return CMX_OK;
+// Releasing a handle is dominated by driver calls that unpin / unmap memory (0.5 s for the C4 problem) and nobody waits
+// for their result: the streams are drained on the caller's thread, the frees run on a detached reaper thread.  The next
+// cmx_create waits for the reapers first, so that its allocations find the memory.
+namespace {
+std::mutex g_reaper_mu;
+std::condition_variable g_reaper_cv;
+int g_reapers_pending = 0;
+void join_reapers() {
+    std::unique_lock<std::mutex> lk(g_reaper_mu);
+    g_reaper_cv.wait(lk, [] { return g_reapers_pending == 0; });
+}
+// a reaper must not outlive the CUDA runtime: the first one registers an exit handler (it runs BEFORE the runtime's own,
+// which was registered earlier, at CUDA initialisation) that waits for the pending frees
+void reap(std::function<void()> work) {
+    static std::once_flag once;
+    std::call_once(once, [] { std::atexit(join_reapers); });
+    { std::lock_guard<std::mutex> lk(g_reaper_mu); ++g_reapers_pending; }
+    std::thread([work] {
+        work();
+        std::lock_guard<std::mutex> lk(g_reaper_mu);
+        --g_reapers_pending;
+        g_reaper_cv.notify_all();
+    }).detach();
+}
+
+void release_handle(cmx_handle *h) {
     cudaSetDevice(h->device);
-    for (FrameCtx *x : h->ctx) if (x->stream) cudaStreamSynchronize(x->stream);
-    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
     for (auto &s : h->ring) {
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.d_in) cudaFree(s.d_in);
@@ -661,11 +736,36 @@ int32_t cmx_destroy(cmx_handle *h) {
     if (h->ev_last) cudaEventDestroy(h->ev_last);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     delete h;
+}
+}  // namespace
+
+int32_t cmx_destroy(cmx_handle *h) {
+    if (!h) return CMX_OK;
+    if (is_group(h)) {
+        for (cmx_handle *c : h->children) cmx_destroy(c);
+        delete h;
+        return CMX_OK;
+    }
+    if (!h->s_copy && h->ctx.empty()) { delete h; return CMX_OK; }   // a group handle whose creation failed early
+    cudaSetDevice(h->device);
+    for (FrameCtx *x : h->ctx) if (x->stream) cudaStreamSynchronize(x->stream);
+    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    if (h->sync_destroy) { release_handle(h); return CMX_OK; }
+    reap([h] { release_handle(h); });      // nothing waits for it but the next cmx_create and the process exit
     return CMX_OK;
 }
 
 static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     const cmx_config &c = *cfg;
+    const bool trace_create = std::getenv("CMX_TRACE") != nullptr;
+    double t_phase = now_ms();
+    auto phase = [&](const char *what) {
+        if (!trace_create) return;
+        cudaDeviceSynchronize();
+        const double t = now_ms();
+        std::fprintf(stderr, "[cmx trace] create: %8.1f ms  %s\n", t - t_phase, what);
+        t_phase = t;
+    };
     if (c.struct_size != (int32_t)sizeof(cmx_config)) return fail(h, CMX_ERR_ARG, "cmx_config.struct_size mismatch (ABI)");
     if (c.solute_nmols < 1 || c.solute_natomspermol < 1 || c.solvent_nmols < 1 || c.solvent_natomspermol < 1)
         return fail(h, CMX_ERR_ARG, "selections must have at least one molecule and one atom per molecule");
@@ -721,6 +821,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     if (const char *e = std::getenv("CMX_RING")) h->ring_width = std::max(0.0, atof(e));
     if (const char *e = std::getenv("CMX_QSIDE")) h->qside = std::max(1.0, atof(e));
     if (const char *e = std::getenv("CMX_CULLDIV")) h->cside = (h->cut_eff + 0.02) / std::max(1.0, atof(e));
+    phase("device properties, kernel attributes");
     CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
     // Frames per batch (grid path): enough frames per launch that the small kernels of the sequence fill the GPU and
     // the launch count per frame drops below 2; large systems fill the GPU on their own and their slots are big.
@@ -746,17 +847,14 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     }
     h->cur = h->ctx[0];
     CK(cudaEventCreate(&h->ev_first)); CK(cudaEventCreate(&h->ev_last));
-    // staging ring of acquire/submit: by default every frame of every batch in flight has a slot (+1 being filled)
-    int slots = c.ring_slots > 0 ? c.ring_slots : std::max(3, batch * nctx + 1);
+    // staging ring of acquire/submit: by default the frames of every batch in flight plus two batches being staged
+    // behind them (their H2D copies run while the older batches compute).  A slot's pinned and device buffers are
+    // allocated the first time it is acquired: a short run never pays for the whole ring, a long one pins the later
+    // slots while the first frames already compute.
+    int slots = c.ring_slots > 0 ? c.ring_slots : std::max(4, batch * (nctx + 2) + 1);
     h->ring.resize(slots);
     h->numa_node = gpu_numa_node(c.device);
-    NumaPrefer numa_guard(h->numa_node);
-    for (auto &s : h->ring) {
-        CK(cudaHostAlloc(&s.h_in, sizeof(float) * h->in_floats, cudaHostAllocDefault));
-        CK(cudaMalloc(&s.d_in, sizeof(float) * h->in_floats));
-        CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
-    }
+    phase("streams, descriptor arrays, staging ring (pinned + device)");
     // problem description
     Prob &P = h->P;
     P.ns_mols = c.solute_nmols; P.ns_apm = c.solute_natomspermol; P.nv_mols = c.solvent_nmols; P.nv_apm = c.solvent_natomspermol;
@@ -788,6 +886,26 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     P.sol_off = h->d_sol_off.p; P.sol_ids = h->d_sol_ids.p; P.solv_off = h->d_solv_off.p; P.solv_ids = h->d_solv_ids.p;
     size_t nb = h->nbins;
     h->cnt_len = nb * (4 + 2 * (size_t)c.n_groups_solute + 2 * (size_t)c.n_groups_solvent);
+    {   // memory guard (the reference checks the Result copies against the RAM, src/parallel_setup.jl:29-54): ONE set of
+        // counters per GPU here, plus its f64 image for cmx_finish, plus the scratch of the frames in flight
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const double nrand_d = (double)(c.coordination_number_only ? 0 : c.n_random_samples);
+        const double chunk = std::max(1.0, std::min(std::max(nrand_d, 1.0), 48.0e6 / (double)h->nv_atoms));
+        const double maxq = std::max((double)h->nv_atoms, chunk * (double)h->nv_atoms);
+        const double slot_b = h->path == 1 ? maxq * (16 + 16 + 16 + 24 + 1) + (double)c.solvent_nmols * (32 + 8 + 16 * chunk) + 27.0 * 16 * c.solute_natomspermol
+                                           : 36.0 * (double)h->nv_atoms + 64.0 * (double)c.solvent_nmols * chunk;
+        const double counters_b = 16.0 * (double)h->cnt_len;      // u64 block + the f64 image written by cmx_finish
+        const double need = counters_b + slot_b * (double)h->ctx.size() * (double)h->batch + 8.0 * (double)h->in_floats * (double)h->ring.size();
+        if (need > 0.95 * (double)free_b) {
+            char buf[400];
+            std::snprintf(buf, sizeof buf, "not enough device memory: counters %.1f GB (nbins x (4 + 2 n_groups_solute + 2 n_groups_solvent) x 16 B) + "
+                          "frames in flight %.1f GB > %.1f GB free on device %d; use fewer groups (ResidueContributions-style custom groups instead of "
+                          "per-atom rows), fewer batches in flight (n_streams) or frames per batch (batch_frames)",
+                          counters_b / 1e9, (need - counters_b) / 1e9, (double)free_b / 1e9, c.device);
+            return fail(h, CMX_ERR_MEMORY, buf);
+        }
+    }
     CK(h->d_cnt.ensure(h->cnt_len)); CK(cudaMemset(h->d_cnt.p, 0, sizeof(u64) * h->d_cnt.n));
     u64 *q = h->d_cnt.p;
     P.md = q; q += nb; P.md_r = q; q += nb; P.rdf = q; q += nb; P.rdf_r = q; q += nb;
@@ -798,6 +916,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     // random phase in chunks of samples: at most ~48 M query atoms of scratch per frame context
     h->sample_chunk = (int)std::max<size_t>(1, std::min<size_t>(std::max<size_t>(nrand, 1), (size_t)(48.0e6 / (double)h->nv_atoms)));
     const size_t nchunk = (size_t)h->sample_chunk;
+    phase("group maps, counters");
     CK(h->d_stats.ensure(8, true));
     P.cnt_base = h->d_cnt.p; P.acc = nullptr; P.w = 1.0;
     // shared-memory histograms: md and rdf always; group rows while all rows fit in 64 KB next to them
@@ -818,18 +937,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         h->cur = x_;
         CK(x_->d_scalars.ensure(16, true));
         if (h->path == 1) {
-            x_->slots.resize((size_t)h->batch);
-            const size_t maxq = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms);
-            for (GridSlot &S : x_->slots) {
-                CK(S.sc.ensure(SC_COUNT, true));
-                CK(S.list.ensure(nvm)); CK(S.bulk_idx.ensure(nvm));
-                CK(S.worklist.ensure(nvm)); CK(S.rand_worklist.ensure(std::max<size_t>(nchunk * nvm, 1)));
-                CK(S.def_real.ensure(nvm)); CK(S.def_rand.ensure(std::max<size_t>(nchunk * nvm, 1)));
-                CK(S.def_real_info.ensure(nvm)); CK(S.def_rand_info.ensure(std::max<size_t>(nchunk * nvm, 1)));
-                CK(S.sorted.ensure(27 * (size_t)c.solute_natomspermol));
-                CK(S.qpos.ensure(maxq)); CK(S.res.ensure(maxq));
-                CK(S.xexact.ensure(std::max<size_t>(3 * nchunk * h->nv_atoms, 1)));
-            }
+            x_->slots.resize((size_t)h->batch);      // (their scratch is allocated at the first flush that uses them)
         } else {
             CK(x_->d_list.ensure(nvm));
             int rc = pairs_create(h); if (rc) return rc;
@@ -841,13 +949,16 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     }
     h->cur = h->ctx[0];
     CK(cudaDeviceSynchronize());
+    phase("frame contexts");
     return CMX_OK;
 }
 
 int32_t cmx_create(const cmx_config *cfg, cmx_handle **out) {
     if (!cfg || !out) { g_create_error = "cmx_create: null argument"; return CMX_ERR_ARG; }
+    join_reapers();      // the memory of handles destroyed before must be back before this one allocates
     cmx_handle *h = new cmx_handle();
-    int rc = create_impl(h, cfg);
+    if (cfg->struct_size != (int32_t)sizeof(cmx_config)) { g_create_error = "cmx_config.struct_size mismatch (ABI)"; delete h; *out = nullptr; return CMX_ERR_ARG; }
+    int rc = cfg->n_devices > 1 ? group_create(h, cfg) : create_impl(h, cfg);
     if (rc) { g_create_error = h->err; cmx_destroy(h); *out = nullptr; return rc; }
     *out = h;
     return CMX_OK;
@@ -855,13 +966,29 @@ int32_t cmx_create(const cmx_config *cfg, cmx_handle **out) {
 
 int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solvent_xyz) {
     if (!h) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        if (h->acquired_child) return fail(h, CMX_ERR_STATE, "cmx_acquire_frame_buffer: previous slot not submitted");
+        cmx_handle *c = h->children[(size_t)h->next_child];
+        int rc = cmx_acquire_frame_buffer(c, solute_xyz, solvent_xyz);
+        if (rc) return group_fail(h, c, rc);
+        h->acquired_child = c;
+        return CMX_OK;
+    }
     CK(cudaSetDevice(h->device));
     if (h->acquired >= 0) return fail(h, CMX_ERR_STATE, "cmx_acquire_frame_buffer: previous slot not submitted");
+    SubmitTimer timer(h);
     Slot &s = h->ring[h->next_slot];
+    if (!s.h_in) {      // first use of this slot: pinned memory on the GPU's NUMA node + its device twin
+        NumaPrefer numa_guard(h->numa_node);
+        CK(cudaHostAlloc(&s.h_in, sizeof(float) * h->in_floats, cudaHostAllocDefault));
+        CK(cudaMalloc(&s.d_in, sizeof(float) * h->in_floats));
+        CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
     if (s.in_flight) {
         // the slot's previous frame may still wait in a batch that is not launched yet (ring shorter than the batches)
         { int rc = flush_if_pending(h, s.consumed); if (rc) return rc; }
-        CK(cudaEventSynchronize(s.consumed)); s.in_flight = false;
+        CK(wait_event(h, s.consumed)); s.in_flight = false;
     }
     h->acquired = h->next_slot;
     h->next_slot = (h->next_slot + 1) % (int)h->ring.size();
@@ -872,8 +999,21 @@ int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solv
 
 int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, const double cell[9]) {
     if (!h || !cell) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        cmx_handle *c = h->acquired_child;
+        if (!c) return fail(h, CMX_ERR_STATE, "cmx_submit_frame: no frame buffer acquired");
+        h->acquired_child = nullptr;
+        h->next_child = (h->next_child + 1) % (int)h->children.size();      // frame k of the run -> device k mod n
+        if (!h->have_weight && weight > 0) {      // ONE reference weight for the integer counters of every device
+            h->have_weight = true; h->w0 = weight;
+            for (cmx_handle *k : h->children) { k->have_weight = true; k->w0 = weight; }
+        }
+        int rc = cmx_submit_frame(c, frame_index, weight, cell);
+        return rc ? group_fail(h, c, rc) : CMX_OK;
+    }
     CK(cudaSetDevice(h->device));
     if (h->acquired < 0) return fail(h, CMX_ERR_STATE, "cmx_submit_frame: no frame buffer acquired");
+    SubmitTimer timer(h);
     Slot &s = h->ring[h->acquired];
     h->acquired = -1;
     CK(cudaMemcpyAsync(s.d_in, s.h_in, sizeof(float) * h->in_floats, cudaMemcpyHostToDevice, h->s_copy));
@@ -892,14 +1032,20 @@ int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, cons
 int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const float *d_solvent_xyz, int64_t frame_index,
                                 double weight, const double cell[9]) {
     if (!h || !cell || !d_solvent_xyz) return CMX_ERR_ARG;
+    if (is_group(h)) return fail(h, CMX_ERR_STATE, "cmx_submit_frame_device: device-resident frames need a single-device handle (n_devices <= 1)");
     CK(cudaSetDevice(h->device));
     const float *dsol = h->cfg.autocorrelation ? d_solvent_xyz : d_solute_xyz;
     if (!dsol) return fail(h, CMX_ERR_ARG, "cmx_submit_frame_device: null solute pointer");
+    SubmitTimer timer(h);
     return submit_common(h, dsol, d_solvent_xyz, frame_index, weight, cell, nullptr);
 }
 
 int32_t cmx_sync(cmx_handle *h) {
     if (!h) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        for (cmx_handle *c : h->children) { int rc = cmx_sync(c); if (rc) return group_fail(h, c, rc); }
+        return CMX_OK;
+    }
     CK(cudaSetDevice(h->device));
     { int rc = flush_all(h); if (rc) return rc; }
     if (h->ev_first_set) for (FrameCtx *x : h->ctx) CK(cudaEventRecord(x->ev_end, x->stream));
@@ -912,7 +1058,7 @@ int32_t cmx_sync(cmx_handle *h) {
     }
     prof_collect(h);
     trace_report(h);
-    for (auto &s : h->ring) s.in_flight = false;
+    for (auto &s : h->ring) s.in_flight = false;   // (everything was synchronised above)
     int sticky = 0;
     for (FrameCtx *x : h->ctx) { int v = 0; CK(cudaMemcpy(&v, x->d_scalars.p + 8, sizeof(int), cudaMemcpyDeviceToHost)); sticky |= v; }
     if (sticky) return fail(h, CMX_ERR_STATE, "deferred-pair buffer overflow: too many exactly tied / cutoff-edge pairs in one frame");
@@ -921,23 +1067,54 @@ int32_t cmx_sync(cmx_handle *h) {
 
 int32_t cmx_counters_device(cmx_handle *h, void **device_ptr, int64_t *n_uint64) {
     if (!h || !device_ptr || !n_uint64) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        int rc = group_merge(h); if (rc) return rc;
+        rc = cmx_counters_device(h->children[0], device_ptr, n_uint64);
+        return rc ? group_fail(h, h->children[0], rc) : CMX_OK;
+    }
     if (h->acc_used) return fail(h, CMX_ERR_STATE, "cmx_counters_device: frame weights varied; integer counters were folded to fp64 (use cmx_finish per GPU and sum)");
     *device_ptr = h->d_cnt.p; *n_uint64 = (int64_t)h->cnt_len;
     return CMX_OK;
 }
 
-int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
-    if (!h || !out) return CMX_ERR_ARG;
-    int rc = cmx_sync(h); if (rc) return rc;
+static int emit_counters(cmx_handle *h) {
     size_t n = h->cnt_len, nb = h->nbins;
     const double w = h->have_weight ? h->w0 : 1.0;
-    const size_t gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
+    const size_t gs = nb * h->cfg.n_groups_solute;
     size_t lo = 4 * nb, hi = 4 * nb + 2 * gs;
     if (!h->cfg.autocorrelation) lo = hi = 0;
     CK(h->d_emit.ensure(n));
     launch(h, k_emit, dim3((unsigned)((n + 255) / 256)), dim3(256), (const u64 *)h->d_cnt.p,
            (const double *)(h->acc_used ? h->d_acc.p : nullptr), h->d_emit.p, n, lo, hi, w);
     CK(cudaStreamSynchronize(h->cur->stream));
+    return CMX_OK;
+}
+
+int32_t cmx_counters_device_f64(cmx_handle *h, double **device_ptr, int64_t *n_f64) {
+    if (!h || !device_ptr || !n_f64) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        int rc = group_merge(h); if (rc) return rc;
+        rc = cmx_counters_device_f64(h->children[0], device_ptr, n_f64);
+        return rc ? group_fail(h, h->children[0], rc) : CMX_OK;
+    }
+    int rc = cmx_sync(h); if (rc) return rc;
+    rc = emit_counters(h); if (rc) return rc;
+    h->emit_valid = true;
+    *device_ptr = h->d_emit.p; *n_f64 = (int64_t)h->cnt_len;
+    return CMX_OK;
+}
+
+int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
+    if (!h || !out) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        int rc = group_merge(h); if (rc) return rc;
+        rc = cmx_finish(h->children[0], out);
+        return rc ? group_fail(h, h->children[0], rc) : CMX_OK;
+    }
+    int rc = cmx_sync(h); if (rc) return rc;
+    size_t nb = h->nbins;
+    const size_t gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
+    if (!h->emit_valid) { rc = emit_counters(h); if (rc) return rc; }
     auto emit = [&](double *dst, size_t off, size_t len) -> cudaError_t {
         if (!dst || !len) return cudaSuccess;
         return cudaMemcpy(dst, h->d_emit.p + off, sizeof(double) * len, cudaMemcpyDeviceToHost);
@@ -959,6 +1136,7 @@ static void md_to_abi(const MdRec &e, cmx_md &o) {
 
 int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out) {
     if (!h || !out) return CMX_ERR_ARG;
+    if (is_group(h)) return fail(h, CMX_ERR_STATE, "cmx_read_minimum_distances needs a single-device handle");
     if (!h->cfg.keep_lists) return fail(h, CMX_ERR_STATE, "cmx_read_minimum_distances needs cmx_config.keep_lists = 1");
     if (isolute < 0 || isolute >= h->cfg.solute_nmols) return fail(h, CMX_ERR_ARG, "isolute out of range");
     int rc = cmx_sync(h); if (rc) return rc;
@@ -981,6 +1159,7 @@ int32_t cmx_read_minimum_distances(cmx_handle *h, int32_t isolute, cmx_md *out) 
 
 int32_t cmx_read_random_minimum_distances(cmx_handle *h, int32_t sample, cmx_md *out) {
     if (!h || !out) return CMX_ERR_ARG;
+    if (is_group(h)) return fail(h, CMX_ERR_STATE, "cmx_read_random_minimum_distances needs a single-device handle");
     if (!h->cfg.keep_lists) return fail(h, CMX_ERR_STATE, "cmx_read_random_minimum_distances needs cmx_config.keep_lists = 1");
     if (sample < 0 || sample >= h->P.nrand) return fail(h, CMX_ERR_ARG, "sample out of range");
     int rc = cmx_sync(h); if (rc) return rc;
@@ -995,25 +1174,35 @@ int32_t cmx_alloc_pinned(void **ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return CMX_ERR_ARG;
     return cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault) == cudaSuccess ? CMX_OK : CMX_ERR_CUDA;
 }
-int32_t cmx_free_pinned(void *ptr) { return (!ptr || cudaFreeHost(ptr) == cudaSuccess) ? CMX_OK : CMX_ERR_CUDA; }
+int32_t cmx_free_pinned(void *ptr) {
+    if (ptr) reap([ptr] { cudaFreeHost(ptr); });      // unpinning hundreds of MB takes longer than a short run: off the caller's thread
+    return CMX_OK;
+}
 
 int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out) {
     if (!h || !out) return CMX_ERR_ARG;
+    if (is_group(h)) { int rc = CMX_OK; *out = group_stats_sum(h, &rc); return rc; }
     int rc = cmx_sync(h); if (rc) return rc;
     u64 st[8];
     CK(cudaMemcpy(st, h->d_stats.p, sizeof st, cudaMemcpyDeviceToHost));
     h->stats.pair_evals = (int64_t)st[0]; h->stats.deferred = (int64_t)st[1];
+    h->stats.volume_total = h->volume_total; h->stats.sum_weights = h->sum_weights;
     *out = h->stats;
     return CMX_OK;
 }
 
 int32_t cmx_reset(cmx_handle *h) {
     if (!h) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        for (cmx_handle *c : h->children) { int rc = cmx_reset(c); if (rc) return group_fail(h, c, rc); }
+        h->have_weight = false; h->w0 = 1.0; h->next_child = 0; h->stopped_by_file = false;
+        return CMX_OK;
+    }
     int rc = cmx_sync(h); if (rc) return rc;
     CK(cudaMemset(h->d_cnt.p, 0, sizeof(u64) * h->d_cnt.n));
     if (h->acc_used) CK(cudaMemset(h->d_acc.p, 0, sizeof(double) * h->d_acc.n));
     CK(cudaMemset(h->d_stats.p, 0, sizeof(u64) * 8));
-    h->acc_used = false; h->P.acc = nullptr; h->have_weight = false; h->w0 = 1.0;
+    h->acc_used = false; h->P.acc = nullptr; h->have_weight = false; h->w0 = 1.0; h->emit_valid = false;
     h->volume_total = 0; h->sum_weights = 0;
     h->stats = cmx_stats{};
     return CMX_OK;
@@ -1021,6 +1210,10 @@ int32_t cmx_reset(cmx_handle *h) {
 
 int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
     if (!h || !name) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        for (cmx_handle *c : h->children) { int rc = cmx_set_option(c, name, value); if (rc) return group_fail(h, c, rc); }
+        return CMX_OK;
+    }
     std::string n(name);
     if (n == "count_pairs") h->count_pairs = value != 0;
     else if (n == "profile") h->profile = value != 0;
@@ -1039,6 +1232,7 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
     }
     else if (n == "group_lanes") { /* accepted, ignored */ }
     else if (n == "poll_stop_file") h->poll_stop_file = value != 0;
+    else if (n == "sync_destroy") h->sync_destroy = value != 0;
     else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
     return CMX_OK;
 }

@@ -290,7 +290,33 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
         if (weights && !(weights[k] > 0)) return fail(h, CMX_ERR_ARG, std::string(src.what) + ": frame weights must be positive (skip zero-weight frames)");
     }
     if (nframes == 0) return CMX_OK;
+    if (is_group(h)) {
+        // one reader/consumer team per device: child c takes the frames k = c, c + n, c + 2n, ... of the list
+        const size_t n = h->children.size();
+        std::vector<std::vector<int64_t>> fr(n);
+        std::vector<std::vector<double>> wt(n);
+        for (int64_t k = 0; k < nframes; ++k) { fr[(size_t)k % n].push_back(frames[k]); if (weights) wt[(size_t)k % n].push_back(weights[k]); }
+        if (!h->have_weight) {      // ONE reference weight for the integer counters of every device
+            h->have_weight = true; h->w0 = weights ? weights[0] : 1.0;
+            for (cmx_handle *c : h->children) if (!c->have_weight) { c->have_weight = true; c->w0 = h->w0; }
+        }
+        std::vector<int> rcs(n, CMX_OK);
+        std::vector<std::thread> team;
+        for (size_t c = 0; c < n; ++c)
+            team.emplace_back([&, c] {
+                if (fr[c].empty()) return;
+                rcs[c] = run_feed(h->children[c], src, solute_indices, solvent_indices, fr[c].data(), weights ? wt[c].data() : nullptr,
+                                  (int64_t)fr[c].size(), n_reader_threads);
+            });
+        for (auto &t : team) t.join();
+        for (size_t c = 0; c < n; ++c) {
+            h->stopped_by_file |= h->children[c]->stopped_by_file;
+            if (rcs[c]) return group_fail(h, h->children[c], rcs[c]);
+        }
+        return CMX_OK;
+    }
     CK(cudaSetDevice(h->device));
+    SubmitTimer timer(h);
     const int T = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_reader_threads > 0 ? n_reader_threads : 2, 16), nframes));
     // ring slots: every compute stream needs a frame in flight and one being staged behind it (a slot is busy from the
     // read until its frame's kernels have finished), bounded to ~4 GB of pinned memory
@@ -406,6 +432,11 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
 
 int32_t cmx_reduce_groups(cmx_handle *h, int32_t which, int32_t n_groups, const int32_t *offsets, const int32_t *rows, double *out) {
     if (!h) return CMX_ERR_ARG;
+    if (is_group(h)) {
+        int rc = group_merge(h); if (rc) return rc;
+        rc = cmx_reduce_groups(h->children[0], which, n_groups, offsets, rows, out);
+        return rc ? group_fail(h, h->children[0], rc) : CMX_OK;
+    }
     if (which < 0 || which > 3 || n_groups < 1 || !offsets || !out) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: invalid argument");
     const int nrows_arr = which < 2 ? h->cfg.n_groups_solute : h->cfg.n_groups_solvent;
     const size_t nb = h->nbins, gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;

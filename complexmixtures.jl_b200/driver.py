@@ -48,20 +48,50 @@ def _dist_info():
     return 0, 1
 
 
-def allreduce_counters(eng: Engine, volume_total: float, sum_weights: float):
-    """The single exchange step: sum the integer accumulators over the GPUs (sum!, results.jl:629-649)."""
+def _device_tensor(ptr: int, n: int, typestr: str, device: int):
     import torch
-    import torch.distributed as dist
-    ptr, n = eng.counters_device()
 
     class _Wrap:
         pass
     w = _Wrap()
-    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
-    t = torch.as_tensor(w, device=f"cuda:{eng.cfg.device}")
-    eng.sync()
+    w.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(w, device=f"cuda:{device}")
+
+
+def weights_agree(my_weights, allreduce_min) -> bool:
+    """True iff every frame of EVERY rank carries one and the same weight.  ``allreduce_min(values)`` returns the
+    element-wise minimum of ``values`` over the ranks (a collective: every rank must call this function, with or
+    without frames of its own)."""
+    ws = [float(x) for x in my_weights]
+    lo, hi = (min(ws), max(ws)) if ws else (float("inf"), float("-inf"))
+    glo, gneg_hi = allreduce_min([lo, -hi])            # global min weight and -(global max weight)
+    return float(glo) == -float(gneg_hi)
+
+
+def allreduce_counters(eng: Engine, my_weights) -> tuple:
+    """The single exchange step: sum the accumulators over the GPUs (sum!, src/results.jl:629-649).
+
+    Integer hits can only be summed when every frame of every rank had ONE and the same weight (each rank scales its
+    integers by its own weight in cmx_finish); the ranks agree on that collectively BEFORE the collective, so no rank can
+    take the other branch.  Otherwise every rank folds its counters to f64 with its weights applied and the f64 arrays
+    are summed.  Returns the all-reduced (volume_total, sum_weights)."""
+    import torch
+    import torch.distributed as dist
+    dev = eng.cfg.device
+    st = eng.stats()
+
+    def _min(values):
+        t = torch.tensor(values, dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return t.tolist()
+    if weights_agree(my_weights, _min):
+        ptr, n = eng.counters_device()
+        t = _device_tensor(ptr, n, "<i8", dev)
+    else:
+        ptr, n = eng.counters_device_f64()
+        t = _device_tensor(ptr, n, "<f8", dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    s = torch.tensor([volume_total, sum_weights], dtype=torch.float64, device=t.device)
+    s = torch.tensor([st["volume_total"], st["sum_weights"]], dtype=torch.float64, device=t.device)
     dist.all_reduce(s, op=dist.ReduceOp.SUM)
     torch.cuda.synchronize(t.device)
     return float(s[0]), float(s[1])
@@ -70,18 +100,24 @@ def allreduce_counters(eng: Engine, volume_total: float, sum_weights: float):
 def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[AtomSelection] = None,
          options: Optional[Options] = None, *, trajectory_format: str = "", frame_weights=(),
          coordination_number_only: bool = False, low_memory: bool = False, device: Optional[int] = None,
-         path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None,
+         devices=None, path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None,
          _engine_cache: Optional[dict] = None, distributed: Optional[bool] = None) -> Result:
     """mddf(trajectory_file, solute, solvent, options; ...) or mddf(trajectory, options; ...).
 
     ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
     counters per GPU regardless of the thread count (src/parallel_setup.jl:21-54 does not apply).
 
+    ``devices``: several GPUs behind ONE engine in this process (``cmx_config.n_devices``; the reference's single call
+    uses the whole machine, src/parallel_setup.jl): frames are dealt to the devices in order and the per-device
+    counters are summed on the first device inside ``cmx_finish``.  Under ``torchrun`` (one process per GPU) leave it
+    unset: the ranks share the frames and sum with one all-reduce.
+
     ``feed``: "native" = the library's own DCD / XTC feed (``cmx_run_dcd`` / ``cmx_run_xtc``: reader threads -> pinned ring ->
     raw frame H2D -> device gather of the selections; the frames of this rank are read by offset, the
     others are never touched), "host" = this module's reader writing into the pinned staging slot
     (``cmx_acquire_frame_buffer`` / ``cmx_submit_frame``), "auto" = native for DCD and XTC files.  Both give
-    the same counters.  The cooperative stop file (src/mddf.jl:301-304) is only polled by the host feed.
+    the same counters.  The cooperative stop file (src/mddf.jl:301-304) is polled by both feeds (the native one checks it
+    between ring refills inside ``cmx_run_dcd`` / ``cmx_run_xtc``).
     """
     if isinstance(trajectory, str):
         if isinstance(solvent, Options) and options is None:      # mddf(file, solute_and_solvent, options)
@@ -104,12 +140,12 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
     # mddf_many: one engine (device state, streams, staging ring) serves every trajectory of the batch
-    key = (tmeta.irefatom, R.autocorrelation, coordination_number_only, device, path)
+    key = (tmeta.irefatom, R.autocorrelation, coordination_number_only, device, path, tuple(devices or ()))
     eng = None if _engine_cache is None else _engine_cache.get(key)
     if eng is None:
         eng = Engine(solute=trajectory.solute, solvent=trajectory.solvent, options=options, irefatom=tmeta.irefatom,
                      autocorrelation=R.autocorrelation, coordination_number_only=coordination_number_only, device=device,
-                     path=path, **(_engine_kw or {}))
+                     path=path, devices=devices, **(_engine_kw or {}))
         if _engine_cache is not None:
             _engine_cache[key] = eng
     else:
@@ -144,9 +180,8 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
         finally:
             trajectory.close()
     if world > 1:
-        c0 = eng.finish()
-        vol, sw = allreduce_counters(eng, c0["volume_total"], c0["sum_weights"])
-        c = eng.finish()
+        vol, sw = allreduce_counters(eng, [wt for _, wt in shard(todo, rank, world)])
+        c = eng.finish()                      # ONE read-back of the (summed) counters
         c["volume_total"], c["sum_weights"] = vol, sw
     else:
         c = eng.finish()

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcmx_b200.so")
 _SRC = [os.path.join(_HERE, "csrc", f) for f in
-        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl", "cmx_feed.inl", "cmx_xtc.inl")]
+        ("cmx_b200.cu", "cmx_kernels.cuh", "cmx_device.cuh", "cmx_pairs.cuh", "cmx_pairs_host.inl", "cmx_group.inl", "cmx_feed.inl", "cmx_xtc.inl")]
 _HDR = os.path.join(os.path.dirname(_HERE), "include", "cmx_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "63"]
@@ -44,7 +44,8 @@ class CmxConfig(C.Structure):
                 ("n_streams", C.c_int32), ("batch_frames", C.c_int32),
                 ("cutoff", C.c_double), ("dbulk", C.c_double), ("binstep", C.c_double), ("seed", C.c_uint64),
                 ("solute_group_offsets", C.c_void_p), ("solute_group_ids", C.c_void_p),
-                ("solvent_group_offsets", C.c_void_p), ("solvent_group_ids", C.c_void_p)]
+                ("solvent_group_offsets", C.c_void_p), ("solvent_group_ids", C.c_void_p),
+                ("n_devices", C.c_int32), ("reserved1", C.c_int32), ("device_ids", C.c_void_p)]
 
 
 class CmxCounters(C.Structure):
@@ -59,7 +60,9 @@ class CmxStats(C.Structure):
     _fields_ = [("frames", C.c_int64), ("kernel_launches", C.c_int64), ("deferred", C.c_int64), ("pair_evals", C.c_int64),
                 ("hits_real", C.c_int64), ("hits_random", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("gpu_ms_total", C.c_double), ("gpu_ms_main", C.c_double), ("gpu_ms_search_real", C.c_double),
-                ("gpu_ms_search_random", C.c_double), ("gpu_ms_reduce", C.c_double)]
+                ("gpu_ms_search_random", C.c_double), ("gpu_ms_reduce", C.c_double),
+                ("host_submit_ms", C.c_double), ("host_wait_ms", C.c_double), ("batches", C.c_int64),
+                ("volume_total", C.c_double), ("sum_weights", C.c_double)]
 
 
 class CmxXtcInfo(C.Structure):
@@ -74,7 +77,7 @@ MD_DTYPE = np.dtype([("within_cutoff", np.int32), ("i", np.int32), ("j", np.int3
                      ("ref_atom_within_cutoff", np.int32), ("d", np.float64), ("d_ref_atom", np.float64)])
 
 EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_acquire_frame_buffer", "cmx_submit_frame",
-           "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_finish", "cmx_read_minimum_distances",
+           "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_counters_device_f64", "cmx_finish", "cmx_read_minimum_distances",
            "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option", "cmx_alloc_pinned",
            "cmx_free_pinned", "cmx_dcd_last_error", "cmx_dcd_open", "cmx_dcd_close", "cmx_dcd_read_frame", "cmx_run_dcd",
            "cmx_reduce_groups", "cmx_xtc_open", "cmx_xtc_close", "cmx_xtc_read_frame", "cmx_run_xtc"]
@@ -101,6 +104,7 @@ def load_library(path: str = LIB_PATH):
     lib.cmx_submit_frame_device.argtypes = [vp, vp, vp, C.c_int64, C.c_double, C.POINTER(C.c_double)]
     lib.cmx_sync.argtypes = [vp]
     lib.cmx_counters_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
+    lib.cmx_counters_device_f64.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64)]
     lib.cmx_finish.argtypes = [vp, C.POINTER(CmxCounters)]
     lib.cmx_read_minimum_distances.argtypes = [vp, C.c_int32, vp]
     lib.cmx_read_random_minimum_distances.argtypes = [vp, C.c_int32, vp]
@@ -220,7 +224,7 @@ class Engine:
 
     def __init__(self, *, solute, solvent, options, irefatom: int, autocorrelation: bool,
                  coordination_number_only: bool = False, device: int = 0, path: int = 0, keep_lists: bool = False,
-                 ring_slots: int = 0, group_lanes: int = 0, n_streams: int = 0, batch_frames: int = 0):
+                 ring_slots: int = 0, group_lanes: int = 0, n_streams: int = 0, batch_frames: int = 0, devices=None):
         self.lib = load_library()
         cfg = CmxConfig()
         cfg.struct_size = C.sizeof(CmxConfig)
@@ -237,9 +241,13 @@ class Engine:
         cfg.path, cfg.ring_slots, cfg.keep_lists, cfg.group_lanes = path, ring_slots, int(keep_lists), group_lanes
         cfg.n_streams = n_streams
         cfg.batch_frames = batch_frames
+        self._keep = []
+        if devices is not None and len(devices) > 1:      # several GPUs behind this one handle (frames dealt k mod n)
+            ids = np.ascontiguousarray(devices, dtype=np.int32)
+            self._keep.append(ids)
+            cfg.n_devices, cfg.device_ids = len(ids), ids.ctypes.data
         cfg.cutoff, cfg.dbulk, cfg.binstep = options.cutoff, options.dbulk, options.binstep
         cfg.seed = options.seed if options.seed > 0 else 0
-        self._keep = []
         for side, sel in (("solute", solute), ("solvent", solvent)):
             off, ids = sel.group_csr()
             if off is not None:
@@ -348,6 +356,13 @@ class Engine:
     def counters_device(self):
         p, n = C.c_void_p(), C.c_int64()
         self._ck(self.lib.cmx_counters_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counters_device_f64(self):
+        """device pointer / length of the f64 counters with the frame weights applied (all-reduce payload when the
+        weights of the ranks are not one and the same number); the next finish() writes the array out as is"""
+        p, n = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.cmx_counters_device_f64(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
     def _result_arrays(self):

@@ -33,6 +33,7 @@ extern "C" {
 #define CMX_ERR_CELL 3     /* unit cell narrower than 2*cutoff in some direction       */
 #define CMX_ERR_STATE 4    /* call sequence error (e.g. submit without acquire)        */
 #define CMX_ERR_IO 5       /* trajectory file error (open / short read / bad header)   */
+#define CMX_ERR_MEMORY 6   /* the counters and scratch of this problem do not fit the device memory (cmx_create) */
 
 typedef struct cmx_handle cmx_handle;
 
@@ -67,6 +68,14 @@ typedef struct cmx_config {
      * src/update_counters.jl:22-36) */
     const int32_t *solute_group_offsets, *solute_group_ids;
     const int32_t *solvent_group_offsets, *solvent_group_ids;
+    /* Several GPUs behind ONE handle (the reference's one mddf() call uses the whole machine: nchunks = nthreads,
+     * src/parallel_setup.jl:7-57): n_devices > 1 and device_ids[n_devices] make cmx_create build one device context per
+     * entry (`device` is then ignored); frames are dealt to them in submission order (k mod n_devices), the native feeds
+     * run one reader/consumer team per device, and cmx_finish / cmx_counters_device / cmx_reduce_groups first sum the
+     * per-device accumulators onto the first device over peer access (sum!, src/results.jl:629-649).  The same ordinal
+     * may be listed more than once (two contexts on one GPU).  n_devices <= 1: one context on `device`. */
+    int32_t n_devices, reserved1;
+    const int32_t *device_ids;
 } cmx_config;
 
 /* Output of cmx_finish: f64 arrays laid out like Result (src/results.jl:73-104); the group
@@ -102,6 +111,11 @@ typedef struct cmx_stats {
     double gpu_ms_search_real;   /* ... of which: real-phase search / pair kernel                  */
     double gpu_ms_search_random; /* ... of which: random-phase search kernel                       */
     double gpu_ms_reduce;        /* device time of the last cmx_reduce_groups row-sum kernel (option "profile") */
+    double host_submit_ms;       /* wall time spent inside the submit / run_* calls ...                        */
+    double host_wait_ms;         /* ... of which blocked on the device (back-pressure: ring slot or batch context busy) */
+    int64_t batches;             /* kernel-sequence launches (one per batch of frames on the grid path)        */
+    double volume_total;         /* running sum_f w_f * det(cell_f) and sum_f w_f of the frames submitted so far: */
+    double sum_weights;          /* the two host-side scalars a multi-process driver adds to its all-reduce     */
 } cmx_stats;
 
 const char *cmx_version(void);
@@ -133,6 +147,12 @@ int32_t cmx_sync(cmx_handle *h);
  * cmx_sync.  Layout: md, md_random, rdf, rdf_random [nbins each], solute_group,
  * solute_group_random [n_groups_solute*nbins each], solvent_group, solvent_group_random. */
 int32_t cmx_counters_device(cmx_handle *h, void **device_ptr, int64_t *n_uint64);
+
+/* The same block as f64 with the frame weights applied (what cmx_finish will write), on the device: the payload of
+ * the all-reduce when the frame weights of the ranks are not all one and the same number (then the integer blocks
+ * cannot be summed: every rank scales them by its own weight).  After an in-place all-reduce of this array the next
+ * cmx_finish writes it out as is.  Valid until the next submit / reset. */
+int32_t cmx_counters_device_f64(cmx_handle *h, double **device_ptr, int64_t *n_f64);
 
 /* Syncs and writes the f64 counters (buffers pre-allocated by the caller; NULL members skipped). */
 int32_t cmx_finish(cmx_handle *h, cmx_counters *out);

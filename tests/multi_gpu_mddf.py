@@ -36,28 +36,32 @@ def main():
         write_dcd(path, frames, np.asarray(s.cell, dtype=np.float64))
     dist.barrier()
     opt = cm.Options(bulk_range=(10.0, 15.0), n_random_samples=5, seed=321, silent=True, irefatom=1)
-    w = [1.0] * nf
-    out = {}
-    for feed in ("native", "host"):
-        R = cm.mddf(path, sol, wat, opt, frame_weights=w, feed=feed, device=local)
-        out[feed] = R
     ok = True
+    # all weights equal (integer all-reduce); equal within a rank but different between ranks; different everywhere
+    # (the last two take the f64 exchange: every rank applies its own weights before the sum)
+    for case, w in (("uniform", [1.0] * nf), ("per-rank", [1.0 if k % world == 0 else 2.0 for k in range(nf)]),
+                    ("mixed", [(0.5, 1.0, 2.0)[k % 3] for k in range(nf)])):
+        out = {}
+        for feed in ("native", "host"):
+            out[feed] = cm.mddf(path, sol, wat, opt, frame_weights=w, feed=feed, device=local)
+        if rank == 0:
+            dist.barrier()
+            # single-process reference on this rank's GPU (the process group is ignored)
+            R1 = cm.mddf(path, sol, wat, opt, frame_weights=w, feed="native", device=local, distributed=False)
+            for feed, R in out.items():
+                for key in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count",
+                            "solvent_group_count", "solute_group_count_random", "mddf", "kb"):
+                    same = np.array_equal(getattr(R, key), getattr(R1, key))
+                    ok &= bool(same)
+                    if not same:
+                        print("MISMATCH", case, feed, key)
+                ok &= R.volume.total == R1.volume.total
+            print(f"MULTI_GPU_MDDF case={case} world={world} frames={nf} hits={R1.md_count.sum():.1f} identical so far={ok}")
+        else:
+            dist.barrier()
     if rank == 0:
-        dist.barrier()
-        # single-process reference on this rank's GPU (the process group is ignored)
-        R1 = cm.mddf(path, sol, wat, opt, frame_weights=w, feed="native", device=local, distributed=False)
-        for feed, R in out.items():
-            for key in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count",
-                        "solvent_group_count", "solute_group_count_random", "mddf", "kb"):
-                same = np.array_equal(getattr(R, key), getattr(R1, key))
-                ok &= bool(same)
-                if not same:
-                    print("MISMATCH", feed, key)
-            ok &= R.volume.total == R1.volume.total
-        print(f"MULTI_GPU_MDDF world={world} frames={nf} hits={R1.md_count.sum():.1f} identical={ok}")
+        print(f"MULTI_GPU_MDDF world={world} identical={ok}")
         os.remove(path)
-    else:
-        dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
         sys.exit(1)

@@ -123,7 +123,7 @@ def test_cabi_exports_every_declared_symbol():
     """libcmx_b200.so loads and exports every function include/cmx_b200.h declares (no compute call)."""
     from cmx_b200 import engine
     hdr = open(os.path.join(ROOT, "include", "cmx_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(cmx_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(cmx_[a-z0-9_]+)\s*\(", hdr)))
     assert len(declared) >= 15
     engine.build()
     lib = ctypes.CDLL(engine.LIB_PATH)
@@ -164,7 +164,7 @@ import os, sys
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
 import numpy as np, torch, torch.distributed as dist
 import cmx_b200 as cm
-from cmx_b200.driver import frames_to_compute, shard
+from cmx_b200.driver import frames_to_compute, shard, weights_agree
 from common import namd
 from oracle import cmx_oracle as orc
 dist.init_process_group("gloo")
@@ -172,31 +172,50 @@ rank, world = dist.get_rank(), dist.get_world_size()
 d = namd()
 protein = cm.AtomSelection(np.arange(1, 1464), nmols=1); tmao = cm.AtomSelection(np.arange(1479, 4013), natomspermol=14)
 opt = cm.Options(bulk_range=(8.0, 10.0), seed=321, silent=True, n_random_samples=3)
-todo = frames_to_compute(opt, 3, [])
-mine = shard(todo, rank, world)
-o = orc.Oracle.from_problem(protein, tmao, opt, 1, False)          # stands in for the per-rank engine (CPU test)
-for f, w in mine:
-    o.frame(d["protein"][f - 1], d["tmao"][f - 1], d["cells"][f - 1], weight=w, frame_index=f)
-c = o.counters()
-flat = torch.from_numpy(np.concatenate([c[k].ravel() for k in sorted(c) if k != "volume_total"]).astype(np.int64))
-dist.all_reduce(flat)                                              # the single exchange step (integer sum)
-vol = torch.tensor([c["volume_total"]], dtype=torch.float64); dist.all_reduce(vol)
+
+def allreduce_min(values):
+    t = torch.tensor(values, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MIN); return t.tolist()
+
+# frames 1, 2, 3, 2 (4 computed frames), three weight patterns: all equal; equal within each rank but different between
+# the ranks (the case that silently gave w_rank * (cnt0 + cnt1)); different within a rank
+for case, weights in (("uniform", [1.0, 1.0, 1.0, 1.0]), ("per-rank", [1.0, 2.0, 1.0, 2.0]), ("mixed", [0.5, 2.0, 1.0, 2.0])):
+    frames = [1, 2, 3, 2]
+    todo = list(zip(frames, weights))
+    mine = shard(todo, rank, world)
+    # the driver's decision, taken collectively BEFORE the exchange: every rank must reach the same branch
+    agree = weights_agree([w for _, w in mine], allreduce_min)
+    flags = torch.tensor([1.0 if agree else 0.0]); lo = flags.clone(); hi = flags.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert float(lo) == float(hi), "ranks disagree on the exchange branch"
+    assert agree == (case == "uniform"), (case, agree)
+    # the per-rank engine of this CPU test is the oracle; integers (uniform) or f64 with the weights applied (otherwise)
+    o = orc.Oracle.from_problem(protein, tmao, opt, 1, False)
+    for f, w in mine:
+        o.frame(d["protein"][f - 1], d["tmao"][f - 1], d["cells"][f - 1], weight=(1.0 if agree else w), frame_index=f)
+    c = o.counters()
+    keys = [k for k in sorted(c) if k != "volume_total"]
+    flat = torch.from_numpy(np.concatenate([c[k].ravel() for k in keys]).astype(np.int64 if agree else np.float64))
+    dist.all_reduce(flat)                                              # the single exchange step
+    if rank == 0:
+        ref = orc.Oracle.from_problem(protein, tmao, opt, 1, False)
+        for f, w in todo:
+            ref.frame(d["protein"][f - 1], d["tmao"][f - 1], d["cells"][f - 1], weight=w, frame_index=f)
+        r = ref.counters()
+        want = np.concatenate([r[k].ravel() for k in keys])
+        got = flat.numpy().astype(np.float64) * (weights[0] if agree else 1.0)
+        assert np.array_equal(got, want), case + ": sharded + all-reduced counters differ from the single-rank run"
 if rank == 0:
-    ref = orc.Oracle.from_problem(protein, tmao, opt, 1, False)
-    for f, w in todo:
-        ref.frame(d["protein"][f - 1], d["tmao"][f - 1], d["cells"][f - 1], weight=w, frame_index=f)
-    r = ref.counters()
-    want = np.concatenate([r[k].ravel() for k in sorted(r) if k != "volume_total"]).astype(np.int64)
-    assert np.array_equal(flat.numpy(), want), "sharded + all-reduced counters differ from the single-rank run"
-    assert np.isclose(float(vol[0]), r["volume_total"])
     print("GLOO_OK")
 dist.destroy_process_group()
 '''
 
 
 def test_frame_sharding_allreduce_gloo_world2(tmp_path):
-    """N>1 host logic on CPU: frames dealt round-robin to 2 ranks, integer counters all-reduced (gloo);
-    the Philox stream is keyed by the global frame index so the result equals the single-rank run."""
+    """N>1 host logic on CPU (gloo, world size 2): frames dealt round-robin, the driver's COLLECTIVE decision between
+    the integer exchange (all weights one number) and the f64 exchange (weights differ between or within ranks --
+    the per-rank case used to return w_rank * (cnt0 + cnt1)), and the sum equal to the single-rank run; the Philox
+    stream is keyed by the global frame index so the random phase does not depend on the sharding.  (The engine itself
+    is run sharded against single-device in the -m gpu suite: tests/test_gpu_multi.py.)"""
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
     env = dict(os.environ, OMP_NUM_THREADS="1")
