@@ -515,7 +515,7 @@ def job_leg(args, b):
     fps = b.fps
     lib, h = eng.lib, eng.h
     ps, pv = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
-    nfill = 64                                   # the first acquisitions fill the ring's slots (host memcpy, as a reader would);
+    nfill = 32 if b.xv[0].nbytes > 4e6 else 96   # the first acquisitions fill the ring's slots (host memcpy, as a reader would);
     for k in range(mine):                        # later ones re-send the bytes a slot already holds: no file I/O in this leg
         if k < nfill:
             a_s, a_v = eng.acquire()

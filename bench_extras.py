@@ -163,10 +163,65 @@ def reduce(args):
     print(json.dumps(reduce_measure(args.rows, args.repeat)))
 
 
+def group(args):
+    """ONE process, ONE handle, several GPUs (cmx_config.n_devices / device_ids): the whole C4 (or --config) trajectory
+    through create -> acquire/submit from pinned host frames -> finish (peer-access merge onto the first device) ->
+    destroy, wall clock -- the in-library counterpart of bench.py's `job` leg under torchrun."""
+    import ctypes as C
+    import time
+    import bench
+    from cmx_b200.engine import Engine, cell_to_c
+    devices = [int(x) for x in args.devices.split(",")]
+    ns = argparse.Namespace(scale=args.scale, n_random_samples=10, frames_per_step=0)
+    w = bench.build_workload(ns, args.config, 0, 1)
+    fps = min(w["fps"], 32)
+    xs, xv = bench.frames_of(w, [1 + k for k in range(fps)])
+    iref = bench.irefatom_of(w, xv[0])
+    total = args.frames or w["traj_frames"]
+    out = {"config": args.config, "frames": total, "runs": []}
+    warm = Engine(solute=w["solute"], solvent=w["solvent"], options=w["opt"], irefatom=iref, autocorrelation=w["auto"], device=devices[0])
+    warm.submit_arrays(xs[0], xv[0], w["system"].cell, frame_index=1); warm.finish(); warm.close()     # CUDA context, module load
+    for devs in ([devices[0]], devices):
+        t0 = time.perf_counter()
+        eng = Engine(solute=w["solute"], solvent=w["solvent"], options=w["opt"], irefatom=iref, autocorrelation=w["auto"],
+                     device=devs[0], devices=devs if len(devs) > 1 else None)
+        t_create = time.perf_counter() - t0
+        lib, h = eng.lib, eng.h
+        cellp = cell_to_c(w["system"].cell).ctypes.data_as(C.POINTER(C.c_double))
+        ps, pv = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        nfill = 32 * len(devs)     # every ring slot of every device is filled once -- with the SAME coordinates, so that the
+        for k in range(total):     # counters of the two runs can be compared (the frame ids, i.e. the random phases, differ)
+            if k < nfill:
+                a_s, a_v = eng.acquire()
+                a_v[...] = xv[0]
+                if not w["auto"]:
+                    a_s[...] = xs[0]
+            elif lib.cmx_acquire_frame_buffer(h, C.byref(ps), C.byref(pv)):
+                raise RuntimeError(lib.cmx_last_error(h).decode())
+            if lib.cmx_submit_frame(h, 1 + k, 1.0, cellp):
+                raise RuntimeError(lib.cmx_last_error(h).decode())
+        eng.sync()
+        t_feed = time.perf_counter() - t0
+        res = eng.finish(copy=False)
+        t_fin = time.perf_counter() - t0
+        hits = float(res["md_count"].sum()), float(res["md_count_random"].sum())
+        st = eng.stats()
+        eng.close()
+        wall = time.perf_counter() - t0
+        out["runs"].append({"devices": devs, "wall_s": wall, "frames_per_s": total / wall, "create_s": t_create, "feed_s": t_feed - t_create,
+                            "merge_finish_s": t_fin - t_feed, "hits": hits, "host_submit_ms": st["host_submit_ms"], "host_wait_ms": st["host_wait_ms"]})
+    r = out["runs"]
+    out["identical_counters"] = r[0]["hits"] == r[-1]["hits"]
+    out["speedup"] = r[0]["wall_s"] / r[-1]["wall_s"]
+    print(json.dumps(out))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["feed", "reduce"])
-    ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("what", choices=["feed", "reduce", "group"])
+    ap.add_argument("--devices", default="0,0", help="group: CUDA ordinals behind the one handle")
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--frames", type=int, default=0, help="feed: frames of the generated file (default 256); group: frames of the run (default: the configuration's trajectory)")
     ap.add_argument("--host-frames", type=int, default=64)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--rows", type=int, default=1000000)
@@ -174,4 +229,10 @@ if __name__ == "__main__":
     ap.add_argument("--tmpdir", default=None)
     ap.add_argument("--format", default="dcd", choices=["dcd", "xtc"], help="trajectory format of the feed measurement")
     a = ap.parse_args()
-    feed(a) if a.what == "feed" else reduce(a)
+    if a.what == "feed":
+        a.frames = a.frames or 256
+        feed(a)
+    elif a.what == "group":
+        group(a)
+    else:
+        reduce(a)

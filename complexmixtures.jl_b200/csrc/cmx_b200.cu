@@ -546,7 +546,8 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
         for (int s0 = 0; s0 < nrand; s0 += h->sample_chunk) {
             const int s1 = std::min(nrand, s0 + h->sample_chunk);
             if (s0 > 0) { k_reset_rand<<<nb, 32, 0, x->stream>>>(fd); h->stats.kernel_launches++; }
-            k_filter_rand<<<dim3((unsigned)((nv_mols + 255) / 256), nb, (unsigned)std::min(s1 - s0, 64)), 256, 0, x->stream>>>(fd, h->P, s0, s1);
+            k_filter_rand<<<dim3((unsigned)((nv_mols + CMX_FRAND_THREADS - 1) / CMX_FRAND_THREADS), nb, (unsigned)std::min((s1 - s0 + 31) / 32, 4096)),
+                            CMX_FRAND_THREADS, 0, x->stream>>>(fd, h->P, s0, s1);
             h->stats.kernel_launches++;
             trace_mark(h, "filter_rand");
             const size_t max_items = (size_t)(s1 - s0) * (size_t)nv_mols;

@@ -101,13 +101,15 @@ __device__ __forceinline__ double dist_pbc64(const Geom &g, double xi, double yi
     return __dsqrt_rn(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
 }
 
-// wrap a position into the primary cell (cartesian); not part of the exact path
-__device__ __forceinline__ void wrap_to_cell(const Geom &g, double x, double y, double z, double &wx,
-                                             double &wy, double &wz) {
+// wrap a position into the primary cell (cartesian); not part of the exact path: the result feeds grid look-ups only,
+// so the image count comes from a multiplication by 1/L (a point within an ulp of a face may land on either side of it;
+// both are images of the same point and the grids extend a cutoff beyond the cell)
+__device__ __forceinline__ void wrap_to_cell(const Geom &g, double x, double y, double z, double &wx, double &wy,
+                                             double &wz) {
     if (g.ortho) {
-        wx = x - g.m[0] * floor(x / g.m[0]);
-        wy = y - g.m[4] * floor(y / g.m[4]);
-        wz = z - g.m[8] * floor(z / g.m[8]);
+        wx = x - g.m[0] * floor(x * g.invl[0]);
+        wy = y - g.m[4] * floor(y * g.invl[1]);
+        wz = z - g.m[8] * floor(z * g.invl[2]);
     } else {
         const double *v = g.inv, *m = g.m;
         double s0 = v[0] * x + v[3] * y + v[6] * z;
@@ -117,6 +119,40 @@ __device__ __forceinline__ void wrap_to_cell(const Geom &g, double x, double y, 
         wx = m[0] * s0 + m[3] * s1 + m[6] * s2;
         wy = m[1] * s0 + m[4] * s1 + m[7] * s2;
         wz = m[2] * s0 + m[5] * s1 + m[8] * s2;
+    }
+}
+// fp32 wrap into the primary cell, relative to the grid centre (culls only)
+__device__ __forceinline__ void wrap_to_cell32(const Geom &g, float x, float y, float z, float &wx, float &wy, float &wz) {
+    if (g.ortho) {
+        wx = x - (float)g.m[0] * floorf(x * (float)g.invl[0]) - (float)g.ctr[0];
+        wy = y - (float)g.m[4] * floorf(y * (float)g.invl[1]) - (float)g.ctr[1];
+        wz = z - (float)g.m[8] * floorf(z * (float)g.invl[2]) - (float)g.ctr[2];
+    } else {
+        const double *v = g.inv, *m = g.m;
+        float s0 = (float)v[0] * x + (float)v[3] * y + (float)v[6] * z;
+        float s1 = (float)v[1] * x + (float)v[4] * y + (float)v[7] * z;
+        float s2 = (float)v[2] * x + (float)v[5] * y + (float)v[8] * z;
+        s0 -= floorf(s0); s1 -= floorf(s1); s2 -= floorf(s2);
+        wx = (float)m[0] * s0 + (float)m[3] * s1 + (float)m[6] * s2 - (float)g.ctr[0];
+        wy = (float)m[1] * s0 + (float)m[4] * s1 + (float)m[7] * s2 - (float)g.ctr[1];
+        wz = (float)m[2] * s0 + (float)m[5] * s1 + (float)m[8] * s2 - (float)g.ctr[2];
+    }
+}
+// fp32 minimum image of a difference of two fp32 coordinates (bounds only: radii, culls)
+__device__ __forceinline__ void min_image32f(const Geom &g, float &x, float &y, float &z) {
+    if (g.ortho) {
+        x -= (float)g.m[0] * rintf(x * (float)g.invl[0]);
+        y -= (float)g.m[4] * rintf(y * (float)g.invl[1]);
+        z -= (float)g.m[8] * rintf(z * (float)g.invl[2]);
+    } else {
+        const double *v = g.inv, *m = g.m;
+        float s0 = (float)v[0] * x + (float)v[3] * y + (float)v[6] * z;
+        float s1 = (float)v[1] * x + (float)v[4] * y + (float)v[7] * z;
+        float s2 = (float)v[2] * x + (float)v[5] * y + (float)v[8] * z;
+        s0 -= rintf(s0); s1 -= rintf(s1); s2 -= rintf(s2);
+        x = (float)m[0] * s0 + (float)m[3] * s1 + (float)m[6] * s2;
+        y = (float)m[1] * s0 + (float)m[4] * s1 + (float)m[7] * s2;
+        z = (float)m[2] * s0 + (float)m[5] * s1 + (float)m[8] * s2;
     }
 }
 

@@ -290,20 +290,37 @@ __device__ __forceinline__ int edt_x_of(const Geom &g, const u64 *__restrict__ o
     return min(min(dl, dr), g.dwin + 1);
 }
 
-// passes X and Y in one kernel: the X distance of the 2*dwin+1 rows of the window is recomputed from the row
-// bitmaps (a handful of bit operations each) instead of being written and re-read by a separate launch
-__global__ void k_edt_xy(const GridFrame *__restrict__ fds) {
+// passes X and Y in one kernel.  A block owns a tile of 32 (x) by 8 (y) cells of one z layer: the X distance of the
+// 8 + 2*dwin rows the tile's windows touch is computed ONCE from the row bitmaps (a handful of bit operations each)
+// into shared memory, then every cell takes the minimum over its window of rows.
+#define CMX_EDT_TX 32
+#define CMX_EDT_TY 8
+__global__ void __launch_bounds__(CMX_EDT_TX * CMX_EDT_TY)
+k_edt_xy(const GridFrame *__restrict__ fds) {
     CMX_FRAME(F)
-    const int ncc = F.ncull;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncc; c += gridDim.x * blockDim.x) {
-        int cx = c % g.ncx, cy = (c / g.ncx) % g.ncy, cz = c / (g.ncx * g.ncy);
-        int D = g.dwin, best = 3 * D * D;
-        for (int dy = -D; dy <= D; ++dy) {
-            int ry = cy + dy;
-            if (ry < 0 || ry >= g.ncy) continue;
-            best = min(best, edt_f(edt_x_of(g, F.occ, cz * g.ncy + ry, cx)) + edt_f(abs(dy)));
+    __shared__ unsigned char ex[CMX_EDT_TY + 2 * 15][CMX_EDT_TX];      // dwin <= 15
+    const int D = g.dwin;
+    const int tx = threadIdx.x & (CMX_EDT_TX - 1), ty = threadIdx.x / CMX_EDT_TX;
+    const int ntx = (g.ncx + CMX_EDT_TX - 1) / CMX_EDT_TX, nty = (g.ncy + CMX_EDT_TY - 1) / CMX_EDT_TY;
+    const int ntiles = ntx * nty * g.ncz;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int cz = tile / (ntx * nty), rem = tile - cz * (ntx * nty);
+        const int x0 = (rem % ntx) * CMX_EDT_TX, y0 = (rem / ntx) * CMX_EDT_TY;
+        const int cx = x0 + tx;
+        __syncthreads();
+        for (int r = ty; r < CMX_EDT_TY + 2 * D; r += CMX_EDT_TY) {
+            const int ry = y0 - D + r;
+            int v = D + 1;                                                  // outside the grid: nothing there
+            if (ry >= 0 && ry < g.ncy && cx < g.ncx) v = edt_x_of(g, F.occ, cz * g.ncy + ry, cx);
+            ex[r][tx] = (unsigned char)v;
         }
-        F.edt_xy[c] = (unsigned short)best;
+        __syncthreads();
+        const int cy = y0 + ty;
+        if (cx < g.ncx && cy < g.ncy) {
+            int best = 3 * D * D;
+            for (int dy = -D; dy <= D; ++dy) best = min(best, edt_f((int)ex[ty + D + dy][tx]) + edt_f(abs(dy)));
+            F.edt_xy[(cz * g.ncy + cy) * g.ncx + cx] = (unsigned short)best;
+        }
     }
 }
 
@@ -339,22 +356,28 @@ __global__ void k_filter_real(const GridFrame *__restrict__ fds, Prob P) {
     float r2max = 0.f;
     if (m < P.nv_mols) {
         const float *x = F.xv + (size_t)3 * P.nv_apm * m;
-        double rx = x[3 * P.iref], ry = x[3 * P.iref + 1], rz = x[3 * P.iref + 2];
-        double sx = 0, sy = 0, sz = 0;
+        const float rx = x[3 * P.iref], ry = x[3 * P.iref + 1], rz = x[3 * P.iref + 2];
+        float sx = 0, sy = 0, sz = 0;
         for (int k = 0; k < P.nv_apm; ++k) {
-            double px = x[3 * k], py = x[3 * k + 1], pz = x[3 * k + 2];
-            double wx, wy, wz; wrap_to_cell(g, px, py, pz, wx, wy, wz);
-            near |= cull_lb2(g, F.lbd2, (float)(wx - g.ctr[0]), (float)(wy - g.ctr[1]), (float)(wz - g.ctr[2])) <= g.cut_hi2;
-            double dx = px - rx, dy = py - ry, dz = pz - rz;
-            min_image64(g, dx, dy, dz);
+            const float px = x[3 * k], py = x[3 * k + 1], pz = x[3 * k + 2];
+            // cull by the distance map (fp32 wrap: its ~1e-4 A error is covered by the margin of the map's cells)
+            // (an fp32 coordinate of magnitude X carries ~1e-7 X; the test is widened by that much: including a
+            // molecule too many costs a search, never a count)
+            float wx, wy, wz; wrap_to_cell32(g, px, py, pz, wx, wy, wz);
+            const float lim = g.cut_hi + 1e-4f + 8e-7f * fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
+            near |= cull_lb2(g, F.lbd2, wx, wy, wz) <= lim * lim;
+            // the molecule re-assembled about its reference atom (bounds only: fp32 differences of the fp32 coordinates)
+            float dx = px - rx, dy = py - ry, dz = pz - rz;
+            min_image32f(g, dx, dy, dz);
             sx += dx; sy += dy; sz += dz;
         }
-        sx /= P.nv_apm; sy /= P.nv_apm; sz /= P.nv_apm;
+        const float inv = 1.0f / (float)P.nv_apm;
+        sx *= inv; sy *= inv; sz *= inv;
         for (int k = 0; k < P.nv_apm; ++k) {
-            double dx = x[3 * k] - rx, dy = x[3 * k + 1] - ry, dz = x[3 * k + 2] - rz;
-            min_image64(g, dx, dy, dz);
+            float dx = x[3 * k] - rx, dy = x[3 * k + 1] - ry, dz = x[3 * k + 2] - rz;
+            min_image32f(g, dx, dy, dz);
             dx -= sx; dy -= sy; dz -= sz;
-            r2max = fmaxf(r2max, (float)(dx * dx + dy * dy + dz * dz));
+            r2max = fmaxf(r2max, dx * dx + dy * dy + dz * dz);
         }
         if (m == F.skip_mol) near = false;   // autocorrelation: the solute molecule itself (minimum_distances.jl:90)
         MdRec e; e.d = CUDART_INF; e.dref = CUDART_INF; e.i = -1; e.j = -1; e.flags = 0; e.pad = 0;
@@ -367,8 +390,8 @@ __global__ void k_filter_real(const GridFrame *__restrict__ fds, Prob P) {
     if (lane == 0 && ball) base = atomicAdd(&F.sc[SC_WORK], __popc(ball));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (near) F.worklist[base + __popc(ball & ((1u << lane) - 1))] = m;
-    // block max of the molecule radius (rounded up)
-    float r = sqrtf(r2max) * 1.000001f + 1e-6f;
+    // block max of the molecule radius (rounded up: fp32 coordinates of ~1e3 A carry ~1e-4 A)
+    float r = sqrtf(r2max) * 1.00001f + 1e-3f;
     for (int o = 16; o; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
     if (lane == 0 && r > 0.f) atomicMax(&F.sc[SC_RMAX], __float_as_int(r));
 }
@@ -804,44 +827,63 @@ k_finalise(const GridFrame *__restrict__ fds, int nframes, Prob P, int s0) {
 // ---------------------------------------------------------------------------------------------
 // Random-phase cull: the random placements, by the position of their centre
 // ---------------------------------------------------------------------------------------------
-// grid.z strides the samples, grid.x covers the slots; the centre is evaluated in fp32 (its error, ~1e-5 A, is far
-// below the 1e-3 A margin of the test); survivors are appended with one global atomic per block
-__global__ void __launch_bounds__(256)
+// A thread owns one solvent slot and walks the samples of the chunk (up to 32 per pass: its survivors are a bit mask);
+// the centre is evaluated in fp32 (its error, ~1e-5 A, is far below the 1e-3 A margin of the test).  The block's
+// survivors are appended with ONE scan and ONE global atomic per pass.
+#define CMX_FRAND_THREADS 256
+__global__ void __launch_bounds__(CMX_FRAND_THREADS)
 k_filter_rand(const GridFrame *__restrict__ fds, Prob P, int s0, int s1) {
     CMX_FRAME(F)
-    __shared__ int s_count, s_base;
+    __shared__ int warp_tot[CMX_FRAND_THREADS / 32];
+    __shared__ int s_base;
     if (F.nrand_k == 0) return;                  // this solute molecule is the reference of no sample of the frame
     const int mol = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float rmax = __int_as_float(F.sc[SC_RMAX]);
-    for (int sample = s0 + blockIdx.z; sample < s1; sample += gridDim.z) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_count = 0;
-        __syncthreads();
-        bool near = false;
+    const bool cull = rmax <= g.rmax_bound;      // else: transform window not valid for this radius, every placement survives
+    const float lim = g.cut_hi + rmax + 2e-3f, lim2 = lim * lim;
+    const float m0 = (float)g.m[0], m1 = (float)g.m[1], m2 = (float)g.m[2], m3 = (float)g.m[3], m4 = (float)g.m[4], m5 = (float)g.m[5],
+                m6 = (float)g.m[6], m7 = (float)g.m[7], m8 = (float)g.m[8], c0 = (float)g.ctr[0], c1 = (float)g.ctr[1], c2 = (float)g.ctr[2];
+    for (int sb = s0 + 32 * (int)blockIdx.z; sb < s1; sb += 32 * (int)gridDim.z) {     // (grid.z strides the passes: many samples, few molecules)
+        const int ns = min(32, s1 - sb);
+        unsigned mask = 0u;
         if (mol < P.nv_mols && mol != F.skip_mol) {
-            bool mine = P.ns_mols == 1 || ref_solute_of_sample(P, F.frame, (uint32_t)sample) == F.isolute;
-            if (mine) {
-                if (rmax > g.rmax_bound) near = true;   // transform window not valid for this radius: no culling
-                else {
-                    uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 0u, P.seed_lo, P.seed_hi);
+            for (int t = 0; t < ns; ++t) {
+                const int sample = sb + t;
+                if (P.ns_mols != 1 && ref_solute_of_sample(P, F.frame, (uint32_t)sample) != F.isolute) continue;
+                bool near = true;
+                if (cull) {
+                    const uint4 r0 = philox4x32((uint32_t)mol, (uint32_t)sample, F.frame, 0u, P.seed_lo, P.seed_hi);
                     const float sc = 1.0f / 4294967296.0f;
-                    float u0 = ((float)r0.y + 0.5f) * sc, u1 = ((float)r0.z + 0.5f) * sc, u2 = ((float)r0.w + 0.5f) * sc;
-                    float cx_ = (float)g.m[0] * u0 + (float)g.m[3] * u1 + (float)g.m[6] * u2 - (float)g.ctr[0];
-                    float cy_ = (float)g.m[1] * u0 + (float)g.m[4] * u1 + (float)g.m[7] * u2 - (float)g.ctr[1];
-                    float cz_ = (float)g.m[2] * u0 + (float)g.m[5] * u1 + (float)g.m[8] * u2 - (float)g.ctr[2];
-                    float lim = g.cut_hi + rmax + 2e-3f;
-                    near = cull_lb2(g, F.lbd2, cx_, cy_, cz_) <= lim * lim;
+                    const float u0 = ((float)r0.y + 0.5f) * sc, u1 = ((float)r0.z + 0.5f) * sc, u2 = ((float)r0.w + 0.5f) * sc;
+                    const float cx_ = m0 * u0 + m3 * u1 + m6 * u2 - c0;
+                    const float cy_ = m1 * u0 + m4 * u1 + m7 * u2 - c1;
+                    const float cz_ = m2 * u0 + m5 * u1 + m8 * u2 - c2;
+                    near = cull_lb2(g, F.lbd2, cx_, cy_, cz_) <= lim2;
                 }
+                mask |= near ? (1u << t) : 0u;
             }
         }
-        unsigned ball = __ballot_sync(0xffffffffu, near);
-        int lane = threadIdx.x & 31, wbase = 0;
-        if (lane == 0 && ball) wbase = atomicAdd(&s_count, __popc(ball));
+        // block-wide exclusive scan of the survivor counts
+        const int mine = __popc(mask);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        __syncthreads();                          // (warp_tot / s_base of the previous pass are no longer read)
+        if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
-        if (threadIdx.x == 0 && s_count) s_base = atomicAdd(&F.sc[SC_RWORK], s_count);
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int k = 0; k < CMX_FRAND_THREADS / 32; ++k) { int v = warp_tot[k]; warp_tot[k] = run; run += v; }
+            s_base = run ? atomicAdd(&F.sc[SC_RWORK], run) : 0;
+        }
         __syncthreads();
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (near) F.rand_worklist[s_base + wbase + __popc(ball & ((1u << lane) - 1))] = (sample - s0) * P.nv_mols + mol;   // item within the chunk
+        int pos = s_base + warp_tot[wid] + incl - mine;
+        while (mask) {
+            const int t = __ffs(mask) - 1;
+            mask &= mask - 1;
+            F.rand_worklist[pos++] = (sb + t - s0) * P.nv_mols + mol;      // item within the chunk
+        }
     }
 }
 
