@@ -89,24 +89,24 @@ struct DevBuf {
 
 struct cmx_feed;   // native DCD feed ring + group-reduction scratch (cmx_feed.inl)
 
-// Device scratch of ONE frame in flight on the grid path (the pointers of a GridFrame descriptor).
+// Device scratch of ONE frame in flight on the grid path (the pointers of a GridFrame descriptor).  The buffers of all
+// slots of a batch context are carved out of ONE device allocation (the context's arena): a handle makes a handful of
+// cudaMalloc / cudaFree calls instead of a thousand -- those calls, not the kernels, were the cost of a short run.
 struct GridSlot {
-    DevBuf<int> sc, cell_count, cell_start, qcell_count, qcell_start, worklist, rand_worklist, bulk_idx;
-    DevBuf<float4> sorted, qpos, qsorted, res;
-    DevBuf<u64> bits, def_real, def_rand, scan_state;
-    DevBuf<float2> def_real_info, def_rand_info;
-    DevBuf<double> xexact;
-    DevBuf<unsigned short> edt_xy;
-    DevBuf<float> lbd2;
-    DevBuf<MdRec> list;
-    DevBuf<unsigned char> tile_valid;
-    void release() {
-        sc.release(); cell_count.release(); cell_start.release(); qcell_count.release(); qcell_start.release(); worklist.release();
-        rand_worklist.release(); bulk_idx.release(); sorted.release(); qpos.release(); qsorted.release(); res.release(); bits.release();
-        def_real.release(); def_rand.release(); scan_state.release(); def_real_info.release(); def_rand_info.release(); xexact.release();
-        edt_xy.release(); lbd2.release(); list.release(); tile_valid.release();
-    }
+    int *sc = nullptr, *cell_count = nullptr, *cell_start = nullptr, *qcell_count = nullptr, *qcell_start = nullptr, *worklist = nullptr,
+        *rand_worklist = nullptr, *bulk_idx = nullptr;
+    float4 *sorted = nullptr, *qpos = nullptr, *qsorted = nullptr, *res = nullptr;
+    u64 *bits = nullptr, *def_real = nullptr, *def_rand = nullptr, *scan_state = nullptr;
+    float2 *def_real_info = nullptr, *def_rand_info = nullptr;
+    double *xexact = nullptr;
+    unsigned short *edt_xy = nullptr;
+    float *lbd2 = nullptr;
+    MdRec *list = nullptr;
+    unsigned char *tile_valid = nullptr;
 };
+
+// sizes (elements) of the geometry-dependent buffers an arena was laid out for
+struct ArenaDims { size_t ncells = 0, ncull = 0, nqc = 0, bits = 0; };
 
 // A frame (x one solute molecule) that was submitted and waits for its batch to be launched.
 struct PendingFrame {
@@ -125,6 +125,8 @@ struct FrameCtx {
     cudaEvent_t ev_end = nullptr, ev_fd = nullptr;
     bool fd_busy = false;
     std::vector<GridSlot> slots;
+    unsigned char *arena = nullptr; size_t arena_bytes = 0;   // ONE device allocation behind all slots of this context
+    ArenaDims dims;
     GridFrame *h_fd = nullptr, *d_fd = nullptr;     // pinned / device descriptor arrays [batch]
     std::vector<PendingFrame> pending;
     std::vector<cudaEvent_t> release_events;        // recorded on `stream` once the pending frames' kernels are enqueued
@@ -135,8 +137,9 @@ struct FrameCtx {
     PairScratch pairs;
     int *h_scalars = nullptr;                       // pinned mirror (rmax feedback)
     void release() {
-        for (auto &s : slots) s.release();
         slots.clear();
+        if (arena) cudaFree(arena);
+        arena = nullptr; arena_bytes = 0;
         d_list.release(); d_scalars.release(); d_cub_tmp.release();
         if (h_fd) cudaFreeHost(h_fd);
         if (d_fd) cudaFree(d_fd);
@@ -204,6 +207,7 @@ struct cmx_handle {
     // CMX_TRACE=skip:count -- device timeline of `count` batches after `skip` flushes (events between the launches), printed at sync
     int trace_skip = -1, trace_count = 0; bool tracing = false;
     std::vector<std::pair<const char *, cudaEvent_t>> trace_events;
+    bool xtc_host_decode = false;   // option "xtc_host_decode": decode XTC frames in the reader threads instead of on the device
     bool sync_destroy = false;      // option "sync_destroy": free everything on the caller's thread
     bool poll_stop_file = true, stopped_by_file = false;   // native feed: the reference's cooperative stop file
     int numa_node = -1;                        // NUMA node of the GPU (-1 unknown): pinned staging memory is placed there
@@ -456,46 +460,82 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     size_t ncells_max = 0, ncull_max = 0, nqc_max = 0, bits_max = 0;
     bool any_random = false;
     for (unsigned k = 0; k < nb; ++k) {
+        const Geom &g = x->pending[k].g;
+        ncells_max = std::max(ncells_max, (size_t)g.nx * g.ny * g.nz); ncull_max = std::max(ncull_max, (size_t)g.ncx * g.ncy * g.ncz);
+        nqc_max = std::max(nqc_max, (size_t)g.nqx * g.nqy * g.nqz);
+        bits_max = std::max(bits_max, (size_t)g.ncy * g.ncz * g.cw + (size_t)g.ny * g.nz * g.rw);
+    }
+    {   // the context's arena: every buffer of every slot, laid out for the largest grids seen (+25 % when it has to grow)
+        const size_t nvm = (size_t)nv_mols, nchunk = (size_t)(nrand ? h->sample_chunk : 0);
+        const size_t maxq = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms), nrw = std::max<size_t>(nchunk * nvm, 1);
+        ArenaDims &D = x->dims;
+        const bool grow = !x->arena || ncells_max > D.ncells || ncull_max > D.ncull || nqc_max > D.nqc || bits_max > D.bits;
+        if (grow) {
+            auto up = [](size_t have, size_t want) { return want > have ? want + want / 4 + 64 : have; };
+            D.ncells = up(D.ncells, ncells_max); D.ncull = up(D.ncull, ncull_max); D.nqc = up(D.nqc, nqc_max); D.bits = up(D.bits, bits_max);
+        }
+        const size_t nscan = std::max(std::max(D.ncells, D.nqc) + 1, nvm) / CMX_SCAN_TILE + 2;
+        size_t off = 0;
+        auto carve = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+        struct Lay { size_t sc, cell_count, cell_start, qcell_count, qcell_start, worklist, rand_worklist, bulk_idx, sorted, qpos, qsorted, res, bits,
+                            def_real, def_rand, scan_state, def_real_info, def_rand_info, xexact, edt_xy, lbd2, list, tile_valid; } L;
+        // (the buffers that must start as zeros come first: one memset covers them)
+        L.sc = carve(sizeof(int) * SC_COUNT); L.cell_count = carve(sizeof(int) * (D.ncells + 1)); L.qcell_count = carve(sizeof(int) * (D.nqc + 1));
+        L.scan_state = carve(sizeof(u64) * nscan);
+        const size_t zero_bytes = off;
+        L.cell_start = carve(sizeof(int) * (D.ncells + 1)); L.qcell_start = carve(sizeof(int) * (D.nqc + 1));
+        L.worklist = carve(sizeof(int) * nvm); L.rand_worklist = carve(sizeof(int) * nrw); L.bulk_idx = carve(sizeof(int) * nvm);
+        L.sorted = carve(sizeof(float4) * 27 * (size_t)c.solute_natomspermol);
+        L.qpos = carve(sizeof(float4) * maxq); L.qsorted = carve(sizeof(float4) * (maxq + 32 * D.nqc)); L.res = carve(sizeof(float4) * maxq);
+        L.bits = carve(sizeof(u64) * D.bits);
+        L.def_real = carve(sizeof(u64) * nvm); L.def_rand = carve(sizeof(u64) * nrw);
+        L.def_real_info = carve(sizeof(float2) * nvm); L.def_rand_info = carve(sizeof(float2) * nrw);
+        L.xexact = carve(sizeof(double) * std::max<size_t>(3 * nchunk * h->nv_atoms, 1));
+        L.edt_xy = carve(sizeof(unsigned short) * D.ncull); L.lbd2 = carve(sizeof(float) * D.ncull);
+        L.list = carve(sizeof(MdRec) * nvm); L.tile_valid = carve(maxq / 32 + D.nqc + 1);
+        const size_t slot_bytes = off;
+        if (grow) {
+            CK(cudaStreamSynchronize(x->stream));             // the previous batch of this context still reads the old arena
+            if (x->arena) { CK(cudaFree(x->arena)); x->arena = nullptr; }
+            x->arena_bytes = slot_bytes * x->slots.size();
+            CK(cudaMalloc(&x->arena, x->arena_bytes));
+            for (size_t k = 0; k < x->slots.size(); ++k) {
+                unsigned char *base = x->arena + k * slot_bytes;
+                CK(cudaMemsetAsync(base, 0, zero_bytes, x->stream));
+                GridSlot &S = x->slots[k];
+                S.sc = (int *)(base + L.sc); S.cell_count = (int *)(base + L.cell_count); S.cell_start = (int *)(base + L.cell_start);
+                S.qcell_count = (int *)(base + L.qcell_count); S.qcell_start = (int *)(base + L.qcell_start);
+                S.worklist = (int *)(base + L.worklist); S.rand_worklist = (int *)(base + L.rand_worklist); S.bulk_idx = (int *)(base + L.bulk_idx);
+                S.sorted = (float4 *)(base + L.sorted); S.qpos = (float4 *)(base + L.qpos); S.qsorted = (float4 *)(base + L.qsorted); S.res = (float4 *)(base + L.res);
+                S.bits = (u64 *)(base + L.bits); S.def_real = (u64 *)(base + L.def_real); S.def_rand = (u64 *)(base + L.def_rand);
+                S.scan_state = (u64 *)(base + L.scan_state);
+                S.def_real_info = (float2 *)(base + L.def_real_info); S.def_rand_info = (float2 *)(base + L.def_rand_info);
+                S.xexact = (double *)(base + L.xexact); S.edt_xy = (unsigned short *)(base + L.edt_xy); S.lbd2 = (float *)(base + L.lbd2);
+                S.list = (MdRec *)(base + L.list); S.tile_valid = base + L.tile_valid;
+            }
+        }
+    }
+    for (unsigned k = 0; k < nb; ++k) {
         const PendingFrame &pf = x->pending[k];
         const Geom &g = pf.g;
         GridSlot &S = x->slots[k];
         const size_t ncells = (size_t)g.nx * g.ny * g.nz, ncc = (size_t)g.ncx * g.ncy * g.ncz, nqc = (size_t)g.nqx * g.nqy * g.nqz;
         const size_t occ_words = (size_t)g.ncy * g.ncz * g.cw, row_words = (size_t)g.ny * g.nz * g.rw;
-        {   // static-size scratch of the slot, allocated when the slot is first used (a no-op afterwards)
-            const size_t nvm = (size_t)nv_mols, nchunk = (size_t)(nrand ? h->sample_chunk : 0);
-            const size_t maxq0 = std::max<size_t>(h->nv_atoms, nchunk * h->nv_atoms);
-            CK(S.sc.ensure(SC_COUNT, true, x->stream));
-            CK(S.list.ensure(nvm)); CK(S.bulk_idx.ensure(nvm));
-            CK(S.worklist.ensure(nvm)); CK(S.rand_worklist.ensure(std::max<size_t>(nchunk * nvm, 1)));
-            CK(S.def_real.ensure(nvm)); CK(S.def_rand.ensure(std::max<size_t>(nchunk * nvm, 1)));
-            CK(S.def_real_info.ensure(nvm)); CK(S.def_rand_info.ensure(std::max<size_t>(nchunk * nvm, 1)));
-            CK(S.sorted.ensure(27 * (size_t)c.solute_natomspermol));
-            CK(S.qpos.ensure(maxq0)); CK(S.res.ensure(maxq0));
-            CK(S.xexact.ensure(std::max<size_t>(3 * nchunk * h->nv_atoms, 1)));
-        }
-        CK(S.cell_count.ensure(ncells + 1, true, x->stream)); CK(S.cell_start.ensure(ncells + 1));
-        CK(S.bits.ensure(occ_words + row_words));
-        CK(S.edt_xy.ensure(ncc)); CK(S.lbd2.ensure(ncc));
-        CK(S.qcell_count.ensure(nqc + 1, true, x->stream)); CK(S.qcell_start.ensure(nqc + 1));
-        const size_t maxq = std::max<size_t>(h->nv_atoms, (size_t)(nrand ? h->sample_chunk : 0) * h->nv_atoms);
-        CK(S.qsorted.ensure(maxq + 32 * nqc)); CK(S.tile_valid.ensure(maxq / 32 + nqc + 1));
-        CK(S.scan_state.ensure(std::max(std::max(ncells, nqc) + 1, (size_t)nv_mols) / CMX_SCAN_TILE + 2, true, x->stream));
         GridFrame &F = x->h_fd[k];
         F.g = g; F.xs = pf.xs; F.xv = pf.xv;
-        F.sc = S.sc.p; F.bits = S.bits.p; F.occ = S.bits.p; F.rowmask = S.bits.p + occ_words;
-        F.cell_count = S.cell_count.p; F.cell_start = S.cell_start.p; F.sorted = S.sorted.p;
-        F.edt_xy = S.edt_xy.p; F.lbd2 = S.lbd2.p;
-        F.qpos = S.qpos.p; F.qsorted = S.qsorted.p; F.res = S.res.p; F.xexact = S.xexact.p;
-        F.qcell_count = S.qcell_count.p; F.qcell_start = S.qcell_start.p; F.tile_valid = S.tile_valid.p;
-        F.list = S.list.p; F.rand_list = c.keep_lists ? h->d_rand_list.p : nullptr;
-        F.worklist = S.worklist.p; F.rand_worklist = S.rand_worklist.p; F.bulk_idx = S.bulk_idx.p;
-        F.def_real = S.def_real.p; F.def_rand = S.def_rand.p; F.def_real_info = S.def_real_info.p; F.def_rand_info = S.def_rand_info.p;
-        F.scan_state = S.scan_state.p;
+        F.sc = S.sc; F.bits = S.bits; F.occ = S.bits; F.rowmask = S.bits + occ_words;
+        F.cell_count = S.cell_count; F.cell_start = S.cell_start; F.sorted = S.sorted;
+        F.edt_xy = S.edt_xy; F.lbd2 = S.lbd2;
+        F.qpos = S.qpos; F.qsorted = S.qsorted; F.res = S.res; F.xexact = S.xexact;
+        F.qcell_count = S.qcell_count; F.qcell_start = S.qcell_start; F.tile_valid = S.tile_valid;
+        F.list = S.list; F.rand_list = c.keep_lists ? h->d_rand_list.p : nullptr;
+        F.worklist = S.worklist; F.rand_worklist = S.rand_worklist; F.bulk_idx = S.bulk_idx;
+        F.def_real = S.def_real; F.def_rand = S.def_rand; F.def_real_info = S.def_real_info; F.def_rand_info = S.def_rand_info;
+        F.scan_state = S.scan_state;
         F.bits_words = (long long)(occ_words + row_words);
         F.ncells = (int)ncells; F.nqcells = (int)nqc; F.ncull = (int)ncc;
         F.frame = pf.frame; F.isolute = pf.isolute; F.skip_mol = pf.skip_mol; F.nrand_k = pf.nrand_k; F.pad0 = 0; F.weight = pf.weight; F.pad1 = 0;
-        ncells_max = std::max(ncells_max, ncells); ncull_max = std::max(ncull_max, ncc); nqc_max = std::max(nqc_max, nqc);
-        bits_max = std::max(bits_max, occ_words + row_words);
+        (void)ncells; (void)ncc; (void)nqc;
         any_random |= pf.nrand_k > 0;
     }
     CK(cudaMemcpyAsync(x->d_fd, x->h_fd, sizeof(GridFrame) * nb, cudaMemcpyHostToDevice, x->stream));
@@ -526,7 +566,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     launch_y(h, k_filter_real, (unsigned)((nv_mols + 127) / 128), nb, 128u, fd, h->P);
     trace_mark(h, "filter_real");
     if (h->stats.frames < 64 || (h->stats.frames & 15) < (int64_t)nb)   // host-side bound for the NEXT frames' cull window (monotone)
-        CK(cudaMemcpyAsync(x->h_scalars + 5, x->slots[0].sc.p + SC_RMAX, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
+        CK(cudaMemcpyAsync(x->h_scalars + 5, x->slots[0].sc + SC_RMAX, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
     launch_y(h, k_gen_real, (unsigned)std::min<size_t>((h->nv_atoms + 255) / 256, (size_t)sms * 4), nb, 256u, fd, h->P);
     trace_mark(h, "gen_real");
     { int rc = search_phase<false>(h, fd, nb, h->nv_atoms, nqc_max, 0); if (rc) return rc; }
@@ -534,7 +574,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     trace_mark(h, "resolve<real>");
     if (c.keep_lists)
         for (unsigned k = 0; k < nb; ++k)
-            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)x->pending[k].isolute * nv_mols, x->slots[k].list.p, sizeof(MdRec) * (size_t)nv_mols,
+            CK(cudaMemcpyAsync(h->d_list_all.p + (size_t)x->pending[k].isolute * nv_mols, x->slots[k].list, sizeof(MdRec) * (size_t)nv_mols,
                                cudaMemcpyDeviceToDevice, x->stream));
     if (any_random) {
         // bulk list of every frame, ascending molecule index (src/mddf.jl:406-415): an ordered compaction
@@ -721,6 +761,8 @@ void reap(std::function<void()> work) {
 
 void release_handle(cmx_handle *h) {
     cudaSetDevice(h->device);
+    const double t_release = now_ms();
+    const bool trace_release = std::getenv("CMX_TRACE") != nullptr;
     for (auto &s : h->ring) {
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.d_in) cudaFree(s.d_in);
@@ -737,6 +779,7 @@ void release_handle(cmx_handle *h) {
     if (h->ev_last) cudaEventDestroy(h->ev_last);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     delete h;
+    if (trace_release) std::fprintf(stderr, "[cmx trace] release: %8.1f ms (reaper thread)\n", now_ms() - t_release);
 }
 }  // namespace
 
@@ -956,7 +999,11 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
 
 int32_t cmx_create(const cmx_config *cfg, cmx_handle **out) {
     if (!cfg || !out) { g_create_error = "cmx_create: null argument"; return CMX_ERR_ARG; }
-    join_reapers();      // the memory of handles destroyed before must be back before this one allocates
+    {
+        const double t0 = now_ms();
+        join_reapers();      // the memory of handles destroyed before must be back before this one allocates
+        if (std::getenv("CMX_TRACE")) std::fprintf(stderr, "[cmx trace] create: %8.1f ms  waiting for the release of earlier handles\n", now_ms() - t0);
+    }
     cmx_handle *h = new cmx_handle();
     if (cfg->struct_size != (int32_t)sizeof(cmx_config)) { g_create_error = "cmx_config.struct_size mismatch (ABI)"; delete h; *out = nullptr; return CMX_ERR_ARG; }
     int rc = cfg->n_devices > 1 ? group_create(h, cfg) : create_impl(h, cfg);
@@ -1234,6 +1281,7 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
     else if (n == "group_lanes") { /* accepted, ignored */ }
     else if (n == "poll_stop_file") h->poll_stop_file = value != 0;
     else if (n == "sync_destroy") h->sync_destroy = value != 0;
+    else if (n == "xtc_host_decode") h->xtc_host_decode = value != 0;
     else return fail(h, CMX_ERR_ARG, "unknown option: " + n);
     return CMX_OK;
 }

@@ -86,17 +86,27 @@ __global__ void k_gather_xyz(const float *__restrict__ raw, const int *__restric
 // What the feed loop needs from a trajectory format: the size of one raw frame in the ring, its layout on the device
 // (0 = DCD records, 1 = fp32 xyz triplets in Angstrom) and a thread-safe "produce raw frame `frame` in `dst`" that also
 // yields the unit cell.
+// Layouts: 0 = DCD records, 1 = fp32 xyz triplets, 2 = a compressed XTC frame (header + group records + bit stream)
+// that a kernel decodes into a device buffer of `decoded_bytes` before the gather.  `fill` may restrict the H2D copy to
+// byte ranges of the slot (a DCD read up to the last selected atom, a compressed frame shorter than the slot) and may
+// pass one integer to the device stage (the number of XTC groups).
+struct FeedFill {
+    std::vector<std::pair<size_t, size_t>> ranges;   // (offset, bytes) of the slot to copy; empty = the whole slot
+    int aux = 0;
+};
 struct FeedSource {
     const char *what = "";
     int64_t natoms = 0, nframes = 0;
-    size_t slot_bytes = 0;
+    size_t slot_bytes = 0, decoded_bytes = 0;
     int layout = 0;
-    std::function<bool(int64_t frame, unsigned char *dst, double cell[9], std::string &err)> fill;
+    std::function<bool(int64_t frame, unsigned char *dst, double cell[9], FeedFill &out, std::string &err)> fill;
 };
+void launch_xtc_decode(const unsigned char *d_raw, float *d_dec, int ngroups, cudaStream_t stream);   // cmx_xtc.inl
 
 struct FeedSlot {
     unsigned char *h_raw = nullptr, *d_raw = nullptr;
-    float *d_xyz = nullptr;
+    float *d_xyz = nullptr, *d_dec = nullptr;
+    FeedFill fill;
     cudaEvent_t h2d_done = nullptr, gathered = nullptr, consumed = nullptr;
     int64_t filled = -1, h2d_issued = -1;
     double cell[9] = {0};
@@ -105,20 +115,24 @@ struct FeedSlot {
 
 struct cmx_feed {
     std::vector<FeedSlot> slots;
-    size_t frame_bytes = 0;
+    unsigned char *h_arena = nullptr, *d_arena = nullptr;      // ONE pinned and ONE device allocation behind the whole ring
+    size_t frame_bytes = 0, decoded_bytes = 0;
     int *d_idx = nullptr; size_t n_idx = 0;
     std::vector<int32_t> idx_host;
     // group reduction scratch
     DevBuf<u64> red_cnt; DevBuf<double> red_acc, red_out; DevBuf<int> red_rows, red_items;
-    void release() {
+    void release_ring() {
         for (auto &s : slots) {
-            if (s.h_raw) cudaFreeHost(s.h_raw);
-            if (s.d_raw) cudaFree(s.d_raw);
-            if (s.d_xyz) cudaFree(s.d_xyz);
             if (s.h2d_done) cudaEventDestroy(s.h2d_done);
             if (s.gathered) cudaEventDestroy(s.gathered);
             if (s.consumed) cudaEventDestroy(s.consumed);
         }
+        if (h_arena) cudaFreeHost(h_arena);
+        if (d_arena) cudaFree(d_arena);
+        h_arena = d_arena = nullptr;
+    }
+    void release() {
+        release_ring();
         slots.clear();
         if (d_idx) cudaFree(d_idx);
         d_idx = nullptr; n_idx = 0; frame_bytes = 0; idx_host.clear();
@@ -132,31 +146,29 @@ void feed_destroy(cmx_handle *h) {
     if (h->feed) { h->feed->release(); delete h->feed; h->feed = nullptr; }
 }
 
-int feed_prepare(cmx_handle *h, int64_t natoms_file, size_t slot_bytes, const int32_t *sol_idx, const int32_t *solv_idx, int nslots) {
+int feed_prepare(cmx_handle *h, int64_t natoms_file, size_t slot_bytes, size_t decoded_bytes, const int32_t *sol_idx, const int32_t *solv_idx, int nslots) {
     if (!h->feed) h->feed = new cmx_feed();
     cmx_feed &F = *h->feed;
     const size_t fb = slot_bytes;
-    if (F.frame_bytes != fb || (int)F.slots.size() != nslots) {
+    if (F.frame_bytes != fb || F.decoded_bytes != decoded_bytes || (int)F.slots.size() != nslots) {
         { int rc = sync_all(h); if (rc) return rc; }
-        for (auto &s : F.slots) {
-            if (s.h_raw) cudaFreeHost(s.h_raw);
-            if (s.d_raw) cudaFree(s.d_raw);
-            if (s.d_xyz) cudaFree(s.d_xyz);
-            if (s.h2d_done) cudaEventDestroy(s.h2d_done);
-            if (s.gathered) cudaEventDestroy(s.gathered);
-            if (s.consumed) cudaEventDestroy(s.consumed);
-        }
+        F.release_ring();
         F.slots.assign((size_t)nslots, FeedSlot());
         NumaPrefer numa_guard(h->numa_node);
-        for (auto &s : F.slots) {
-            CK(cudaHostAlloc(&s.h_raw, fb, cudaHostAllocDefault));
-            CK(cudaMalloc(&s.d_raw, fb));
-            CK(cudaMalloc(&s.d_xyz, sizeof(float) * h->in_floats));
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t hb = pad(fb), xb = pad(sizeof(float) * h->in_floats), db = pad(decoded_bytes);
+        CK(cudaHostAlloc(&F.h_arena, hb * (size_t)nslots, cudaHostAllocDefault));
+        CK(cudaMalloc(&F.d_arena, (hb + xb + db) * (size_t)nslots));
+        for (size_t k = 0; k < F.slots.size(); ++k) {
+            FeedSlot &s = F.slots[k];
+            s.h_raw = F.h_arena + k * hb;
+            unsigned char *d = F.d_arena + k * (hb + xb + db);
+            s.d_raw = d; s.d_xyz = (float *)(d + hb); s.d_dec = decoded_bytes ? (float *)(d + hb + xb) : nullptr;
             CK(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.gathered, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
         }
-        F.frame_bytes = fb;
+        F.frame_bytes = fb; F.decoded_bytes = decoded_bytes;
     }
     CK(cudaStreamSynchronize(h->s_copy));   // copies of an earlier run still reading the pinned slots
     for (auto &s : F.slots) { s.filled = -1; s.h2d_issued = -1; }
@@ -324,7 +336,7 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
     const int64_t cap = std::max<int64_t>(3, (int64_t)(4.0e9 / (double)src.slot_bytes));
     // (a frame also occupies its slot while it waits in a batch that is not launched yet: B frames per context)
     const int S = (int)std::min<int64_t>(std::max((nctx + 1) * h->batch + 2, T + 2), cap);
-    { int rc = feed_prepare(h, src.natoms, src.slot_bytes, solute_indices, solvent_indices, S); if (rc) return rc; }
+    { int rc = feed_prepare(h, src.natoms, src.slot_bytes, src.decoded_bytes, solute_indices, solvent_indices, S); if (rc) return rc; }
     cmx_feed &F = *h->feed;
     std::mutex mu;
     std::condition_variable cv;
@@ -347,7 +359,8 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
                 return;
             }
             std::string err;
-            bool ok = src.fill(frames[k], s.h_raw, s.cell, err);
+            s.fill.ranges.clear(); s.fill.aux = 0;
+            bool ok = src.fill(frames[k], s.h_raw, s.cell, s.fill, err);
             std::lock_guard<std::mutex> lk(mu);
             if (!ok) { if (!abort_flag.load()) io_error = err; abort_flag = true; }
             else s.filled = k;
@@ -375,7 +388,12 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
         cudaError_t e = cudaSuccess;
         auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
         if (s.used) step(cudaStreamWaitEvent(h->s_copy, s.gathered, 0));            // d_raw free again
-        step(cudaMemcpyAsync(s.d_raw, s.h_raw, fb, cudaMemcpyHostToDevice, h->s_copy));
+        size_t copied = 0;
+        if (s.fill.ranges.empty()) { step(cudaMemcpyAsync(s.d_raw, s.h_raw, fb, cudaMemcpyHostToDevice, h->s_copy)); copied = fb; }
+        else for (const auto &r : s.fill.ranges) {
+            step(cudaMemcpyAsync(s.d_raw + r.first, s.h_raw + r.first, r.second, cudaMemcpyHostToDevice, h->s_copy));
+            copied += r.second;
+        }
         step(cudaEventRecord(s.h2d_done, h->s_copy));
         {
             std::lock_guard<std::mutex> lk(mu);
@@ -390,12 +408,17 @@ static int run_feed(cmx_handle *h, const FeedSource &src, const int32_t *solute_
         if (e == cudaSuccess) {
             const unsigned nblk = (unsigned)((F.n_idx + 255) / 256);
             if (src.layout == 0) k_gather_dcd<<<nblk, 256, 0, next->stream>>>(s.d_raw, (long long)src.natoms, F.d_idx, (int)F.n_idx, s.d_xyz);
-            else k_gather_xyz<<<nblk, 256, 0, next->stream>>>((const float *)s.d_raw, F.d_idx, (int)F.n_idx, s.d_xyz);
+            else if (src.layout == 1) k_gather_xyz<<<nblk, 256, 0, next->stream>>>((const float *)s.d_raw, F.d_idx, (int)F.n_idx, s.d_xyz);
+            else {      // compressed XTC frame: decode on the device (one thread per group of the bit stream), then gather
+                launch_xtc_decode(s.d_raw, s.d_dec, s.fill.aux, next->stream);
+                k_gather_xyz<<<nblk, 256, 0, next->stream>>>((const float *)s.d_dec, F.d_idx, (int)F.n_idx, s.d_xyz);
+                h->stats.kernel_launches++;
+            }
             h->stats.kernel_launches++;
             step(cudaEventRecord(s.gathered, next->stream));
         }
         if (e != cudaSuccess) { h->err = std::string(src.what) + ": " + cudaGetErrorString(e); rc = CMX_ERR_CUDA; break; }
-        h->stats.h2d_bytes += (int64_t)fb;
+        h->stats.h2d_bytes += (int64_t)copied;
         const float *dsol = s.d_xyz, *dsolv = s.d_xyz + 3 * ns;
         // `consumed` is recorded behind the frame's kernels, i.e. when its batch is launched
         rc = submit_common(h, dsol, dsolv, frames[k] + 1, weights ? weights[k] : 1.0, cell, s.consumed);
@@ -419,9 +442,28 @@ int32_t cmx_run_dcd(cmx_handle *h, cmx_dcd *d, const int32_t *solute_indices, co
     src.what = "cmx_run_dcd"; src.natoms = d->info.natoms; src.nframes = d->info.nframes;
     src.slot_bytes = (size_t)d->info.frame_bytes; src.layout = 0;
     const int fd = d->fd;
-    const int64_t first = d->info.first_frame_offset, fb = d->info.frame_bytes;
-    src.fill = [fd, first, fb](int64_t frame, unsigned char *dst, double cell[9], std::string &err) {
-        if (!pread_all(fd, dst, (size_t)fb, (off_t)(first + frame * fb))) { err = "short read in DCD frame " + std::to_string((long long)frame); return false; }
+    const int64_t first = d->info.first_frame_offset, fb = d->info.frame_bytes, natoms = d->info.natoms;
+    // As the reference does with `lastatom` (src/trajectory_formats/NamdDCD.jl:86-118,151-166), each of the X, Y, Z
+    // records is read -- and sent to the device -- only up to the last selected atom: solute + cosolvent selections
+    // usually sit at the start of the file (C1: 4 012 of 62 026 atoms, 15 x fewer bytes per frame).
+    int64_t last = 0;
+    const cmx_handle *hh = is_group(h) ? h->children[0] : h;      // (a group handle keeps the problem sizes in its children)
+    if (solvent_indices) for (size_t k = 0; k < hh->nv_atoms; ++k) last = std::max<int64_t>(last, solvent_indices[k]);
+    if (solute_indices && !hh->cfg.autocorrelation) for (size_t k = 0; k < hh->ns_atoms; ++k) last = std::max<int64_t>(last, solute_indices[k]);
+    last = std::min<int64_t>(std::max<int64_t>(last, 1), natoms);
+    const bool partial = last * 4 < natoms * 3;       // worth three reads instead of one
+    src.fill = [fd, first, fb, natoms, last, partial](int64_t frame, unsigned char *dst, double cell[9], FeedFill &out, std::string &err) {
+        const off_t base = (off_t)(first + frame * fb);
+        if (!partial) {
+            if (!pread_all(fd, dst, (size_t)fb, base)) { err = "short read in DCD frame " + std::to_string((long long)frame); return false; }
+        } else {
+            if (!pread_all(fd, dst, 56, base)) { err = "short read in DCD frame " + std::to_string((long long)frame); return false; }
+            for (int k = 0; k < 3; ++k) {
+                const size_t off = 56 + (size_t)k * (8 + 4 * (size_t)natoms);      // [4-byte marker][4*natoms][4-byte marker]
+                if (!pread_all(fd, dst + off, 4 + 4 * (size_t)last, base + (off_t)off)) { err = "short read in DCD frame " + std::to_string((long long)frame); return false; }
+                out.ranges.push_back({off, 4 + 4 * (size_t)last});
+            }
+        }
         double u[6];
         std::memcpy(u, dst + 4, sizeof u);
         dcd_cell(u, cell);

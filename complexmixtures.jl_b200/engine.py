@@ -80,7 +80,7 @@ EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_ac
            "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_counters_device_f64", "cmx_finish", "cmx_read_minimum_distances",
            "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option", "cmx_alloc_pinned",
            "cmx_free_pinned", "cmx_dcd_last_error", "cmx_dcd_open", "cmx_dcd_close", "cmx_dcd_read_frame", "cmx_run_dcd",
-           "cmx_reduce_groups", "cmx_xtc_open", "cmx_xtc_close", "cmx_xtc_read_frame", "cmx_run_xtc"]
+           "cmx_reduce_groups", "cmx_xtc_open", "cmx_xtc_close", "cmx_xtc_read_frame", "cmx_xtc_read_frame_device", "cmx_run_xtc"]
 
 _lib = None
 
@@ -123,6 +123,7 @@ def load_library(path: str = LIB_PATH):
     lib.cmx_xtc_close.argtypes = [vp]
     lib.cmx_run_xtc.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
     lib.cmx_xtc_read_frame.argtypes = [vp, C.c_int64, vp, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    lib.cmx_xtc_read_frame_device.argtypes = [vp, C.c_int64, C.c_int32, vp, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name not in ("cmx_version", "cmx_last_error", "cmx_dcd_last_error"):
             getattr(lib, name).restype = C.c_int32
@@ -206,6 +207,15 @@ class XtcFile:
         if rc:
             raise CmxError(rc, self.lib.cmx_dcd_last_error().decode())
         return xyz, cell.reshape(3, 3).T.copy(), int(step.value), float(time.value)
+
+    def read_frame_device(self, iframe: int, device: int = 0):
+        """the same frame decoded on the GPU (the decoder of the native feed): (xyz fp32 [natoms,3] in Angstrom, cell)"""
+        xyz = np.empty((self.natoms, 3), dtype=np.float32)
+        cell = np.zeros(9)
+        rc = self.lib.cmx_xtc_read_frame_device(self.h, int(iframe), int(device), xyz.ctypes.data, cell.ctypes.data_as(C.POINTER(C.c_double)))
+        if rc:
+            raise CmxError(rc, self.lib.cmx_dcd_last_error().decode())
+        return xyz, cell.reshape(3, 3).T.copy()
 
     def close(self):
         if getattr(self, "h", None):

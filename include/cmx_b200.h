@@ -210,9 +210,12 @@ int32_t cmx_xtc_open(const char *path, cmx_xtc **out, cmx_xtc_info *info);
 int32_t cmx_xtc_close(cmx_xtc *x);
 /* frame (0-based) -> xyz[3*natoms] fp32 Angstrom (may be NULL), cell[9] (may be NULL), MD step and time (may be NULL) */
 int32_t cmx_xtc_read_frame(cmx_xtc *x, int64_t iframe, float *xyz, double cell[9], int32_t *step, float *time);
-/* The frame loop for an XTC file (arguments as cmx_run_dcd): the reader threads read AND decode whole frames into the
- * pinned ring (n_reader_threads = 0: half of the available cores, 2..8), one H2D per decoded frame, selection gather on
- * the device. */
+/* The same frame decoded on CUDA device `device` (the decoder cmx_run_xtc uses: the host walks only the run codes of the
+ * compressed bit stream, one device thread decodes each group of atoms); bit-identical to cmx_xtc_read_frame. */
+int32_t cmx_xtc_read_frame_device(cmx_xtc *x, int64_t iframe, int32_t device, float *xyz, double cell[9]);
+/* The frame loop for an XTC file (arguments as cmx_run_dcd): the reader threads read the compressed frames into the pinned
+ * ring and walk their run codes (n_reader_threads = 0: half of the available cores, 2..8), one H2D per COMPRESSED frame,
+ * decode + selection gather on the device (option "xtc_host_decode" = 1: decode in the reader threads instead). */
 int32_t cmx_run_xtc(cmx_handle *h, cmx_xtc *x, const int32_t *solute_indices, const int32_t *solvent_indices,
                     const int64_t *frames, const double *weights, int64_t nframes, int32_t n_reader_threads);
 

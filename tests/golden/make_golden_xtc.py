@@ -27,3 +27,15 @@ for k in range(f.nframes):
                           "sum_sq": float(np.sum(x.astype(np.float64) ** 2))})
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "xtc_nucleic.json"), "w"), indent=1)
 print("wrote xtc_nucleic.json", f.natoms, f.nframes)
+
+# the first frame of the fixture, byte for byte (the frames of an XTC file are self-contained): a real GROMACS-written
+# compressed frame that travels to the GPU box, where the DEVICE decoder is checked against the host decoder and against
+# the summary above (tests/test_gpu_feed.py)
+raw = open(SRC, "rb").read()
+import struct
+nbytes = struct.unpack(">i", raw[56 + 32:56 + 36])[0]          # header 56 B, then the 36-byte block header
+first_len = 56 + 36 + ((nbytes + 3) & ~3)
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "nucleic_frame0.xtc"), "wb").write(raw[:first_len])
+g = XtcFile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "nucleic_frame0.xtc"))
+assert (g.natoms, g.nframes) == (f.natoms, 1) and np.array_equal(g.read_frame(0)[0], f.read_frame(0)[0])
+print("wrote nucleic_frame0.xtc", first_len, "bytes")

@@ -385,6 +385,42 @@ def test_native_xtc_reader_reference_fixture():
     x.close()
 
 
+def test_native_xtc_reader_golden_frame():
+    """the first frame of the reference's XTC fixture travels with the repository (tests/golden/nucleic_frame0.xtc, made by
+    tests/golden/make_golden_xtc.py): the host decoder against the committed summary, on every machine."""
+    from cmx_b200.engine import XtcFile
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "xtc_nucleic.json")))
+    x = XtcFile(os.path.join(ROOT, "tests", "golden", "nucleic_frame0.xtc"))
+    assert (x.natoms, x.nframes) == (95988, 1)
+    xyz, cell, step, time = x.read_frame(0)
+    x.close()
+    fr = g["frames"][0]
+    assert step == fr["step"] and time == fr["time"] and np.array_equal(cell, np.array(fr["cell"]))
+    assert np.array_equal(xyz[:4].astype(float), np.array(fr["first_atoms"])) and np.array_equal(xyz[-3:].astype(float), np.array(fr["last_atoms"]))
+    assert np.allclose(np.sum(xyz.astype(np.float64), axis=0), fr["sum"], rtol=1e-12)
+    assert np.isclose(float(np.sum(xyz.astype(np.float64) ** 2)), fr["sum_sq"], rtol=1e-12)
+
+
+def test_native_dcd_reader_reference_fixture():
+    """the native DCD reader on the reference's own file test/data/NAMD/traj_duplicated_first_frame.dcd (build container
+    only): frame count from the file size, unit cells, and the coordinates of the selections equal to the golden arrays
+    tests/golden/make_golden.py extracted from it with an independent numpy reader."""
+    from cmx_b200.engine import DcdFile
+    from common import namd
+    src = "/root/reference/test/data/NAMD/traj_duplicated_first_frame.dcd"
+    if not os.path.exists(src):
+        pytest.skip("reference fixture not present on this machine")
+    d = namd()
+    f = DcdFile(src)
+    assert (f.natoms, f.nframes) == (62026, 3)
+    for k in range(3):
+        xyz, cell = f.read_frame(k)
+        assert np.array_equal(xyz[0:1463], d["protein"][k]) and np.array_equal(xyz[1478:4012], d["tmao"][k])
+        assert np.allclose(cell, d["cells"][k], rtol=0, atol=1e-12)
+    assert np.array_equal(f.read_frame(0)[0], f.read_frame(1)[0])          # "duplicated first frame"
+    f.close()
+
+
 def test_xtc_compressed_block_roundtrip(tmp_path):
     """decoder of the compressed coordinate block against the test-suite's independent writer (tests/common.py:
     xtc_compress): water-like runs (swapped first pair, adaptive small range), unordered atoms (no runs), a mixture,
