@@ -1290,3 +1290,4 @@ int32_t cmx_set_option(cmx_handle *h, const char *name, double value) {
 
 #include "cmx_feed.inl"
 #include "cmx_xtc.inl"
+#include "cmx_final.inl"

@@ -121,6 +121,8 @@ struct cmx_feed {
     std::vector<int32_t> idx_host;
     // group reduction scratch
     DevBuf<u64> red_cnt; DevBuf<double> red_acc, red_out; DevBuf<int> red_rows, red_items;
+    bool red_has_acc = false;      // the last row reduction also produced an fp64 part (F.red_acc)
+    DevBuf<double> fin_prof, fin_sc, fin_selr_acc; DevBuf<u64> fin_selr;   // cmx_final.inl: profile block, scalars, ideal-gas row sums
     void release_ring() {
         for (auto &s : slots) {
             if (s.h2d_done) cudaEventDestroy(s.h2d_done);
@@ -137,6 +139,7 @@ struct cmx_feed {
         if (d_idx) cudaFree(d_idx);
         d_idx = nullptr; n_idx = 0; frame_bytes = 0; idx_host.clear();
         red_cnt.release(); red_acc.release(); red_out.release(); red_rows.release(); red_items.release();
+        fin_prof.release(); fin_sc.release(); fin_selr_acc.release(); fin_selr.release();
     }
 };
 
@@ -193,6 +196,7 @@ int feed_prepare(cmx_handle *h, int64_t natoms_file, size_t slot_bytes, size_t d
 // ---- group reduction kernels ------------------------------------------------------------------------
 // one block per (item, bin chunk); an item is a run of <= CMX_RED_ROWS rows of one group: {group, q_begin, q_end}
 #define CMX_RED_ROWS 256
+template <bool HAS_CNT>      // false: the f64 block alone is authoritative (after cmx_counters_device_f64 + all-reduce)
 __global__ void __launch_bounds__(256)
 k_reduce_rows(const u64 *__restrict__ cnt, const double *__restrict__ acc, int nbins, const int *__restrict__ items,
               const int *__restrict__ rows, u64 *__restrict__ out_cnt, double *__restrict__ out_acc) {
@@ -204,13 +208,15 @@ k_reduce_rows(const u64 *__restrict__ cnt, const double *__restrict__ acc, int n
     int q = q0;
     for (; q + 4 <= q1; q += 4) {   // four independent 8-byte streams per thread, each row segment coalesced over the bins
         const size_t r0 = (size_t)__ldg(&rows[q]), r1 = (size_t)__ldg(&rows[q + 1]), r2 = (size_t)__ldg(&rows[q + 2]), r3 = (size_t)__ldg(&rows[q + 3]);
-        s0 += __ldcs(&cnt[r0 * nbins + b]); s1 += __ldcs(&cnt[r1 * nbins + b]);
-        s2 += __ldcs(&cnt[r2 * nbins + b]); s3 += __ldcs(&cnt[r3 * nbins + b]);
+        if (HAS_CNT) {
+            s0 += __ldcs(&cnt[r0 * nbins + b]); s1 += __ldcs(&cnt[r1 * nbins + b]);
+            s2 += __ldcs(&cnt[r2 * nbins + b]); s3 += __ldcs(&cnt[r3 * nbins + b]);
+        }
         if (acc) a += (__ldcs(&acc[r0 * nbins + b]) + __ldcs(&acc[r1 * nbins + b])) + (__ldcs(&acc[r2 * nbins + b]) + __ldcs(&acc[r3 * nbins + b]));
     }
     for (; q < q1; ++q) {
         const size_t r = (size_t)__ldg(&rows[q]);
-        s0 += __ldcs(&cnt[r * nbins + b]);
+        if (HAS_CNT) s0 += __ldcs(&cnt[r * nbins + b]);
         if (acc) a += __ldcs(&acc[r * nbins + b]);
     }
     const u64 s = (s0 + s1) + (s2 + s3);
@@ -221,6 +227,61 @@ k_reduce_rows(const u64 *__restrict__ cnt, const double *__restrict__ acc, int n
 __global__ void k_reduce_emit(const u64 *__restrict__ cnt, const double *__restrict__ acc, size_t n, double scale, double *__restrict__ out) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[k] = (acc ? acc[k] : 0.0) + scale * (double)cnt[k];
+}
+
+// Row sums of one group-count array into F.red_cnt (+ F.red_acc when frame weights varied): [n_groups][nbins], on the
+// handle's current stream (not synchronised).  Shared by cmx_reduce_groups and cmx_contributions.
+int reduce_rows_device(cmx_handle *h, int32_t which, int32_t n_groups, const int32_t *offsets, const int32_t *rows) {
+    if (which < 0 || which > 3 || n_groups < 1 || !offsets) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: invalid argument");
+    const int nrows_arr = which < 2 ? h->cfg.n_groups_solute : h->cfg.n_groups_solvent;
+    const size_t nb = h->nbins, gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
+    const size_t base = 4 * nb + (which == 0 ? 0 : which == 1 ? gs : which == 2 ? 2 * gs : 2 * gs + gv);
+    const size_t nids = (size_t)offsets[n_groups];
+    if (offsets[0] != 0) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: offsets[0] must be 0");
+    if (nids && !rows) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: null rows");
+    std::vector<int> items;
+    for (int g = 0; g < n_groups; ++g) {
+        if (offsets[g + 1] < offsets[g]) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: offsets must be non-decreasing");
+        for (int q = offsets[g]; q < offsets[g + 1]; q += CMX_RED_ROWS) {
+            items.push_back(g); items.push_back(q); items.push_back(std::min(q + CMX_RED_ROWS, offsets[g + 1]));
+        }
+    }
+    for (size_t k = 0; k < nids; ++k)
+        if (rows[k] < 0 || rows[k] >= nrows_arr) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: row id out of range");
+    { int rc = cmx_sync(h); if (rc) return rc; }
+    if (!h->feed) h->feed = new cmx_feed();
+    cmx_feed &F = *h->feed;
+    const size_t nout = (size_t)n_groups * nb;
+    // emit_valid: the f64 block of cmx_counters_device_f64 holds the (all-reduced) counters with the weights applied
+    const bool f64only = h->emit_valid;
+    F.red_has_acc = h->acc_used || f64only;
+    CK(F.red_cnt.ensure(nout)); CK(F.red_out.ensure(nout));
+    if (F.red_has_acc) CK(F.red_acc.ensure(nout));
+    CK(F.red_rows.ensure(std::max<size_t>(nids, 1))); CK(F.red_items.ensure(std::max<size_t>(items.size(), 3)));
+    cudaStream_t st = h->cur->stream;
+    CK(cudaMemsetAsync(F.red_cnt.p, 0, sizeof(u64) * nout, st));
+    if (F.red_has_acc) CK(cudaMemsetAsync(F.red_acc.p, 0, sizeof(double) * nout, st));
+    if (nids) CK(cudaMemcpyAsync(F.red_rows.p, rows, sizeof(int) * nids, cudaMemcpyHostToDevice, st));
+    if (!items.empty()) {
+        CK(cudaMemcpyAsync(F.red_items.p, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice, st));
+        dim3 grid((unsigned)(items.size() / 3), (unsigned)((nb + 255) / 256));
+        cudaEvent_t pe = prof_begin(h, 2);
+        if (f64only)
+            launch(h, k_reduce_rows<false>, grid, dim3(256), (const u64 *)nullptr, (const double *)(h->d_emit.p + base),
+                   (int)nb, (const int *)F.red_items.p, (const int *)F.red_rows.p, F.red_cnt.p, F.red_acc.p);
+        else
+            launch(h, k_reduce_rows<true>, grid, dim3(256), (const u64 *)(h->d_cnt.p + base), (const double *)(h->acc_used ? h->d_acc.p + base : nullptr),
+                   (int)nb, (const int *)F.red_items.p, (const int *)F.red_rows.p, F.red_cnt.p, h->acc_used ? F.red_acc.p : (double *)nullptr);
+        prof_end(h, pe);
+        if (h->profile && h->prof_used) {   // time of the reduction kernel alone (option "profile")
+            CK(cudaStreamSynchronize(st));
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->prof_events[h->prof_used - 1].first, h->prof_events[h->prof_used - 1].second) == cudaSuccess)
+                h->stats.gpu_ms_reduce = ms;
+            h->prof_used--;
+        }
+    }
+    return CMX_OK;
 }
 
 }  // namespace
@@ -479,54 +540,18 @@ int32_t cmx_reduce_groups(cmx_handle *h, int32_t which, int32_t n_groups, const 
         rc = cmx_reduce_groups(h->children[0], which, n_groups, offsets, rows, out);
         return rc ? group_fail(h, h->children[0], rc) : CMX_OK;
     }
-    if (which < 0 || which > 3 || n_groups < 1 || !offsets || !out) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: invalid argument");
-    const int nrows_arr = which < 2 ? h->cfg.n_groups_solute : h->cfg.n_groups_solvent;
-    const size_t nb = h->nbins, gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
-    const size_t base = 4 * nb + (which == 0 ? 0 : which == 1 ? gs : which == 2 ? 2 * gs : 2 * gs + gv);
-    const size_t nids = (size_t)offsets[n_groups];
-    if (offsets[0] != 0) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: offsets[0] must be 0");
-    if (nids && !rows) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: null rows");
-    std::vector<int> items;
-    for (int g = 0; g < n_groups; ++g) {
-        if (offsets[g + 1] < offsets[g]) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: offsets must be non-decreasing");
-        for (int q = offsets[g]; q < offsets[g + 1]; q += CMX_RED_ROWS) {
-            items.push_back(g); items.push_back(q); items.push_back(std::min(q + CMX_RED_ROWS, offsets[g + 1]));
-        }
-    }
-    for (size_t k = 0; k < nids; ++k)
-        if (rows[k] < 0 || rows[k] >= nrows_arr) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: row id out of range");
-    { int rc = cmx_sync(h); if (rc) return rc; }
-    if (!h->feed) h->feed = new cmx_feed();
+    if (!out) return fail(h, CMX_ERR_ARG, "cmx_reduce_groups: invalid argument");
+    { int rc = reduce_rows_device(h, which, n_groups, offsets, rows); if (rc) return rc; }
     cmx_feed &F = *h->feed;
-    const size_t nout = (size_t)n_groups * nb;
-    CK(F.red_cnt.ensure(nout)); CK(F.red_out.ensure(nout));
-    if (h->acc_used) CK(F.red_acc.ensure(nout));
-    CK(F.red_rows.ensure(std::max<size_t>(nids, 1))); CK(F.red_items.ensure(std::max<size_t>(items.size(), 3)));
+    const size_t nout = (size_t)n_groups * h->nbins;
     cudaStream_t st = h->cur->stream;
-    CK(cudaMemsetAsync(F.red_cnt.p, 0, sizeof(u64) * nout, st));
-    if (h->acc_used) CK(cudaMemsetAsync(F.red_acc.p, 0, sizeof(double) * nout, st));
-    if (nids) CK(cudaMemcpyAsync(F.red_rows.p, rows, sizeof(int) * nids, cudaMemcpyHostToDevice, st));
-    if (!items.empty()) {
-        CK(cudaMemcpyAsync(F.red_items.p, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice, st));
-        dim3 grid((unsigned)(items.size() / 3), (unsigned)((nb + 255) / 256));
-        cudaEvent_t pe = prof_begin(h, 2);
-        launch(h, k_reduce_rows, grid, dim3(256), (const u64 *)(h->d_cnt.p + base), (const double *)(h->acc_used ? h->d_acc.p + base : nullptr),
-               (int)nb, (const int *)F.red_items.p, (const int *)F.red_rows.p, F.red_cnt.p, h->acc_used ? F.red_acc.p : (double *)nullptr);
-        prof_end(h, pe);
-    }
     // frame weight as in cmx_finish; the group counts of an autocorrelation carry w/2 (src/update_counters.jl:52-53)
     const double w = h->have_weight ? h->w0 : 1.0;
     const double scale = (h->cfg.autocorrelation && which < 2) ? w / 2 : w;
     launch(h, k_reduce_emit, dim3((unsigned)((nout + 255) / 256)), dim3(256), (const u64 *)F.red_cnt.p,
-           (const double *)(h->acc_used ? F.red_acc.p : nullptr), nout, scale, F.red_out.p);
+           (const double *)(F.red_has_acc ? F.red_acc.p : nullptr), nout, scale, F.red_out.p);
     CK(cudaStreamSynchronize(st));
     CK(cudaMemcpy(out, F.red_out.p, sizeof(double) * nout, cudaMemcpyDeviceToHost));
-    if (h->profile && h->prof_used) {   // time of the reduction kernel alone (option "profile")
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, h->prof_events[h->prof_used - 1].first, h->prof_events[h->prof_used - 1].second) == cudaSuccess)
-            h->stats.gpu_ms_reduce = ms;
-        h->prof_used--;
-    }
     return CMX_OK;
 }
 

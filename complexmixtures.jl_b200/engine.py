@@ -65,6 +65,19 @@ class CmxStats(C.Structure):
                 ("volume_total", C.c_double), ("sum_weights", C.c_double)]
 
 
+FINAL_VECTORS = ("d", "md_count", "md_count_random", "coordination_number", "coordination_number_random", "mddf", "kb",
+                 "rdf_count", "rdf_count_random", "sum_rdf_count", "sum_rdf_count_random", "rdf", "kb_rdf", "volume_shell")
+FINAL_SCALARS = ("volume_total", "volume_bulk", "volume_domain", "density_solute", "density_solvent", "density_solvent_bulk",
+                 "density_fix", "sum_weights")
+CONTRIBUTION_TYPES = ("mddf", "coordination_number", "md_count", "kbi")
+
+
+class CmxFinal(C.Structure):
+    """cmx_final (include/cmx_b200.h): the O(nbins) part of Result after finalresults!"""
+    _fields_ = ([("nbins", C.c_int32), ("reserved", C.c_int32)] + [(k, C.c_void_p) for k in FINAL_VECTORS]
+                + [(k, C.c_double) for k in FINAL_SCALARS])
+
+
 class CmxXtcInfo(C.Structure):
     _fields_ = [("natoms", C.c_int64), ("nframes", C.c_int64)]
 
@@ -80,7 +93,7 @@ EXPORTS = ["cmx_version", "cmx_last_error", "cmx_create", "cmx_destroy", "cmx_ac
            "cmx_submit_frame_device", "cmx_sync", "cmx_counters_device", "cmx_counters_device_f64", "cmx_finish", "cmx_read_minimum_distances",
            "cmx_read_random_minimum_distances", "cmx_get_stats", "cmx_reset", "cmx_set_option", "cmx_alloc_pinned",
            "cmx_free_pinned", "cmx_dcd_last_error", "cmx_dcd_open", "cmx_dcd_close", "cmx_dcd_read_frame", "cmx_run_dcd",
-           "cmx_reduce_groups", "cmx_xtc_open", "cmx_xtc_close", "cmx_xtc_read_frame", "cmx_xtc_read_frame_device", "cmx_run_xtc"]
+           "cmx_reduce_groups", "cmx_final_results", "cmx_contributions", "cmx_xtc_open", "cmx_xtc_close", "cmx_xtc_read_frame", "cmx_xtc_read_frame_device", "cmx_run_xtc"]
 
 _lib = None
 
@@ -119,6 +132,8 @@ def load_library(path: str = LIB_PATH):
     lib.cmx_dcd_read_frame.argtypes = [vp, C.c_int64, vp, vp, vp, C.POINTER(C.c_double)]
     lib.cmx_run_dcd.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
     lib.cmx_reduce_groups.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp]
+    lib.cmx_final_results.argtypes = [vp, C.c_double, C.c_double, C.POINTER(CmxFinal)]
+    lib.cmx_contributions.argtypes = [vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, vp, vp, vp]
     lib.cmx_xtc_open.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(CmxXtcInfo)]
     lib.cmx_xtc_close.argtypes = [vp]
     lib.cmx_run_xtc.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32]
@@ -350,6 +365,37 @@ class Engine:
                                     if len(groups) and off[-1] else np.zeros(0, dtype=np.int32), dtype=np.int32)
         out = np.zeros((len(groups), self.nbins))
         self._ck(self.lib.cmx_reduce_groups(self.h, code, len(groups), off.ctypes.data, rows.ctypes.data if rows.size else None,
+                                            out.ctypes.data))
+        return out
+
+    @staticmethod
+    def _groups_csr(groups):
+        off = np.zeros(len(groups) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(g) for g in groups])
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(g, dtype=np.int32).reshape(-1) for g in groups])
+                                    if len(groups) and off[-1] else np.zeros(0, dtype=np.int32), dtype=np.int32)
+        return off, rows
+
+    def final_results(self, sum_weights: float = 0.0, volume_sum: float = 0.0) -> dict:
+        """cmx_final_results: finalresults! (src/results.jl:311-469) on the device -- the O(nbins) vectors and the
+        Volume / Density scalars of Result.  ``sum_weights`` / ``volume_sum`` <= 0: the handle's own sums."""
+        f = CmxFinal()
+        out = {k: np.zeros(self.nbins) for k in FINAL_VECTORS}
+        for k, v in out.items():
+            setattr(f, k, v.ctypes.data)
+        self._ck(self.lib.cmx_final_results(self.h, float(sum_weights), float(volume_sum), C.byref(f)))
+        out.update({k: getattr(f, k) for k in FINAL_SCALARS})
+        return out
+
+    def contributions(self, side: str, groups, type: str = "mddf", sum_weights: float = 0.0, volume_sum: float = 0.0) -> np.ndarray:
+        """cmx_contributions: contributions(R, SoluteGroup|SolventGroup; type) (src/tools/contributions.jl:70-248) for
+        many groups at once, on the device.  ``side``: "solute" | "solvent"; ``groups``: sequence of sequences of 0-based
+        rows of that side's group-count array; ``type``: mddf | coordination_number | md_count | kbi.
+        Returns f64 [n_groups, nbins] (the matrix of ResidueContributions when the groups are residues)."""
+        off, rows = self._groups_csr(groups)
+        out = np.zeros((len(groups), self.nbins))
+        self._ck(self.lib.cmx_contributions(self.h, ("solute", "solvent").index(side), CONTRIBUTION_TYPES.index(type), float(sum_weights),
+                                            float(volume_sum), len(groups), off.ctypes.data, rows.ctypes.data if rows.size else None,
                                             out.ctypes.data))
         return out
 

@@ -230,6 +230,36 @@ int32_t cmx_run_xtc(cmx_handle *h, cmx_xtc *x, const int32_t *solute_indices, co
 int32_t cmx_reduce_groups(cmx_handle *h, int32_t which, int32_t n_groups, const int32_t *offsets,
                           const int32_t *rows, double *out);
 
+/* ---- finalresults! and contributions on the device -----------------------------------
+ * cmx_final_results: _mddf_final_results! / _coordination_number_final_results! + renormalize!
+ * (src/results.jl:311-469) evaluated on the device from the accumulators, in fp64 and in the reference's operation
+ * order (cumulative sums serial).  Every array pointer is caller-allocated [nbins] f64 and may be NULL.
+ * sum_weights: Q = sum of the weights of the frames of the run (sum_frame_weights, src/results.jl:288-297); <= 0 means
+ * "the frames this handle was given" (a multi-process driver passes the global sum after its all-reduce).
+ * volume_sum: sum_f w_f det(cell_f); <= 0 means the handle's own. */
+typedef struct cmx_final {
+    int32_t nbins, reserved;
+    double *d, *md_count, *md_count_random, *coordination_number, *coordination_number_random, *mddf, *kb;
+    double *rdf_count, *rdf_count_random, *sum_rdf_count, *sum_rdf_count_random, *rdf, *kb_rdf;
+    double *volume_shell;                                   /* Volume.shell                                  */
+    double volume_total, volume_bulk, volume_domain;        /* Volume (src/results.jl:35-42)                 */
+    double density_solute, density_solvent, density_solvent_bulk;   /* Density (:50-56)                      */
+    double density_fix;                                     /* density.solvent_bulk / density.solvent (:375) */
+    double sum_weights;                                     /* the Q that was used                           */
+} cmx_final;
+int32_t cmx_final_results(cmx_handle *h, double sum_weights, double volume_sum, cmx_final *out);
+
+/* contributions(R, SoluteGroup|SolventGroup; type) (src/tools/contributions.jl:70-248) for n_groups groups at once --
+ * also the matrix of ResidueContributions (src/tools/residue_contributions.jl:157-215) when the groups are residues:
+ * the rows of the group-count array that belong to each group are summed on the device (exact integer sums), scaled
+ * like finalresults! and converted to `type`; out: host array [n_groups][nbins] f64.
+ * side: 0 solute groups, 1 solvent groups (an autocorrelation has one set: src/results.jl:341-343).
+ * type: 0 :mddf (count / md_count_random, 0 where that is 0), 1 :coordination_number (cumulative sum),
+ *       2 :md_count, 3 :kbi (units.Angs3tocm3permol / density.solvent_bulk * (cumsum(count) - cumsum(count_random))).
+ * CSR group -> rows as in cmx_reduce_groups; sum_weights / volume_sum as in cmx_final_results. */
+int32_t cmx_contributions(cmx_handle *h, int32_t side, int32_t type, double sum_weights, double volume_sum, int32_t n_groups,
+                          const int32_t *offsets, const int32_t *rows, double *out);
+
 int32_t cmx_get_stats(cmx_handle *h, cmx_stats *out);
 int32_t cmx_reset(cmx_handle *h);                       /* zero all accumulators and statistics */
 int32_t cmx_set_option(cmx_handle *h, const char *name, double value);

@@ -175,4 +175,47 @@ function reduce_groups(h::Ptr{Cvoid}, which::Integer, groups::Vector{Vector{Int}
     return out
 end
 
+"""
+    final_results(h, nbins; sum_weights = 0.0, volume_sum = 0.0) -> NamedTuple
+
+`finalresults!` (src/results.jl:311-469) on the device: the `nbins` vectors of `Result` and the `Volume` / `Density`
+scalars, from the accumulators in HBM.  Field order = `cmx_final` (include/cmx_b200.h).
+"""
+mutable struct CmxFinal
+    nbins::Int32; reserved::Int32
+    d::Ptr{Float64}; md_count::Ptr{Float64}; md_count_random::Ptr{Float64}; coordination_number::Ptr{Float64}
+    coordination_number_random::Ptr{Float64}; mddf::Ptr{Float64}; kb::Ptr{Float64}; rdf_count::Ptr{Float64}
+    rdf_count_random::Ptr{Float64}; sum_rdf_count::Ptr{Float64}; sum_rdf_count_random::Ptr{Float64}; rdf::Ptr{Float64}
+    kb_rdf::Ptr{Float64}; volume_shell::Ptr{Float64}
+    volume_total::Float64; volume_bulk::Float64; volume_domain::Float64
+    density_solute::Float64; density_solvent::Float64; density_solvent_bulk::Float64; density_fix::Float64; sum_weights::Float64
+end
+const FINAL_VECTORS = (:d, :md_count, :md_count_random, :coordination_number, :coordination_number_random, :mddf, :kb, :rdf_count,
+                       :rdf_count_random, :sum_rdf_count, :sum_rdf_count_random, :rdf, :kb_rdf, :volume_shell)
+function final_results(h::Ptr{Cvoid}, nbins::Integer; sum_weights::Float64 = 0.0, volume_sum::Float64 = 0.0)
+    vecs = Dict(k => zeros(nbins) for k in FINAL_VECTORS)
+    f = CmxFinal(nbins, 0, (pointer(vecs[k]) for k in FINAL_VECTORS)..., 0, 0, 0, 0, 0, 0, 0, 0)
+    GC.@preserve vecs check(h, ccall((:cmx_final_results, libcmx), Int32, (Ptr{Cvoid}, Float64, Float64, Ref{CmxFinal}), h, sum_weights, volume_sum, f))
+    return (; vecs..., volume_total = f.volume_total, volume_bulk = f.volume_bulk, volume_domain = f.volume_domain,
+            density_solute = f.density_solute, density_solvent = f.density_solvent, density_solvent_bulk = f.density_solvent_bulk)
+end
+
+"""
+    contributions(h, side, type, groups, nbins) -> Matrix{Float64}(nbins, length(groups))
+
+`contributions(R, SoluteGroup|SolventGroup; type)` (src/tools/contributions.jl:70-248) for many groups at once on the
+device; `side` = :solute | :solvent, `type` = :mddf | :coordination_number | :md_count | :kbi, `groups[g]` = 1-based rows.
+"""
+function contributions(h::Ptr{Cvoid}, side::Symbol, type::Symbol, groups::Vector{Vector{Int}}, nbins::Integer;
+                       sum_weights::Float64 = 0.0, volume_sum::Float64 = 0.0)
+    off = Int32[0; cumsum(length.(groups))]
+    rows = Int32.(reduce(vcat, groups; init=Int[]) .- 1)
+    out = zeros(nbins, length(groups))
+    t = findfirst(==(type), (:mddf, :coordination_number, :md_count, :kbi)) - 1
+    GC.@preserve off rows out check(h, ccall((:cmx_contributions, libcmx), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Float64, Float64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        h, side == :solute ? 0 : 1, t, sum_weights, volume_sum, length(groups), off, rows, out))
+    return out
+end
+
 end # module
