@@ -74,7 +74,8 @@ def parse():
 
 
 def ncu_traffic(config, phase):
-    """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture."""
+    """DRAM bytes (read + write) per FRAME of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json; the caller scales by its frames per launch)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         return t[config][phase]
@@ -440,8 +441,9 @@ class Bench:
         pe = eng.stats()["pair_evals"] / fps
         eng.set_option("count_pairs", 0); eng.set_option("active_streams", 0)
         fpl = fps / nbatch      # frames per launch (batched launches on the grid path)
+        tpf = ncu_traffic(self.w["config"], "random" if dom.startswith("random") else "real")
         return {"bound": "hbm", "kernel": f"{kernel_name} ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu_traffic(self.w["config"], "random" if dom.startswith("random") else "real"), "peak_source": peak_src,
+                "traffic": None if tpf is None else tpf * fpl, "traffic_per_frame": tpf, "peak_source": peak_src,
                 "frames_per_launch": fpl, "algorithmic_bytes_per_launch": dom_bytes * fpl, "kernel_ms_per_launch": dom_ms * fpl,
                 "algorithmic_bytes_per_frame": dom_bytes, "kernel_ms_per_frame": dom_ms,
                 "kernel_share_of_frame": dom_ms / ms_frame if ms_frame > 0 else None,
