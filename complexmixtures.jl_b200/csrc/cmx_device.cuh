@@ -226,9 +226,16 @@ struct RandMol {
         newcm[2] = dadd(dadd(dmul(m[2], u0), dmul(m[5], u1)), dmul(m[8], u2));
         const double twopi = 6.283185307179586476925286766559;
         double c1, s1_, c2, s2_, c3, s3_;
+#ifdef CMX_SINCOSPI     // sin/cos(2 pi u) as sincospi(2 u): no argument-reduction slow path (no stack frame, fewer registers)
+        (void)twopi;
+        sincospi(dmul(2.0, u01(r1.x)), &s1_, &c1);
+        sincospi(dmul(2.0, u01(r1.y)), &s2_, &c2);
+        sincospi(dmul(2.0, u01(r1.z)), &s3_, &c3);
+#else
         sincos(dmul(twopi, u01(r1.x)), &s1_, &c1);
         sincos(dmul(twopi, u01(r1.y)), &s2_, &c2);
         sincos(dmul(twopi, u01(r1.z)), &s3_, &c3);
+#endif
         // eulermat, src/rigid_body.jl:45-57 (row-major)
         A[0] = dmul(c2, c3);                                   A[1] = dmul(-c2, s3_);                                  A[2] = s2_;
         A[3] = dadd(dmul(c1, s3_), dmul(dmul(c3, s1_), s2_));  A[4] = dsub(dmul(c1, c3), dmul(dmul(s1_, s2_), s3_));   A[5] = dmul(-c2, s1_);

@@ -432,7 +432,10 @@ __global__ void k_gen_real(const GridFrame *__restrict__ fds, Prob P) {
     }
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef CMX_GEN_MINBLOCKS
+#define CMX_GEN_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, CMX_GEN_MINBLOCKS)
 k_gen_rand(const GridFrame *__restrict__ fds, Prob P, int s0) {
     CMX_FRAME(F)
     const int count = F.sc[SC_RWORK];
@@ -499,7 +502,7 @@ __device__ __forceinline__ float warp_maxf(float x) { return fkey_inv(__reduce_m
 struct SearchFrame {
     const int *cell_start; const float4 *sorted; const u64 *rowmask; const float4 *qsorted; const unsigned char *tile_valid;
     float4 *res;
-    float gmin[3], side, inv_side, inv_sidex, search2, tol_d2, ring;
+    float gmin[3], side, inv_side, sidex, inv_sidex, search2, tol_d2, ring;
     int nx, ny, nz, rw, tile_end;     // tile_end: end of this frame's range in the batch-wide tile numbering
 };
 #define CMX_MAX_BATCH 32
@@ -516,9 +519,37 @@ struct SearchFrame {
 #ifndef CMX_SWEEP_UNROLL
 #define CMX_SWEEP_UNROLL 4
 #endif
+#ifndef CMX_XRING
+#define CMX_XRING 1                   // rings limited along x too (shells), rows taken span by span; 0 = rows swept over the full reach at once
+#endif
 constexpr int kSweepUnroll = CMX_SWEEP_UNROLL;
+#ifndef CMX_TILE_TMA
+#define CMX_TILE_TMA 1                // the next tile's 32 queries arrive by a 1-D bulk async copy (cp.async.bulk + mbarrier) while this tile is searched
+#endif
 #define CMX_SEG_MAX (32 * CMX_ROWS_PER_LANE)
-#define CMX_WARP_SMEM (CMX_STAGE * 16 + CMX_SEG_MAX * 4 + CMX_STAGE + 16)   // staged atoms, segment table, owner marks, carry
+#define CMX_WARP_SMEM_BASE (CMX_STAGE * 16 + CMX_SEG_MAX * 4 + CMX_STAGE + 16)   // staged atoms, segment table, owner marks, carry
+#if CMX_TILE_TMA
+#define CMX_WARP_SMEM (CMX_WARP_SMEM_BASE + 2 * 512 + 16)                         // + two query tiles (double buffer) + two mbarriers
+#else
+#define CMX_WARP_SMEM CMX_WARP_SMEM_BASE
+#endif
+static_assert(CMX_WARP_SMEM % 16 == 0 && CMX_WARP_SMEM_BASE % 16 == 0, "per-warp shared memory is carved in 16-byte units (bulk copies)");
+
+// ---- 1-D bulk async copy global -> shared, completion on an mbarrier (sm_90+: SASS UBLKCP / SYNCS) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, void *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 #define CMX_SEARCH_SMEM (CMX_SEARCH_WARPS * CMX_WARP_SMEM)
 
 template <bool COUNT, bool RANDOM>
@@ -533,7 +564,7 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
         SearchFrame s;
         s.cell_start = F.cell_start; s.sorted = F.sorted; s.rowmask = F.rowmask; s.qsorted = F.qsorted; s.tile_valid = F.tile_valid; s.res = F.res;
         s.gmin[0] = F.g.gmin[0]; s.gmin[1] = F.g.gmin[1]; s.gmin[2] = F.g.gmin[2];
-        s.side = F.g.side; s.inv_side = F.g.inv_side; s.inv_sidex = F.g.inv_sidex; s.search2 = F.g.search2; s.tol_d2 = F.g.tol_d2; s.ring = F.g.ring;
+        s.side = F.g.side; s.inv_side = F.g.inv_side; s.sidex = F.g.sidex; s.inv_sidex = F.g.inv_sidex; s.search2 = F.g.search2; s.tol_d2 = F.g.tol_d2; s.ring = F.g.ring;
         s.nx = F.g.nx; s.ny = F.g.ny; s.nz = F.g.nz; s.rw = F.g.rw;
         s.tile_end = F.qcell_start[F.nqcells];    // exclusive scan of the per-cell tile counts: total tiles of the frame
         sf[threadIdx.x] = s;
@@ -550,6 +581,44 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
     int *seg_src = reinterpret_cast<int *>(wsm + CMX_STAGE * 16);                 // per segment: (first cell-sorted atom) - (position in the ring's flattened order)
     unsigned char *owner = wsm + CMX_STAGE * 16 + CMX_SEG_MAX * 4;                // per staged position: 1 + segment that STARTS there, else 0
     int *carry = reinterpret_cast<int *>(wsm + CMX_STAGE * 16 + CMX_SEG_MAX * 4 + CMX_STAGE);
+#if CMX_TILE_TMA
+    // Tickets run TWO tiles ahead and the query tile ONE ahead: while tile i is searched, the 512 bytes of tile i+1 are
+    // on their way into the warp's other buffer (bulk async copy, completion counted on an mbarrier) together with its
+    // valid-lane count, and the atomic for ticket i+2 is in flight -- the warp never waits for a global round trip between tiles.
+    float4 *qbuf = reinterpret_cast<float4 *>(wsm + CMX_WARP_SMEM_BASE);            // [2][32]
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(wsm + CMX_WARP_SMEM_BASE + 1024);
+    if (lane == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init_fence(); }
+    __syncwarp();
+    int t_cur = 0, t_nxt = 0, nv_cur = 0, fi_cur = 0, tile_cur = 0;
+    auto locate = [&](int gt, int &fi, int &tile) { fi = 0; while (gt >= sf[fi].tile_end) ++fi; tile = gt - (fi ? sf[fi - 1].tile_end : 0); };
+    if (lane == 0) {
+        t_cur = atomicAdd(tile_queue, 1); t_nxt = atomicAdd(tile_queue, 1);
+        if (t_cur < ntiles_all) {
+            locate(t_cur, fi_cur, tile_cur);
+            bulk_load(qbuf, sf[fi_cur].qsorted + (size_t)tile_cur * 32, 512u, &mbar[0]);
+            nv_cur = sf[fi_cur].tile_valid[tile_cur];
+        }
+    }
+    for (int it = 0;; ++it) {
+        const int gt = __shfl_sync(0xffffffffu, t_cur, 0);
+        if (gt >= ntiles_all) break;
+        const int fi = __shfl_sync(0xffffffffu, fi_cur, 0), nvalid = __shfl_sync(0xffffffffu, nv_cur, 0);
+        const int buf = it & 1;
+        if (lane == 0) {        // (the buffer of tile it+1 was last read at the start of tile it-1: free)
+            t_cur = t_nxt;
+            t_nxt = atomicAdd(tile_queue, 1);
+            if (t_cur < ntiles_all) {
+                locate(t_cur, fi_cur, tile_cur);
+                bulk_load(qbuf + 32 * (buf ^ 1), sf[fi_cur].qsorted + (size_t)tile_cur * 32, 512u, &mbar[buf ^ 1]);
+                nv_cur = sf[fi_cur].tile_valid[tile_cur];
+            }
+        }
+        const SearchFrame &S = sf[fi];
+        const bool valid = lane < nvalid;
+        mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));
+        float4 q = qbuf[32 * buf + (valid ? lane : 0)];                           // unused lanes shadow the tile's first query
+        __syncwarp();
+#else
     int gt_next = 0;
     if (lane == 0) gt_next = atomicAdd(tile_queue, 1);
     while (true) {
@@ -563,12 +632,16 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
         const int nvalid = S.tile_valid[tile];
         const bool valid = lane < nvalid;
         float4 q = __ldg(&S.qsorted[(size_t)tile * 32 + (valid ? lane : 0)]);   // unused lanes shadow the tile's first query
+#endif
         const float xmin = warp_minf(q.x), xmax = warp_maxf(q.x), ymin = warp_minf(q.y), ymax = warp_maxf(q.y),
                     zmin = warp_minf(q.z), zmax = warp_maxf(q.z);
         const float2 nqx = make_float2(-q.x, -q.x), nqy = make_float2(-q.y, -q.y), nqz = make_float2(-q.z, -q.z);
         float b1 = CUDART_INF_F, b2 = CUDART_INF_F; int bi = -1;
         float bound = S.search2;
         const float gmin0 = S.gmin[0], gmin1 = S.gmin[1], gmin2 = S.gmin[2], side = S.side, inv_side = S.inv_side, inv_sidex = S.inv_sidex;
+#if CMX_XRING
+        const float sidex = S.sidex;
+#endif
         const int nx = S.nx, ny = S.ny, nz = S.nz, rw = S.rw;
         const float reach = sqrtf(bound) + slack;
         const int ry_lo = max((int)floorf((ymin - reach - gmin1) * inv_side), 0);
@@ -582,9 +655,15 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
             // ---- probe: lane handles rows chunk + u*32 + lane
             float rd[CMX_ROWS_PER_LANE];
             int rrow[CMX_ROWS_PER_LANE];          // (rz * ny + ry) of the probed row
+#if CMX_XRING
+            unsigned cons[CMX_ROWS_PER_LANE];     // cells of the row already swept: [lo 16 bits, hi 16 bits]; lo > hi = none yet
+#endif
 #pragma unroll
             for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
                 rd[u] = CUDART_INF_F; rrow[u] = 0;
+#if CMX_XRING
+                cons[u] = 0x0000ffffu;
+#endif
                 int r = chunk + u * 32 + lane;
                 if (r < nrows) {
                     int rzq = r / nry;
@@ -611,6 +690,65 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
                 }
             }
             // ---- consume the occupied rows in rings of increasing distance
+#if CMX_XRING
+            // A ring is a SHELL around the tile in all three directions: a row within reach of the ring is swept only over
+            // the x-span the ring's radius allows (hx = sqrt(lim - rd), not sqrt(bound - rd)); what is left of it -- the
+            // cells to the left and to the right of the swept span -- stays in play with the lower bound
+            // key = rd + (swept half-width)^2 and is taken by a later ring, if the shrinking tile bound still reaches it.
+            // (Before: the first ring swept its rows over the full reach of the INITIAL bound, +-cutoff along x, although
+            // the bound of a tile inside or next to the solute drops to a few A^2 after that ring.)
+            while (true) {
+                float key[CMX_ROWS_PER_LANE];
+                float m = CUDART_INF_F;
+#pragma unroll
+                for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
+                    const int cl = (int)(cons[u] & 0xffffu), ch = (int)(cons[u] >> 16);
+                    float k = rd[u];
+                    if (cl <= ch) {
+                        const float l = cl == 0 ? CUDART_INF_F : xmin - (gmin0 + cl * sidex);
+                        const float r = ch == nx - 1 ? CUDART_INF_F : (gmin0 + (ch + 1) * sidex) - xmax;
+                        const float hw = fmaxf(fminf(l, r) - slack, 0.f);
+                        k = rd[u] + hw * hw;              // (rd = inf stays inf; both sides at the grid edge -> inf)
+                    }
+                    key[u] = k;
+                    m = fminf(m, k);
+                }
+                const float wm = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(m)));   // keys >= 0: bit order == value order
+                if (!(wm <= bound)) break;
+                const float rt = sqrtf(wm) + S.ring;
+                const float lim = fminf(rt * rt, bound);
+                const bool last = lim >= bound;           // this ring reaches as far as the tile bound: its rows are finished
+              for (int sd = 0; sd < 2; ++sd) {            // sd 0: the spans to the right of what was swept; sd 1: to the left (or the whole span)
+                bool mine = false;
+#pragma unroll
+                for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) mine |= key[u] <= lim && (sd == 1 || (cons[u] & 0xffffu) <= (cons[u] >> 16));
+                if (!__any_sync(0xffffffffu, mine)) continue;
+                int aa[CMX_ROWS_PER_LANE], na[CMX_ROWS_PER_LANE];
+                int mytotal = 0;
+#pragma unroll
+                for (int u = 0; u < CMX_ROWS_PER_LANE; ++u) {
+                    aa[u] = 0; na[u] = 0;
+                    if (key[u] <= lim) {
+                        const float hx = sqrtf(fmaxf(lim - rd[u], 0.f)) + slack;
+                        const int cxl = max((int)floorf((xmin - hx - gmin0) * inv_sidex), 0);
+                        const int cxh = min((int)floorf((xmax + hx - gmin0) * inv_sidex), nx - 1);
+                        int cl = (int)(cons[u] & 0xffffu), ch = (int)(cons[u] >> 16);
+                        const bool none = cl > ch;
+                        int s0 = 0, s1 = -1;              // cells [s0, s1] of this pass
+                        if (sd == 0) { if (!none && cxh > ch) { s0 = ch + 1; s1 = cxh; ch = cxh; } }
+                        else if (none) { s0 = cxl; s1 = cxh; if (cxl <= cxh) { cl = cxl; ch = cxh; } }
+                        else if (cxl < cl) { s0 = cxl; s1 = cl - 1; cl = cxl; }
+                        if (s0 <= s1) {
+                            const int rowbase = rrow[u] * nx;
+                            aa[u] = __ldg(&cell_start[rowbase + s0]);
+                            na[u] = __ldg(&cell_start[rowbase + s1 + 1]) - aa[u];
+                        }
+                        cons[u] = (unsigned)cl | ((unsigned)ch << 16);
+                        if (sd == 1 && (last || (cl == 0 && ch == nx - 1) || cxl > cxh)) rd[u] = CUDART_INF_F;
+                        mytotal += na[u];
+                    }
+                }
+#else
             while (true) {
                 float m = rd[0];
 #pragma unroll
@@ -619,6 +757,7 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
                 if (!(wm <= bound)) break;
                 const float rt = sqrtf(wm) + S.ring;
                 const float lim = fminf(rt * rt, bound);
+              {
                 // my rows of this ring -> cell ranges [aa, aa + na)
                 int aa[CMX_ROWS_PER_LANE], na[CMX_ROWS_PER_LANE];
                 int mytotal = 0;
@@ -638,6 +777,7 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
                         mytotal += na[u];
                     }
                 }
+#endif
                 int incl = mytotal;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -716,6 +856,7 @@ k_tile_search(const GridFrame *__restrict__ fds, int nframes, u64 *__restrict__ 
                         bi = d2.x <= d2.y ? __float_as_int(zw.z) : __float_as_int(zw.w);
                     }
                 }
+              }   // pass (x-limited rings: two passes per ring)
                 const float mine = valid ? fminf(b1 + S.tol_d2, S.search2) : 0.f;
                 bound = fminf(bound, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mine))));
             }
