@@ -871,7 +871,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     // Frames per batch (grid path): enough frames per launch that the small kernels of the sequence fill the GPU and
     // the launch count per frame drops below 2; large systems fill the GPU on their own and their slots are big.
     const size_t natoms_in = h->nv_atoms + (c.autocorrelation ? 0 : h->ns_atoms);
-    int batch = c.batch_frames > 0 ? c.batch_frames : (int)std::min<size_t>(16, std::max<size_t>(1, (size_t)4000000 / std::max<size_t>(natoms_in, 1)));
+    int batch = c.batch_frames > 0 ? c.batch_frames : (int)std::min<size_t>(16, std::max<size_t>(1, (size_t)8000000 / std::max<size_t>(natoms_in, 1)));   // (C4, 930 k atoms in: 8 frames per launch 3882 frames/s, 4: 3759)
     if (const char *e = std::getenv("CMX_BATCH")) { int v = atoi(e); if (v > 0) batch = std::min(v, CMX_MAX_BATCH); }   // experiments only
     if (h->path == 2) batch = 1;
     int nctx = c.n_streams > 0 ? c.n_streams : (h->path == 2 ? (natoms_in > 2000000 ? 4 : 8) : (batch > 1 ? 3 : 4));

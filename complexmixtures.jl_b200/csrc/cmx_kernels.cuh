@@ -524,7 +524,9 @@ struct SearchFrame {
 #endif
 constexpr int kSweepUnroll = CMX_SWEEP_UNROLL;
 #ifndef CMX_TILE_TMA
-#define CMX_TILE_TMA 1                // the next tile's 32 queries arrive by a 1-D bulk async copy (cp.async.bulk + mbarrier) while this tile is searched
+#define CMX_TILE_TMA 0                // 1: the next tile's 32 queries arrive by a 1-D bulk async copy (cp.async.bulk + mbarrier: UBLKCP / SYNCS in the
+                                      // SASS) while this tile is searched.  Measured, C4 / C2 frames/s: off 4018 / 10214, on 3759 / 9902 (kernel alone
+                                      // 112.5 vs 116.1 us per C4 frame): the resident warps already hide the 512-byte load, the lane-0 issue path costs more
 #endif
 #define CMX_SEG_MAX (32 * CMX_ROWS_PER_LANE)
 #define CMX_WARP_SMEM_BASE (CMX_STAGE * 16 + CMX_SEG_MAX * 4 + CMX_STAGE + 16)   // staged atoms, segment table, owner marks, carry

@@ -59,7 +59,7 @@ typedef struct cmx_config {
     int32_t keep_lists;               /* keep per-frame minimum-distance lists for cmx_read_*    */
     int32_t group_lanes;              /* reserved (ignored: the search works on 32-query tiles)  */
     int32_t n_streams;                /* batches in flight on separate compute streams (0 -> auto)             */
-    int32_t batch_frames;             /* frames per kernel launch on the grid path (0 -> auto: 16 for small systems ... 1 above 4 M atoms; <= 32) */
+    int32_t batch_frames;             /* frames per kernel launch on the grid path (0 -> auto: 16 for small systems ... 1 above 4 M atoms per frame; <= 32) */
     double cutoff;                    /* Options.cutoff                                          */
     double dbulk;                     /* Options.dbulk                                           */
     double binstep;                   /* Options.binstep                                         */

@@ -24,6 +24,7 @@ struct CmxConfig
     cutoff::Float64; dbulk::Float64; binstep::Float64; seed::UInt64
     solute_group_offsets::Ptr{Int32}; solute_group_ids::Ptr{Int32}
     solvent_group_offsets::Ptr{Int32}; solvent_group_ids::Ptr{Int32}
+    n_devices::Int32; reserved1::Int32; device_ids::Ptr{Int32}       # several GPUs behind ONE handle (src/parallel_setup.jl:7-57)
 end
 
 mutable struct CmxCounters
@@ -49,23 +50,28 @@ function group_csr(sel::AtomSelection)
 end
 
 """
-    mddf_b200(trajectory, options; frame_weights, coordination_number_only, device=0)
+    mddf_b200(trajectory, options; frame_weights, coordination_number_only, device=0, devices=Int[])
 
 Drop-in for `ComplexMixtures.mddf(trajectory, options; ...)`: same arguments, same `Result`.
+`devices = [0, 1, ..., 7]` puts the whole box behind this ONE call (as the reference's single `mddf` uses every
+thread): frames are dealt to the GPUs in order and their counters are summed on the first one inside `cmx_finish`.
 """
 function mddf_b200(trajectory::Trajectory, options::Options=Options();
-                   frame_weights=Float64[], coordination_number_only=false, low_memory=false, device::Integer=0)
+                   frame_weights=Float64[], coordination_number_only=false, low_memory=false, device::Integer=0,
+                   devices::Vector{<:Integer}=Int[])
     tmeta = TrajectoryMetaData(trajectory, options)
     R = Result(trajectory, options; trajectory_data=tmeta, frame_weights)
     sol, solv = trajectory.solute, trajectory.solvent
     soff, sids = group_csr(sol); voff, vids = group_csr(solv)
-    GC.@preserve soff sids voff vids begin
+    devs = Int32.(devices)
+    GC.@preserve soff sids voff vids devs begin
         cfg = Ref(CmxConfig(sizeof(CmxConfig), device, sol.nmols, sol.natomspermol, solv.nmols, solv.natomspermol,
             R.autocorrelation, tmeta.irefatom, options.usecutoff, options.n_random_samples, coordination_number_only,
             options.lcell, tmeta.n_groups_solute, tmeta.n_groups_solvent, 0, 0, 0, 0, 0, 0,
             options.cutoff, options.dbulk, options.binstep, UInt64(max(options.seed, 0)),
             sol.custom_groups ? pointer(soff) : C_NULL, sol.custom_groups ? pointer(sids) : C_NULL,
-            solv.custom_groups ? pointer(voff) : C_NULL, solv.custom_groups ? pointer(vids) : C_NULL))
+            solv.custom_groups ? pointer(voff) : C_NULL, solv.custom_groups ? pointer(vids) : C_NULL,
+            length(devs) > 1 ? length(devs) : 0, 0, length(devs) > 1 ? pointer(devs) : C_NULL))
         href = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:cmx_create, libcmx), Int32, (Ref{CmxConfig}, Ref{Ptr{Cvoid}}), cfg, href)
         rc == 0 || error(unsafe_string(ccall((:cmx_last_error, libcmx), Cstring, (Ptr{Cvoid},), C_NULL)))

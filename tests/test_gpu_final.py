@@ -167,5 +167,5 @@ def test_device_final_results_match_the_public_result():
         close(fin[k], getattr(R, k), k, atol=1e-9 if k in ("kb", "kb_rdf") else 1e-300)
     close(fin["volume_domain"], R.volume.domain, "volume.domain"); close(fin["density_solvent_bulk"], R.density.solvent_bulk, "density.solvent_bulk")
     got = eng.contributions("solvent", [[0], [3]], "mddf")
-    close(got[0], cm.contributions(R, cm.SolventGroup(atom_indices=[int(tr.solvent.indices[0])]), type="mddf") * tr.solvent.nmols, "SolventGroup first atom type")
+    close(got[0], cm.contributions(R, cm.SolventGroup([int(tr.solvent.indices[0])]), type="mddf") * tr.solvent.nmols, "SolventGroup first atom type")
     eng.close()

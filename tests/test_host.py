@@ -133,13 +133,43 @@ def test_cabi_exports_every_declared_symbol():
     lib.cmx_version.restype = ctypes.c_char_p
     assert b"sm_100a" in lib.cmx_version()
     # struct layouts agree with the header (compiled with the host compiler)
-    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats), sizeof(cmx_dcd_info), sizeof(cmx_xtc_info));}'
+    src = '#include "cmx_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu", sizeof(cmx_config), sizeof(cmx_counters), sizeof(cmx_md), sizeof(cmx_stats), sizeof(cmx_dcd_info), sizeof(cmx_xtc_info), sizeof(cmx_final));}'
     exe = os.path.join("/tmp", f"cmx_sz_{os.getpid()}")
     subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
     os.remove(exe)
     assert sizes == [ctypes.sizeof(engine.CmxConfig), ctypes.sizeof(engine.CmxCounters), engine.MD_DTYPE.itemsize, ctypes.sizeof(engine.CmxStats),
-                     ctypes.sizeof(engine.CmxDcdInfo), ctypes.sizeof(engine.CmxXtcInfo)]
+                     ctypes.sizeof(engine.CmxDcdInfo), ctypes.sizeof(engine.CmxXtcInfo), ctypes.sizeof(engine.CmxFinal)]
+
+
+def test_julia_shim_struct_layouts_match_the_abi():
+    """julia/CMXB200.jl cannot be executed here (no Julia): its `struct` mirrors are parsed instead and their C layout
+    (field order, names, sizes, natural alignment) compared with the ctypes mirrors, which are checked against the header
+    by the test above."""
+    from cmx_b200 import engine
+    jl = open(os.path.join(ROOT, "julia", "CMXB200.jl")).read()
+    size_of = {"Int32": 4, "UInt32": 4, "Int64": 8, "UInt64": 8, "Float64": 8, "Float32": 4}
+
+    def layout(name):
+        body = re.search(r"struct " + name + r"\n(.*?)\nend", jl, re.S).group(1)
+        fields = []
+        for line in body.splitlines():
+            line = line.split("#")[0]
+            for m in re.finditer(r"(\w+)::([\w{}]+)", line):
+                fields.append((m.group(1), 8 if m.group(2).startswith("Ptr") else size_of[m.group(2)]))
+        off, out = 0, []
+        for fname, sz in fields:
+            off = (off + sz - 1) // sz * sz
+            out.append((fname, off, sz))
+            off += sz
+        return out, (off + 7) // 8 * 8
+
+    for jname, cstruct in (("CmxConfig", engine.CmxConfig), ("CmxCounters", engine.CmxCounters), ("CmxFinal", engine.CmxFinal)):
+        fields, total = layout(jname)
+        assert total == ctypes.sizeof(cstruct), jname
+        assert [f[0] for f in fields] == [f[0] for f in cstruct._fields_], jname
+        for (fname, off, sz), (cname, ctype) in zip(fields, cstruct._fields_):
+            assert off == getattr(cstruct, cname).offset and sz == ctypes.sizeof(ctype), (jname, fname)
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_oracle():
