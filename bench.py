@@ -517,20 +517,24 @@ def job_leg(args, b):
     fps = b.fps
     lib, h = eng.lib, eng.h
     ps, pv = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
-    nfill = 32 if b.xv[0].nbytes > 4e6 else 96   # the first acquisitions fill the ring's slots (host memcpy, as a reader would);
-    for k in range(mine):                        # later ones re-send the bytes a slot already holds: no file I/O in this leg
-        if k < nfill:
-            a_s, a_v = eng.acquire()
-            a_v[...] = b.xv[k % fps]
+    done = 0
+    seen = set()                                 # a slot of the ring is filled the first time it is handed out (host memcpy, as a
+    for k in range(mine):                        # reader would); later acquisitions re-send the bytes it already holds: no file I/O in this leg
+        rc = lib.cmx_acquire_frame_buffer(h, C.byref(ps), C.byref(pv))
+        if rc:
+            raise RuntimeError(lib.cmx_last_error(h).decode())
+        addr = C.cast(pv, C.c_void_p).value
+        if addr not in seen:
+            seen.add(addr)
+            C.memmove(pv, b.xv[k % fps].ctypes.data, b.xv[k % fps].nbytes)
             if not w["auto"]:
-                a_s[...] = b.xs[k % fps]
-        else:
-            rc = lib.cmx_acquire_frame_buffer(h, C.byref(ps), C.byref(pv))
-            if rc:
-                raise RuntimeError(lib.cmx_last_error(h).decode())
+                C.memmove(ps, b.xs[k % fps].ctypes.data, b.xs[k % fps].nbytes)
         rc = lib.cmx_submit_frame(h, 1 + b.rank + world * k, 1.0, b.cellp)
         if rc:
             raise RuntimeError(lib.cmx_last_error(h).decode())
+        done = k + 1
+        if (k & 63) == 63 and time.perf_counter() - t0 > 120.0:      # never lets a sick run hold the ranks' collectives hostage
+            break
     eng.sync()
     t_feed = time.perf_counter() - t0
     if world > 1:
@@ -552,6 +556,9 @@ def job_leg(args, b):
     t_destroy = time.perf_counter() - t1
     b.barrier()
     (wall,) = b.max_over_ranks(time.perf_counter() - t0)
+    (done_all,) = b.max_over_ranks(float(mine - done))
+    if done_all > 0:     # a rank stopped early (120 s guard): the leg is reported as truncated, not as a throughput
+        return {"frames": total, "frames_per_rank": mine, "truncated_after_s": wall, "frames_per_s": None, "md_count_sum": hits}
     return {"frames": total, "frames_per_rank": mine, "wall_s": wall, "frames_per_s": total / wall, "create_s": t_create,
             "feed_s": t_feed - t_create, "allreduce_finish_s": t_finish - t_feed, "destroy_s": t_destroy, "md_count_sum": hits,
             "what": "whole trajectory, strong scaling: create -> acquire/submit from pinned host frames -> sync -> all-reduce -> finish -> destroy, wall clock"}

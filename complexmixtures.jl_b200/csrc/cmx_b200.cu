@@ -871,7 +871,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     // Frames per batch (grid path): enough frames per launch that the small kernels of the sequence fill the GPU and
     // the launch count per frame drops below 2; large systems fill the GPU on their own and their slots are big.
     const size_t natoms_in = h->nv_atoms + (c.autocorrelation ? 0 : h->ns_atoms);
-    int batch = c.batch_frames > 0 ? c.batch_frames : (int)std::min<size_t>(16, std::max<size_t>(1, (size_t)8000000 / std::max<size_t>(natoms_in, 1)));   // (C4, 930 k atoms in: 8 frames per launch 3882 frames/s, 4: 3759)
+    int batch = c.batch_frames > 0 ? c.batch_frames : (int)std::min<size_t>(16, std::max<size_t>(1, (size_t)4000000 / std::max<size_t>(natoms_in, 1)));   // (C4, 930 k atoms in: 4 frames per launch; 8 gave +3 % frames/s for twice the scratch and staging ring)
     if (const char *e = std::getenv("CMX_BATCH")) { int v = atoi(e); if (v > 0) batch = std::min(v, CMX_MAX_BATCH); }   // experiments only
     if (h->path == 2) batch = 1;
     int nctx = c.n_streams > 0 ? c.n_streams : (h->path == 2 ? (natoms_in > 2000000 ? 4 : 8) : (batch > 1 ? 3 : 4));
@@ -1126,8 +1126,10 @@ int32_t cmx_counters_device(cmx_handle *h, void **device_ptr, int64_t *n_uint64)
     return CMX_OK;
 }
 
-static int emit_counters(cmx_handle *h) {
-    size_t n = h->cnt_len, nb = h->nbins;
+// f64 image of the counters with the frame weights applied; head_only: just md / md_random / rdf / rdf_random (what
+// a caller that leaves the group arrays on the device asks for -- C5 per-atom: 24 kB instead of 12 GB)
+static int emit_counters(cmx_handle *h, bool head_only = false) {
+    size_t n = head_only ? 4 * (size_t)h->nbins : h->cnt_len, nb = h->nbins;
     const double w = h->have_weight ? h->w0 : 1.0;
     const size_t gs = nb * h->cfg.n_groups_solute;
     size_t lo = 4 * nb, hi = 4 * nb + 2 * gs;
@@ -1163,7 +1165,8 @@ int32_t cmx_finish(cmx_handle *h, cmx_counters *out) {
     int rc = cmx_sync(h); if (rc) return rc;
     size_t nb = h->nbins;
     const size_t gs = nb * h->cfg.n_groups_solute, gv = nb * h->cfg.n_groups_solvent;
-    if (!h->emit_valid) { rc = emit_counters(h); if (rc) return rc; }
+    const bool head_only = !out->solute_group_count && !out->solute_group_count_random && !out->solvent_group_count && !out->solvent_group_count_random;
+    if (!h->emit_valid) { rc = emit_counters(h, head_only); if (rc) return rc; }
     auto emit = [&](double *dst, size_t off, size_t len) -> cudaError_t {
         if (!dst || !len) return cudaSuccess;
         return cudaMemcpy(dst, h->d_emit.p + off, sizeof(double) * len, cudaMemcpyDeviceToHost);

@@ -100,8 +100,8 @@ def allreduce_counters(eng: Engine, my_weights) -> tuple:
 def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[AtomSelection] = None,
          options: Optional[Options] = None, *, trajectory_format: str = "", frame_weights=(),
          coordination_number_only: bool = False, low_memory: bool = False, device: Optional[int] = None,
-         devices=None, path: int = 0, feed: str = "auto", reader_threads: int = 0, _engine_kw: Optional[dict] = None,
-         _engine_cache: Optional[dict] = None, distributed: Optional[bool] = None) -> Result:
+         devices=None, path: int = 0, feed: str = "auto", reader_threads: int = 0, group_arrays: bool = True,
+         _engine_kw: Optional[dict] = None, _engine_cache: Optional[dict] = None, distributed: Optional[bool] = None) -> Result:
     """mddf(trajectory_file, solute, solvent, options; ...) or mddf(trajectory, options; ...).
 
     ``low_memory`` is accepted for compatibility and is a no-op: the device keeps ONE set of
@@ -111,6 +111,12 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
     uses the whole machine, src/parallel_setup.jl): frames are dealt to the devices in order and the per-device
     counters are summed on the first device inside ``cmx_finish``.  Under ``torchrun`` (one process per GPU) leave it
     unset: the ranks share the frames and sum with one all-reduce.
+
+    ``group_arrays=False``: the group-count arrays (per atom / per custom group x nbins: 12 GB for a 5 M-atom system with
+    per-atom contributions) STAY on the device.  The Result carries the O(nbins) vectors as usual and ``R.device``, a
+    :class:`DeviceResult` whose ``contributions(side, groups, type)`` / ``reduce_groups`` / ``final_results`` evaluate
+    ``contributions(R, group; type)`` (src/tools/contributions.jl:70-248) for any number of groups on the accumulators in
+    HBM; call ``R.device.close()`` when done.
 
     ``feed``: "native" = the library's own DCD / XTC feed (``cmx_run_dcd`` / ``cmx_run_xtc``: reader threads -> pinned ring ->
     raw frame H2D -> device gather of the selections; the frames of this rank are read by offset, the
@@ -181,18 +187,44 @@ def mddf(trajectory, solute: Optional[AtomSelection] = None, solvent: Optional[A
             trajectory.close()
     if world > 1:
         vol, sw = allreduce_counters(eng, [wt for _, wt in shard(todo, rank, world)])
-        c = eng.finish()                      # ONE read-back of the (summed) counters
+        c = eng.finish(groups=group_arrays)   # ONE read-back of the (summed) counters
         c["volume_total"], c["sum_weights"] = vol, sw
     else:
-        c = eng.finish()
+        c = eng.finish(groups=group_arrays)
     R.engine_stats = eng.stats()
-    if _engine_cache is None:
-        eng.close()
-    for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random", "solute_group_count",
-              "solute_group_count_random", "solvent_group_count", "solvent_group_count_random"):
+    for k in ("md_count", "md_count_random", "rdf_count", "rdf_count_random"):
         setattr(R, k, c[k])
+    for k in ("solute_group_count", "solute_group_count_random", "solvent_group_count", "solvent_group_count_random"):
+        setattr(R, k, c[k] if group_arrays else np.zeros((0, R.nbins)))
     R.volume.total = c["volume_total"]
+    if not group_arrays:
+        R.device = DeviceResult(eng, c["sum_weights"], c["volume_total"], owns=_engine_cache is None)
+    elif _engine_cache is None:
+        eng.close()
     return finalresults(R, options, coordination_number_only=coordination_number_only)
+
+
+class DeviceResult:
+    """The accumulators of a finished run, still in HBM (``mddf(..., group_arrays=False)``): the post-processing calls of
+    the reference that read the group arrays, evaluated on the device for many groups at once."""
+
+    def __init__(self, eng: Engine, sum_weights: float, volume_sum: float, owns: bool = True):
+        self.engine, self.sum_weights, self.volume_sum, self._owns = eng, float(sum_weights), float(volume_sum), owns
+
+    def contributions(self, side: str, groups, type: str = "mddf") -> np.ndarray:
+        """[n_groups, nbins]: ``contributions(R, SoluteGroup|SolventGroup(rows); type)`` for every group of 0-based rows"""
+        return self.engine.contributions(side, groups, type, self.sum_weights, self.volume_sum)
+
+    def reduce_groups(self, which: str, groups) -> np.ndarray:
+        return self.engine.reduce_groups(which, groups)
+
+    def final_results(self) -> dict:
+        return self.engine.final_results(self.sum_weights, self.volume_sum)
+
+    def close(self):
+        if self._owns and self.engine is not None:
+            self.engine.close()
+        self.engine = None
 
 
 def coordination_number(trajectory, solute=None, solvent=None, options=None, **kw) -> Result:

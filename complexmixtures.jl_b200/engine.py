@@ -295,9 +295,9 @@ class Engine:
             raise CmxError(rc, self.lib.cmx_last_error(self.h).decode())
 
     def close(self):
-        if getattr(self, "_pinned", None):
-            self.lib.cmx_free_pinned(self._pinned)
-            self._pinned, self._out = None, None
+        for blk in getattr(self, "_pinned_blocks", []):
+            self.lib.cmx_free_pinned(blk)
+        self._pinned_blocks, self._out, self._out_head = [], None, None
         if getattr(self, "h", None) is not None and self.h:
             self.lib.cmx_destroy(self.h)
             self.h = None
@@ -421,31 +421,36 @@ class Engine:
         self._ck(self.lib.cmx_counters_device_f64(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def _result_arrays(self):
-        """Result arrays in page-locked memory, allocated once per engine."""
-        if getattr(self, "_out", None) is None:
+    def _result_arrays(self, groups: bool = True):
+        """Result arrays in page-locked memory, allocated once per engine (the group arrays only when asked for)."""
+        key = "_out" if groups else "_out_head"
+        if getattr(self, key, None) is None:
             nb, gs, gv = self.nbins, self.cfg.n_groups_solute, self.cfg.n_groups_solvent
-            shapes = dict(md_count=(nb,), md_count_random=(nb,), rdf_count=(nb,), rdf_count_random=(nb,),
-                          solute_group_count=(gs, nb), solute_group_count_random=(gs, nb),
-                          solvent_group_count=(gv, nb), solvent_group_count_random=(gv, nb))
+            shapes = dict(md_count=(nb,), md_count_random=(nb,), rdf_count=(nb,), rdf_count_random=(nb,))
+            if groups:
+                shapes.update(solute_group_count=(gs, nb), solute_group_count_random=(gs, nb),
+                              solvent_group_count=(gv, nb), solvent_group_count_random=(gv, nb))
             total = sum(int(np.prod(sh)) for sh in shapes.values())
             p = C.c_void_p()
             if self.lib.cmx_alloc_pinned(C.byref(p), total * 8):
                 raise CmxError(2, "cudaHostAlloc failed")
-            self._pinned = p
+            self._pinned_blocks = getattr(self, "_pinned_blocks", []) + [p]
             flat = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(total,))
-            self._out, off = {}, 0
+            out, off = {}, 0
             for k, sh in shapes.items():
                 n = int(np.prod(sh))
-                self._out[k] = flat[off:off + n].reshape(sh)
+                out[k] = flat[off:off + n].reshape(sh)
                 off += n
-        return self._out
+            setattr(self, key, out)
+        return getattr(self, key)
 
-    def finish(self, copy: bool = True) -> dict:
+    def finish(self, copy: bool = True, groups: bool = True) -> dict:
         """cmx_finish: sync, (all-reduced) counters -> f64 arrays laid out like Result.  With
         copy=False the returned arrays are views of the engine's pinned buffers (valid until the
-        next finish/close)."""
-        out = self._result_arrays()
+        next finish/close).  groups=False leaves the group arrays on the device (NULL members of cmx_counters):
+        only md_count / rdf_count (+ random) come back -- for per-atom arrays of GBs, followed by
+        ``contributions`` / ``reduce_groups`` / ``final_results`` on the device."""
+        out = self._result_arrays(groups)
         c = CmxCounters()
         for k, v in out.items():
             setattr(c, k, v.ctypes.data)

@@ -169,3 +169,28 @@ def test_device_final_results_match_the_public_result():
     got = eng.contributions("solvent", [[0], [3]], "mddf")
     close(got[0], cm.contributions(R, cm.SolventGroup([int(tr.solvent.indices[0])]), type="mddf") * tr.solvent.nmols, "SolventGroup first atom type")
     eng.close()
+
+
+def test_group_arrays_left_on_the_device():
+    """mddf(..., group_arrays=False): the O(nbins) Result is the same, the group arrays never travel, and R.device
+    evaluates contributions() on the device == the host contributions() of the full Result."""
+    d = namd()
+    mk = lambda: cm.ArrayTrajectory(np.concatenate([d["protein"], d["tmao"]], axis=1), d["cells"],
+                                    cm.AtomSelection(np.arange(1, 1464), nmols=1), cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14))
+    o = opts(bulk_range=(8.0, 10.0), n_random_samples=4)
+    Rfull = cm.mddf(mk(), o, frame_weights=[1.0, 2.0, 0.5])
+    R = cm.mddf(mk(), o, frame_weights=[1.0, 2.0, 0.5], group_arrays=False)
+    assert R.solute_group_count.shape == (0, R.nbins) and R.solvent_group_count_random.shape == (0, R.nbins)
+    for k in ("md_count", "md_count_random", "coordination_number", "mddf", "kb", "rdf", "kb_rdf"):
+        assert np.array_equal(getattr(R, k), getattr(Rfull, k)), k
+    residues = [list(range(a, min(a + 16, 1463))) for a in range(0, 1463, 16)]
+    for type in ("mddf", "coordination_number", "md_count"):
+        got = R.device.contributions("solute", residues, type)
+        want = np.stack([cm.contributions(Rfull, cm.SoluteGroup([r + 1 for r in res]), type=type) for res in residues])
+        close(got, want, f"residue {type}")
+    got = R.device.contributions("solute", residues[:5], "kbi")
+    want = np.stack([cm.contributions(Rfull, cm.SoluteGroup([r + 1 for r in res]), type="kbi") for res in residues[:5]])
+    close(got, want, "residue kbi", atol=1e-9)
+    fin = R.device.final_results()
+    close(fin["mddf"], Rfull.mddf, "mddf")
+    R.device.close()
