@@ -418,6 +418,25 @@ class Bench:
                 "step": f"{nfe} frames from pinned host memory (the share of one GPU of 8 of the {self.w['traj_frames']}-frame trajectory; "
                         f"{self.fps} distinct frames cycled), one all-reduce and one cmx_finish (D2H of all counters) per step"}
 
+    def measure_h2d_ceiling(self, in_bytes_per_frame):
+        """What the host side allows: every rank copies pinned host memory to its GPU AT THE SAME TIME (the traffic
+        pattern of the e2e leg without any kernel) -- aggregate GB/s and the frames/s ceiling it puts on `e2e`."""
+        torch = self.torch
+        n = 256 << 20
+        src = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dst = torch.empty(n, dtype=torch.uint8, device=f"cuda:{self.local_rank}")
+        reps = 8
+        dst.copy_(src, non_blocking=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        self.barrier()
+        (dt,) = self.max_over_ranks(time.perf_counter() - t0)
+        agg = reps * n * self.world / dt / 1e9
+        return {"aggregate_GBps": agg, "per_gpu_GBps": agg / self.world, "frames_per_s_ceiling": agg * 1e9 / in_bytes_per_frame,
+                "what": f"{self.world} rank(s) copying 8 x 256 MiB of pinned host memory to their GPUs simultaneously, wall clock, max over ranks"}
+
     def measure_roofline(self, value):
         eng, w, fps = self.eng, self.w, self.fps
         eng.reset(); eng.set_option("active_streams", 1); eng.set_option("profile", 1)   # one batch at a time: clean per-kernel times
@@ -589,6 +608,8 @@ def main():
     w, fps = b.w, b.fps
     v = b.measure_value(args.steps, args.warmup)
     e2e = None if args.no_e2e else b.measure_e2e(max(2, min(args.steps, 5)), args.warmup)
+    if e2e is not None:
+        e2e["h2d_ceiling"] = b.measure_h2d_ceiling(e2e["h2d_bytes_per_step"] / e2e["frames_per_step"])
     guard = b.guard_multi_gpu() if world > 1 else None
     roof = b.measure_roofline(v["value"]) if rank == 0 else None
     if world > 1:
