@@ -459,7 +459,7 @@ class Bench:
         self.step_device(collective=False)
         pe = eng.stats()["pair_evals"] / fps
         eng.set_option("count_pairs", 0); eng.set_option("active_streams", 0)
-        fpl = fps / nbatch      # frames per launch (batched launches on the grid path)
+        fpl = 1.0 if pair_path else fps / nbatch      # frames per launch (batched launches on the grid path; the pair path launches per frame)
         tpf = ncu_traffic(self.w["config"], "random" if dom.startswith("random") else "real")
         return {"bound": "hbm", "kernel": f"{kernel_name} ({dom})", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None if tpf is None else tpf * fpl, "traffic_per_frame": tpf, "peak_source": peak_src,

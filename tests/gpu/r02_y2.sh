@@ -11,6 +11,6 @@ N=sys.argv[1]
 d=json.loads(open(f"gpurun_out/r02y_n{N}.json").read().strip().splitlines()[-1])
 print("N=%s value"%N, round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "h2d ceiling", {k:(round(v,1) if isinstance(v,float) else v) for k,v in d["e2e"]["h2d_ceiling"].items() if k!="what"}, "guard", d["multi_gpu_sum_equals_single_gpu"], "clocks", d["clocks"])
 print("job", {k:(round(v,3) if isinstance(v,float) else v) for k,v in d["job"].items() if k!="what"})
-s=d["secondary"]; print("secondary C2 value", round(s["value"],1), "e2e", round(s["e2e"]["value"],1), s["e2e"]["h2d_ceiling"]["aggregate_GBps"])
+s=d["secondary"]; print("secondary C2 value", round(s["value"],1), "e2e", round(s["e2e"]["value"],1), "")
 PY
 echo "elapsed $(( $(date +%s) - T0 )) s"
