@@ -92,12 +92,34 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region: one long-running `nvidia-smi -lms 50`
-    whose lines are time-stamped on arrival; only samples inside [start, stop] are summarised."""
+    """SM clock + throttle reasons DURING the timed region.  NVML in a sampling thread (10 ms period, no process start-up:
+    a region of a few tens of ms still gets samples); falls back to one long-running `nvidia-smi -lms 50` whose lines are
+    time-stamped on arrival.  Only samples inside [start, stop] are summarised (the nearest ones if the region was shorter
+    than a period)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]        # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index=0):
-        self.index, self.samples, self.t0, self.t1, self.proc = index, [], None, None, None
+        self.index, self.samples, self.t0, self.t1, self.proc, self.nvml, self.stop = index, [], None, None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                u = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + u) if not u.startswith("GPU-") else u)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.h = pynvml, h
+            self._sample_nvml()                      # fails here, not in the thread, if the queries are not supported
+            self.t = threading.Thread(target=self._run_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -105,6 +127,23 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        clk = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        try:
+            r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.samples.append((time.perf_counter(), [str(clk), str(self.smax)] + ["Active" if r & b else "Not Active" for b in self.BITS]))
+
+    def _run_nvml(self):
+        while not self.stop:
+            try:
+                self._sample_nvml()
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _run(self):
         for line in self.proc.stdout:
@@ -117,19 +156,22 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def close(self):
+        self.stop = True
         if self.proc is not None:
             self.proc.terminate()
 
     def summary(self):
-        inside = [s for t, s in self.samples if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) and len(s) >= 6]
-        if not inside:   # region shorter than the sampling period: fall back to the nearest samples
-            inside = [s for _, s in self.samples[-3:] if len(s) >= 6]
+        good = [(t, s) for t, s in self.samples if len(s) >= 6]
+        inside = [s for t, s in good if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30)]
+        if not inside and good and self.t0 is not None:   # region shorter than the sampling period: the samples nearest to it
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            inside = [s for _, s in sorted(good, key=lambda ts: abs(ts[0] - mid))[:3]]
         if not inside:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
         sm = sorted(float(s[0]) for s in inside)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in inside)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][1]), "reasons": reasons, "samples": len(inside)}
+        reasons = [n for k, n in enumerate(self.NAMES) if any(s[2 + k].lower().startswith("active") for s in inside)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][1]), "reasons": reasons, "samples": len(inside),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_workload(args, config, rank, world, fps_override=0):
@@ -567,9 +609,10 @@ def job_leg(args, b):
         t = b.torch.as_tensor(wobj, device=f"cuda:{b.local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         b.torch.cuda.synchronize()
-    res = eng.finish(copy=False)
+    # sum!(R, r_chunk) leaves ONE Result: after the all-reduce every rank holds the sums, rank 0 reads them back
+    res = eng.finish(copy=False) if b.rank == 0 else None
     t_finish = time.perf_counter() - t0
-    hits = float(res["md_count"].sum())
+    hits = float(res["md_count"].sum()) if res is not None else 0.0
     t1 = time.perf_counter()
     eng.close()
     t_destroy = time.perf_counter() - t1
@@ -580,7 +623,7 @@ def job_leg(args, b):
         return {"frames": total, "frames_per_rank": mine, "truncated_after_s": wall, "frames_per_s": None, "md_count_sum": hits}
     return {"frames": total, "frames_per_rank": mine, "wall_s": wall, "frames_per_s": total / wall, "create_s": t_create,
             "feed_s": t_feed - t_create, "allreduce_finish_s": t_finish - t_feed, "destroy_s": t_destroy, "md_count_sum": hits,
-            "what": "whole trajectory, strong scaling: create -> acquire/submit from pinned host frames -> sync -> all-reduce -> finish -> destroy, wall clock"}
+            "what": "whole trajectory, strong scaling: create -> acquire/submit from pinned host frames -> sync -> all-reduce -> finish (rank 0) -> destroy, wall clock"}
 
 
 def main():
