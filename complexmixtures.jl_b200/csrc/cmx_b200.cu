@@ -159,7 +159,7 @@ struct cmx_handle {
     size_t ns_atoms = 0, nv_atoms = 0, in_floats = 0;
     double cut_eff = 0;
     int Kdiv = 2;
-    double side = 0, sidex = 0, cside = 0, qside = 0, ring_width = 3.5;   // (ring: measured with the x-limited rings, C4 / C2 frames/s: 2.5 A 3813 / 9567, 3.5 A 4020 / 10212)
+    double side = 0, sidex = 0, cside = 0, qside = 0, ring_width = 4.5;   // (ring: measured with the x-limited rings in the random phase, C4 / C2 frames/s: 2.5 A 3813 / 9567, 3.5 A 4040 / 10618, 4.5 A 4133 / 10815, 5.5 A worse)
     cudaStream_t s_copy = nullptr;
     size_t hist_smem = 0;           // bytes of the shared-memory histograms (HistPriv) of the counting kernels
     int batch = 1;                  // frames per batch (grid path); 1 on the molecule-pair path
