@@ -715,3 +715,40 @@ def test_xtc_compressed_feed(tmp_path):
     dev2 = p.run_engine(eng2); eng2.close()
     for key in dev:
         assert np.array_equal(dev[key], dev2[key]), key
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_geometries_against_the_oracle(seed):
+    """Randomised systems (the search takes every branch of its ring / span bookkeeping somewhere): random orthorhombic or
+    triclinic cell, solute blob anywhere in it -- across faces, shifted by whole cell vectors --, solute density from
+    sparse to packed, solvent of 1 / 3 / 5 atoms per molecule with unwrapped coordinates, random cutoffs, several frames
+    per batch.  Counters bit-exact against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    L = rng.uniform(38.0, 64.0, size=3)
+    cell = np.diag(L)
+    if seed % 2:
+        cell[0, 1], cell[0, 2], cell[1, 2] = rng.uniform(-0.2, 0.2, size=3) * L[[0, 0, 1]]      # columns = lattice vectors
+    ib, ic = int(rng.integers(8, 16)), int(rng.integers(2, 8))
+    dbulk, cutoff = 0.5 * ib, 0.5 * (ib + ic)               # multiples of 0.5 A (cutoff must be a multiple of binstep = 0.02)
+    ns = int(rng.integers(1, 900))
+    napm = int(rng.choice([1, 3, 5]))
+    nmol = int(rng.integers(50, 1500))
+    spread = float(rng.uniform(2.0, 12.0))
+    tmpl = rng.normal(scale=0.9, size=(napm, 3))
+    frames_s, frames_v = [], []
+    for f in range(3):
+        centre = cell @ rng.uniform(0.0, 1.0, size=3)
+        xs = centre + rng.normal(scale=spread, size=(ns, 3)) + cell @ rng.integers(-2, 3, size=3)
+        com = (cell @ rng.uniform(0.0, 1.0, size=(3, nmol))).T + (cell @ rng.integers(-1, 2, size=(3, nmol))).T
+        q = rng.normal(size=(nmol, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+        w, x, y, z = q.T
+        R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                      np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                      np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
+        xv = (com[:, None, :] + np.einsum("mij,aj->mai", R, tmpl)).reshape(-1, 3)
+        frames_s.append(xs.astype(np.float32)); frames_v.append(xv.astype(np.float32))
+    sol = cm.AtomSelection(np.arange(1, ns + 1), nmols=1)
+    solv = cm.AtomSelection(np.arange(ns + 1, ns + 1 + nmol * napm), natomspermol=napm)
+    p = Problem(sol, solv, opts(bulk_range=(dbulk, cutoff), n_random_samples=int(rng.integers(1, 5))), frames_s, frames_v, cell)
+    dev, o, stats = check(p, lists=False, engine_kw=dict(batch_frames=int(rng.choice([1, 2, 3])), n_streams=int(rng.choice([1, 2]))))
+    assert stats["frames"] == 3
