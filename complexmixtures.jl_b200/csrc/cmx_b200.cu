@@ -960,7 +960,6 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
     size_t nvm = c.solvent_nmols, nrand = (size_t)P.nrand;
     // random phase in chunks of samples: at most ~48 M query atoms of scratch per frame context
     h->sample_chunk = (int)std::max<size_t>(1, std::min<size_t>(std::max<size_t>(nrand, 1), (size_t)(48.0e6 / (double)h->nv_atoms)));
-    const size_t nchunk = (size_t)h->sample_chunk;
     phase("group maps, counters");
     CK(h->d_stats.ensure(8, true));
     P.cnt_base = h->d_cnt.p; P.acc = nullptr; P.w = 1.0;

@@ -340,7 +340,6 @@ size_t xtc_skeleton(const unsigned char *block, size_t avail, int natoms, unsign
     H.rec_off = (uint32_t)sizeof(XtcDevHeader);
     XtcGroup *rec = reinterpret_cast<XtcGroup *>(slot + H.rec_off);
     const size_t max_groups = (slot_bytes - sizeof(XtcDevHeader) - (size_t)H.nbytes - 32) / sizeof(XtcGroup);
-    XtcBits br{block + 36, H.nbytes};
     const unsigned char *stream = block + 36;
     uint64_t pos = 0;
     int i = 0, run = 0, ng = 0;
