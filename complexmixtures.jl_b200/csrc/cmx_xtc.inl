@@ -348,7 +348,6 @@ size_t xtc_skeleton(const unsigned char *block, size_t avail, int natoms, unsign
         for (int k = 0; k < 8; ++k) acc = (acc << 8) | (b0 + (size_t)k < (size_t)H.nbytes ? stream[b0 + k] : 0);
         return (uint32_t)((acc >> (64 - (int)(at & 7) - nbits)) & ((1ull << nbits) - 1ull));
     };
-    (void)br;
     while (i < natoms) {
         if ((size_t)ng >= max_groups) return 0;
         XtcGroup G{};
