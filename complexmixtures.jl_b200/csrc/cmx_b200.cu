@@ -4,7 +4,6 @@
 // per-handle state (build_particle_system / Buffer / Result -> cmx_create), frame staging
 // (pinned ring, async H2D), per-frame kernel sequence (mddf_frame!, src/mddf.jl:361-429),
 // frame-weight handling and the final counters (sum!, src/results.jl:629-649).
-#include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -133,14 +132,13 @@ struct FrameCtx {
     // molecule-pair path (one frame per context at a time) and shared odds and ends
     DevBuf<MdRec> d_list;
     DevBuf<int> d_scalars;                          // [8] sticky overflow flag of the pair path
-    DevBuf<unsigned char> d_cub_tmp;
     PairScratch pairs;
     int *h_scalars = nullptr;                       // pinned mirror (rmax feedback)
     void release() {
         slots.clear();
         if (arena) cudaFree(arena);
         arena = nullptr; arena_bytes = 0;
-        d_list.release(); d_scalars.release(); d_cub_tmp.release();
+        d_list.release(); d_scalars.release();
         if (h_fd) cudaFreeHost(h_fd);
         if (d_fd) cudaFree(d_fd);
         if (h_scalars) cudaFreeHost(h_scalars);
@@ -985,10 +983,6 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         } else {
             CK(x_->d_list.ensure(nvm));
             int rc = pairs_create(h); if (rc) return rc;
-            // cub temp storage of the anchor-cell scan
-            size_t t1 = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, t1, (int *)nullptr, (int *)nullptr, 1 << 20);
-            CK(x_->d_cub_tmp.ensure(t1 + 1024));
         }
     }
     h->cur = h->ctx[0];

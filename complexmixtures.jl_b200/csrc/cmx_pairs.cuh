@@ -17,7 +17,6 @@
 // its bulk molecules are compacted in ascending order (src/mddf.jl:406-415) and the random
 // placements are generated and measured on the fly (src/mddf.jl:65-88).
 #pragma once
-#include <cub/block/block_scan.cuh>
 
 #include "cmx_device.cuh"
 
@@ -408,11 +407,43 @@ __global__ void k_ref_lists(Geom g, PairGeom pg, Prob P, uint32_t frame, int fix
     if (b < P.nv_mols) lists[(size_t)s * P.nv_mols + b] = e;
 }
 
+// block-wide exclusive prefix sum of one int per thread (blockDim.x = THREADS, a multiple of 32): position of the thread's
+// value and the block total.  warp_sums: THREADS / 32 ints of shared memory, free to reuse after the call returns.
+template <int THREADS>
+__device__ __forceinline__ void block_exclusive_sum(int v, int &pos, int &total, int *warp_sums) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                                   // (warp_sums of a previous call are no longer read)
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < THREADS / 32; ++k) { const int sk = warp_sums[k]; before += k < w ? sk : 0; all += sk; }
+    pos = before + incl - v; total = all;
+}
+
+// exclusive prefix sum of the anchor-cell counts (n = cells + 1, a few hundred to a few thousand entries): ONE block walks
+// the array in chunks of 1024 -- the pair path has no library kernel either
+__global__ void __launch_bounds__(1024)
+k_scan_block(const int *__restrict__ in, int *__restrict__ out, int n) {
+    __shared__ int warp_sums[32];
+    int carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? in[i] : 0;
+        int pos, total;
+        block_exclusive_sum<1024>(v, pos, total, warp_sums);
+        if (i < n) out[i] = carry + pos;
+        carry += total;
+    }
+}
+
 // ordered compaction of the bulk molecules of each sample's list (one block per sample)
 __global__ void __launch_bounds__(512)
 k_bulk_compact(Prob P, uint32_t frame, int s0, const MdRec *__restrict__ lists, int *__restrict__ bulk_idx, int *__restrict__ n_bulk) {
-    typedef cub::BlockScan<int, 512> Scan;
-    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int warp_sums[16];
     __shared__ int base_sh;
     int s = blockIdx.x;                      // sample within the chunk
     int a = ref_solute_of_sample(P, frame, (uint32_t)(s0 + s));
@@ -423,7 +454,7 @@ k_bulk_compact(Prob P, uint32_t frame, int s0, const MdRec *__restrict__ lists, 
         int f = 0;
         if (m < P.nv_mols && !(P.autocorr && m == a)) f = inbulk(P, lists[(size_t)s * P.nv_mols + m]) ? 1 : 0;
         int pos, total;
-        Scan(tmp).ExclusiveSum(f, pos, total);
+        block_exclusive_sum<512>(f, pos, total, warp_sums);
         int base = base_sh;
         if (f) bulk_idx[(size_t)s * P.nv_mols + base + pos] = m;
         __syncthreads();

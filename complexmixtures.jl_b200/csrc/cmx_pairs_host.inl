@@ -112,9 +112,7 @@ int frame_pair_path(cmx_handle *h, const float *d_solute, const float *d_solvent
     int nvm = c.solvent_nmols;
     launch(h, k_anchor_bin<false>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)nullptr,
            (int *)nullptr, (double *)nullptr, (float *)nullptr, (float4 *)nullptr);
-    size_t tmp_bytes = h->cur->d_cub_tmp.n;
-    CK(cub::DeviceScan::ExclusiveSum(h->cur->d_cub_tmp.p, tmp_bytes, S.cell_count, S.cell_start, (int)(ncells + 1), h->cur->stream));
-    h->stats.kernel_launches += 2;
+    launch(h, k_scan_block, dim3(1), dim3(1024), (const int *)S.cell_count, S.cell_start, (int)(ncells + 1));
     launch(h, k_anchor_bin<true>, dim3((nvm + 127) / 128), dim3(128), g, pg, S.solv, nvm, S.cell_count, (const int *)S.cell_start,
            S.sorted_id, S.s_anchor, S.s_rad, S.s_anchor4);
     size_t smem = sizeof(float4) * CMX_PAIR_WARPS * c.solute_natomspermol + sizeof(int) * CMX_PAIR_WARPS * 64;

@@ -8,7 +8,8 @@
  *   ./mddf_dcd trajectory.dcd 1 1463 1479 2534 14      (protein x TMAO of the reference's NAMD example, 1-based)
  *
  * This is the call sequence a ComplexMixtures.jl maintainer makes through ccall (julia/CMXB200.jl): cmx_create,
- * cmx_run_dcd, cmx_finish; normalisation (finalresults!, src/results.jl:320-428) stays with the host.
+ * cmx_run_dcd, cmx_finish -- and, for the step after the path, cmx_final_results (finalresults!, src/results.jl:311-469)
+ * and cmx_contributions (contributions(R, SoluteGroup(...); type = :coordination_number)) evaluated on the device.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -65,7 +66,23 @@ int main(int argc, char **argv) {
            out.nbins, cutoff, hits / out.sum_weights, hits_r / out.sum_weights / cfg.n_random_samples, out.volume_total / out.sum_weights);
     printf("%lld frames, %lld kernel launches, %.1f ms on the device, %lld molecules resolved in fp64\n",
            (long long)st.frames, (long long)st.kernel_launches, st.gpu_ms_total, (long long)st.deferred);
+    /* finalresults! on the device: the mddf and the KB integral; contributions of the first half of the solute's atoms */
+    double *mddf = calloc((size_t)nbins, sizeof(double)), *kb = calloc((size_t)nbins, sizeof(double)), *d = calloc((size_t)nbins, sizeof(double));
+    cmx_final fin;
+    memset(&fin, 0, sizeof fin);
+    fin.mddf = mddf; fin.kb = kb; fin.d = d;
+    CHECK(cmx_final_results(h, 0.0, 0.0, &fin), h);
+    int bmax = 0;
+    for (int b = 1; b < fin.nbins; ++b) if (mddf[b] > mddf[bmax]) bmax = b;
+    printf("mddf peak %.3f at %.2f A, KB integral %.1f cm^3/mol, bulk density %.5f /A^3, domain volume %.1f A^3\n",
+           mddf[bmax], d[bmax], kb[fin.nbins - 1], fin.density_solvent_bulk, fin.volume_domain);
+    const int nhalf = ns / 2 > 0 ? ns / 2 : 1;
+    int32_t offsets[2] = {0, nhalf}, *rows = malloc(sizeof(int32_t) * (size_t)nhalf);
+    for (int k = 0; k < nhalf; ++k) rows[k] = k;                   /* 0-based rows of solute_group_count */
+    double *cn = calloc((size_t)nbins, sizeof(double));
+    CHECK(cmx_contributions(h, 0 /* solute */, 1 /* :coordination_number */, 0.0, 0.0, 1, offsets, rows, cn), h);
+    printf("coordination number of the first %d solute atoms at the cutoff: %.3f\n", nhalf, cn[fin.nbins - 1]);
     cmx_destroy(h); cmx_dcd_close(dcd);
-    free(sol); free(solv); free(frames); free(md); free(md_r);
+    free(sol); free(solv); free(frames); free(md); free(md_r); free(mddf); free(kb); free(d); free(rows); free(cn);
     return 0;
 }

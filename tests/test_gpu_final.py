@@ -194,3 +194,34 @@ def test_group_arrays_left_on_the_device():
     fin = R.device.final_results()
     close(fin["mddf"], Rfull.mddf, "mddf")
     R.device.close()
+
+
+def test_c_example_runs_on_the_gpu_and_agrees_with_the_python_host(tmp_path):
+    """examples/mddf_dcd.c (plain C over the ABI: cmx_run_dcd -> cmx_finish -> cmx_final_results -> cmx_contributions)
+    prints the same numbers as the Python host obtains for the same run."""
+    import os, re, subprocess
+    from common import write_dcd
+    from cmx_b200 import engine
+    from cmx_b200.engine import DcdFile, Engine
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mddf_dcd")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "mddf_dcd.c"),
+                    "-L", os.path.dirname(engine.LIB_PATH), "-lcmx_b200", "-Wl,-rpath," + os.path.dirname(engine.LIB_PATH),
+                    "-Wl,--allow-shlib-undefined", "-o", exe], check=True)
+    d = namd()
+    path = str(tmp_path / "t.dcd")
+    write_dcd(path, np.concatenate([d["protein"], d["tmao"]], axis=1), d["cells"])
+    r = subprocess.run([exe, path, "1", "1463", "1464", "2534", "14"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    peak, at, kbv = map(float, re.search(r"mddf peak ([\d.]+) at ([\d.]+) A, KB integral (-?[\d.]+)", r.stdout).groups())
+    cn = float(re.search(r"coordination number of the first 731 solute atoms at the cutoff: ([\d.]+)", r.stdout).group(1))
+    sol = cm.AtomSelection(np.arange(1, 1464), nmols=1)
+    tm = cm.AtomSelection(np.arange(1464, 1464 + 2534), natomspermol=14)
+    eng = Engine(solute=sol, solvent=tm, options=opts(bulk_range=(8.0, 10.0), n_random_samples=10), irefatom=1, autocorrelation=False)
+    f = DcdFile(path)
+    eng.run_dcd(f, sol.indices, tm.indices, [0, 1, 2], n_reader_threads=2)
+    fin = eng.final_results()
+    b = int(np.argmax(fin["mddf"]))
+    assert abs(peak - fin["mddf"][b]) < 1e-3 and abs(at - fin["d"][b]) < 1e-2 and abs(kbv - fin["kb"][-1]) < 0.1
+    assert abs(cn - eng.contributions("solute", [np.arange(731)], "coordination_number")[0, -1]) < 1e-3
+    f.close(); eng.close()
