@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--n-random-samples", type=int, default=10)
     ap.add_argument("--streams", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0, help="frames per kernel launch (0 = the library's choice)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel measurement (tuning runs only)")
     ap.add_argument("--no-hbm-kernel", action="store_true",
                     help="skip the extra measurement of the HBM-bound kernel of the path's tail (cmx_reduce_groups, 6 GB)")
     return ap.parse_args()
@@ -654,7 +655,7 @@ def main():
     if e2e is not None:
         e2e["h2d_ceiling"] = b.measure_h2d_ceiling(e2e["h2d_bytes_per_step"] / e2e["frames_per_step"])
     guard = b.guard_multi_gpu() if world > 1 else None
-    roof = b.measure_roofline(v["value"]) if rank == 0 else None
+    roof = b.measure_roofline(v["value"]) if rank == 0 and not args.no_roofline else None
     if world > 1:
         dist.barrier()
     cpu = b.measure_cpu(ncores) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None

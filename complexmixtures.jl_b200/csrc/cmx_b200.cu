@@ -197,6 +197,7 @@ struct cmx_handle {
     int num_sms = 148;
     int search_grid[2] = {148 * 5, 148 * 4};   // one resident wave of k_tile_search<false/true> (occupancy query at create)
     int search_blocks_env = 0;
+    double grid_scale = 1.0;           // experiments only (CMX_GRID_SCALE): scales the block caps of the latency-bound grid-stride kernels
     cmx_feed *feed = nullptr;
     // group handle (cmx_group.inl): one child per device; a group owns no device state of its own
     std::vector<cmx_handle *> children;
@@ -420,7 +421,7 @@ int search_phase(cmx_handle *h, const GridFrame *fd, unsigned nb, size_t max_ato
     launch_y(h, k_chain_scan<ScanTiles<RANDOM>>, (unsigned)std::min<size_t>((nqc_max + CMX_SCAN_TILE) / CMX_SCAN_TILE, sms * 2), nb, CMX_SCAN_THREADS,
              fd, h->P, ++h->scan_epoch);
     trace_mark(h, RANDOM ? "scan_tiles<rand>" : "scan_tiles<real>");
-    launch_y(h, k_qscatter<RANDOM>, (unsigned)std::min<size_t>((max_atoms + 255) / 256, (size_t)sms * 8), nb, 256u, fd, h->P);
+    launch_y(h, k_qscatter<RANDOM>, (unsigned)std::min<size_t>((max_atoms + 255) / 256, (size_t)std::max(1.0, sms * 8 * h->grid_scale)), nb, 256u, fd, h->P);
     trace_mark(h, RANDOM ? "qscatter<rand>" : "qscatter<real>");
     cudaEvent_t pe = prof_begin(h, RANDOM ? 1 : 0);
     u64 *pev = h->count_pairs ? h->d_stats.p : nullptr;
@@ -437,7 +438,7 @@ int search_phase(cmx_handle *h, const GridFrame *fd, unsigned nb, size_t max_ato
     prof_end(h, pe);
     trace_mark(h, RANDOM ? "tile_search<rand>" : "tile_search<real>");
     {   // persistent blocks (their private histograms are flushed once)
-        unsigned gfin = sms * 4;   // (measured on C4: 74 blocks 270 us per batch, 296 -> 90, 592 -> 70, 1184 -> 72; the flush is not the limit)
+        unsigned gfin = (unsigned)std::max(1.0, sms * 4 * h->grid_scale);   // (measured on C4: 74 blocks 270 us per batch, 296 -> 90, 592 -> 70, 1184 -> 72; the flush is not the limit)
         if (const char *e = std::getenv("CMX_FIN_BLOCKS")) gfin = (unsigned)std::max(1, atoi(e));   // experiments only
         k_finalise<RANDOM><<<gfin, CMX_FIN_THREADS, h->hist_smem, h->cur->stream>>>(fd, (int)nb, h->P, s0);
         h->stats.kernel_launches++;
@@ -556,7 +557,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     trace_mark(h, "scan_cells");
     launch_y(h, k_solute_bin<true>, (unsigned)((ns_apm + 127) / 128), nb, 128u, fd, ns_apm);
     trace_mark(h, "solute_bin<scatter>");
-    const unsigned gcull = (unsigned)std::min<size_t>((ncull_max + 255) / 256, (size_t)sms * 16);
+    const unsigned gcull = (unsigned)std::min<size_t>((ncull_max + 255) / 256, (size_t)std::max(1.0, sms * 16 * h->grid_scale));
     launch_y(h, k_edt_xy, gcull, nb, 256u, fd);
     trace_mark(h, "edt_xy");
     launch_y(h, k_edt_z, gcull, nb, 256u, fd);
@@ -566,7 +567,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
     trace_mark(h, "filter_real");
     if (h->stats.frames < 64 || (h->stats.frames & 15) < (int64_t)nb)   // host-side bound for the NEXT frames' cull window (monotone)
         CK(cudaMemcpyAsync(x->h_scalars + 5, x->slots[0].sc + SC_RMAX, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
-    launch_y(h, k_gen_real, (unsigned)std::min<size_t>((h->nv_atoms + 255) / 256, (size_t)sms * 4), nb, 256u, fd, h->P);
+    launch_y(h, k_gen_real, (unsigned)std::min<size_t>((h->nv_atoms + 255) / 256, (size_t)std::max(1.0, sms * 4 * h->grid_scale)), nb, 256u, fd, h->P);
     trace_mark(h, "gen_real");
     { int rc = search_phase<false>(h, fd, nb, h->nv_atoms, nqc_max, 0); if (rc) return rc; }
     launch_y(h, k_resolve<false>, std::max(16u, sms * 2 / nb), nb, (unsigned)CMX_RESOLVE_THREADS, fd, h->P, h->d_stats.p);
@@ -590,7 +591,7 @@ int flush_ctx(cmx_handle *h, FrameCtx *x) {
             h->stats.kernel_launches++;
             trace_mark(h, "filter_rand");
             const size_t max_items = (size_t)(s1 - s0) * (size_t)nv_mols;
-            launch_y(h, k_gen_rand, (unsigned)std::min<size_t>((max_items + 127) / 128, (size_t)sms * 8), nb, 128u, fd, h->P, s0);
+            launch_y(h, k_gen_rand, (unsigned)std::min<size_t>((max_items + 127) / 128, (size_t)std::max(1.0, sms * 8 * h->grid_scale)), nb, 128u, fd, h->P, s0);
     trace_mark(h, "gen_rand");
             { int rc = search_phase<true>(h, fd, nb, (size_t)(s1 - s0) * h->nv_atoms, nqc_max, s0); if (rc) return rc; }
             launch_y(h, k_resolve<true>, std::max(16u, sms * 2 / nb), nb, (unsigned)CMX_RESOLVE_THREADS, fd, h->P, h->d_stats.p);
@@ -839,6 +840,7 @@ static int create_impl(cmx_handle *h, const cmx_config *cfg) {
         h->search_grid[0] = h->num_sms * std::max(1, b0); h->search_grid[1] = h->num_sms * std::max(1, b1);
         if (const char *e = std::getenv("CMX_TRACE")) { int a = 0, b = 1; if (std::sscanf(e, "%d:%d", &a, &b) >= 1) { h->trace_skip = a; h->trace_count = b; } }
         if (const char *e = std::getenv("CMX_SEARCH_BLOCKS_PER_SM")) h->search_blocks_env = std::max(1, atoi(e));   // experiments only
+        if (const char *e = std::getenv("CMX_GRID_SCALE")) h->grid_scale = std::max(0.01, atof(e));                  // experiments only
     }
     h->nbins = std::max(1, (int)std::ceil(c.cutoff / c.binstep));   // setbin(cutoff, binstep), src/results.jl:131
     h->cut_eff = c.usecutoff ? c.cutoff : c.dbulk;                   // src/minimum_distances.jl:168
