@@ -136,7 +136,7 @@ int32_t cmx_acquire_frame_buffer(cmx_handle *h, float **solute_xyz, float **solv
 int32_t cmx_submit_frame(cmx_handle *h, int64_t frame_index, double weight, const double cell[9]);
 
 /* Same, for coordinates already resident in device memory (device pointers to fp32 xyz).  The arrays
- * must stay valid and unmodified until cmx_sync: up to n_streams frames are in flight. */
+ * must stay valid and unmodified until cmx_sync: up to n_streams batches of batch_frames frames are in flight. */
 int32_t cmx_submit_frame_device(cmx_handle *h, const float *d_solute_xyz, const float *d_solvent_xyz,
                                 int64_t frame_index, double weight, const double cell[9]);
 
@@ -154,7 +154,8 @@ int32_t cmx_counters_device(cmx_handle *h, void **device_ptr, int64_t *n_uint64)
  * cmx_finish writes it out as is.  Valid until the next submit / reset. */
 int32_t cmx_counters_device_f64(cmx_handle *h, double **device_ptr, int64_t *n_f64);
 
-/* Syncs and writes the f64 counters (buffers pre-allocated by the caller; NULL members skipped). */
+/* Syncs and writes the f64 counters (buffers pre-allocated by the caller; NULL members skipped: with all four group arrays
+ * NULL only md / rdf (+ random) are converted and copied -- the group arrays stay on the device for cmx_contributions). */
 int32_t cmx_finish(cmx_handle *h, cmx_counters *out);
 
 /* Parity hooks: system.list after minimum_distances! (src/minimum_distances.jl:147) of the LAST
