@@ -307,7 +307,11 @@ def reference_arm(args, ncores):
     return {"metric": METRIC, "value": val, "unit": "frames/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "frames_per_step": nf, "scale": args.scale, "n_random_samples": args.n_random_samples},
+            # the b200 arm's configuration (same workload, same frames per step of the GPU arm); the CPU steps are a bounded
+            # sample of it: `cpu_sample_frames_per_step` frames each, stated again in cpu_baseline.sample
+            "config": {"workload": w["desc"], "frames_per_step": w["fps"], "frames_per_step_total": w["fps"] * max(1, int(os.environ.get("WORLD_SIZE", "1"))),
+                       "scale": args.scale, "n_random_samples": args.n_random_samples, "bulk_range": [w["opt"].dbulk, w["opt"].cutoff],
+                       "cpu_sample_frames_per_step": nf},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
