@@ -524,3 +524,37 @@ def test_c_example_compiles_links_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode == 0 and "solvent molecules within" in r.stdout, r.stdout + r.stderr
     else:
         assert r.returncode == 1 and "cmx_create" in r.stderr, r.stdout + r.stderr
+
+
+def test_bench_contract_pieces_on_cpu():
+    """bench.py without a GPU: the clock summary (samples inside the timed region, nearest ones for a region shorter than
+    the sampling period, 'unavailable' without samples), the Julia probe's answer in this image, and the reference arm's
+    JSON line (contract keys; config of the GPU arm, CPU sample stated separately)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.nvml, s.proc = None, None
+    row = lambda clk, power: [str(clk), "1965.0", "Not Active", "Not Active", "Not Active", power]
+    s.samples = [(1.0, row(1200, "Not Active")), (2.0, row(1965, "Not Active")), (2.1, row(1950, "Active")), (3.0, row(300, "Not Active"))]
+    s.t0, s.t1 = 1.9, 2.2
+    out = s.summary()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    s.t0, s.t1 = 2.04, 2.05                       # shorter than the sampling period: the nearest samples are used
+    assert s.summary()["samples"] == 3
+    s.samples = []
+    assert s.summary()["reasons"] == ["unavailable"]
+    ok, why = bench.julia_probe()
+    assert isinstance(ok, bool) and isinstance(why, str) and (ok or why)
+    import argparse
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", config="C2", frames_per_step=0, scale=0.02, cpu_frames=2,
+                              n_random_samples=2)
+    line = bench.reference_arm(args, 2)
+    for k in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] in ("port", "julia") and line["cpu_baseline"]["cores"] == 2
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["config"]["workload"].startswith("C2 ") and line["config"]["cpu_sample_frames_per_step"] == 2
